@@ -1,0 +1,137 @@
+/* mrphy_b200.h -- C ABI of libmrphy_b200.so (hand-written CUDA for sm_100a).
+ *
+ * The drop-in boundary of the Bloch-simulation hot path of MRphy.py (reference v0.2.0).  The
+ * reference is pure Python/PyTorch and has no FFI; what a maintainer would bind is exactly the
+ * operator pair below, called from `mrphy/sims.py` (`BlochSim.forward/backward`, sims.py:31-269)
+ * and from `mrphy/mobjs.py` (`SpinArray.applypulse`, mobjs.py:394-450).  INTEGRATION.md shows the
+ * ctypes stub.  No torch types cross this boundary: plain device pointers, element strides and
+ * sizes.  The library never allocates or frees device memory; every buffer (outputs, checkpoints,
+ * workspaces) is owned by the caller.  All entry points are re-entrant, launch asynchronously
+ * on the given CUDA stream and return 0 or a negative mrphy_status; mrphy_last_error() gives the
+ * thread-local message.
+ *
+ * Shapes follow the reference (mrphy/__init__.py:20-47): N batch, nM spins per batch (compact),
+ * nT time steps, nC transmit coils.  `dtype` is MRPHY_F32 or MRPHY_F64 and selects the arithmetic
+ * type T of the kernel: Mi/Mo, rf, gr, loc, b1Map, gradients and workspaces are arrays of T.
+ * The per-spin / per-batch physical constants (gamma, dt, T1, T2, df) may independently be fp32
+ * or fp64 (`*_f64` flags), so the float64 0-dim defaults of the reference (mrphy/__init__.py:58-65)
+ * are consumed without a cast.  Strides are in ELEMENTS; a stride of 0 broadcasts (the reference
+ * stores T1_/T2_/gamma_ as stride-0 expands, mobjs.py:389).
+ */
+#ifndef MRPHY_B200_H
+#define MRPHY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRPHY_ABI_VERSION 1
+
+enum mrphy_dtype { MRPHY_F32 = 0, MRPHY_F64 = 1 };
+
+enum mrphy_status {
+  MRPHY_OK = 0,
+  MRPHY_ERR_ARG = -1,      /* inconsistent sizes / null pointers / unsupported option   */
+  MRPHY_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed               */
+  MRPHY_ERR_WORKSPACE = -3 /* caller-provided workspace too small                       */
+};
+
+enum mrphy_flags {
+  MRPHY_TRIG_PRECISE = 1 << 0, /* fp32 only: Newton rsqrt + polynomial sincos instead of MUFU   */
+  MRPHY_NEED_GMI = 1 << 1,     /* backward: also write dL/dMi                                   */
+  MRPHY_RF_COIL_DIM = 1 << 2,  /* rf (and its gradient) carry the trailing nCoils dimension     */
+  MRPHY_NEED_GBEFF = 1 << 3    /* explicit-field backward: also write dL/dBeff                  */
+};
+
+/* A strided per-spin scalar: element (n, i) lives at ptr[n*sn + i*sm]; f64 selects the type. */
+typedef struct mrphy_param {
+  const void* ptr; /* device pointer or NULL when the quantity is absent */
+  int64_t sn, sm;
+  int32_t f64;
+  int32_t _pad;
+} mrphy_param;
+
+/* Arguments of the fused path  rf,gr,loc,df,b1Map -> Beff -> (u,phi) -> rotate -> relax  for all
+ * nT steps, replacing  beffective.rfgr2beff (beffective.py:107-168) + sims.BlochSim.forward
+ * (sims.py:31-132)  and, for the backward entry point, sims.BlochSim.backward (sims.py:134-269)
+ * + the autograd of rfgr2beff (sum over spins -> rf.grad, gr.grad).                            */
+typedef struct mrphy_fused_args {
+  int32_t dtype;  /* mrphy_dtype */
+  int32_t flags;  /* mrphy_flags */
+  int32_t N, nM, nT;
+  int32_t nC;     /* coils of rf; with b1 == NULL the coils are summed (beffective.py:147-151) */
+  int32_t K;      /* checkpoint interval in steps (>= 1)                                       */
+  int32_t _pad;
+
+  const void* Mi; int64_t Mi_sn, Mi_sm;   /* (N,nM,3), inner stride 1                          */
+  const void* rf; int64_t rf_sn, rf_sx, rf_st, rf_sc; /* (N,2,nT[,nC])                         */
+  const void* gr; int64_t gr_sn, gr_sx, gr_st;        /* (N,3,nT)                              */
+  const void* loc; int64_t loc_sn, loc_sm;            /* (N,nM,3), inner stride 1              */
+  const void* b1; int64_t b1_sn, b1_sm;   /* (N,nM,2,nC) inner (2,nC) contiguous, or NULL      */
+  mrphy_param df;                         /* (N,nM) Hz, or ptr NULL                            */
+  mrphy_param T1, T2;                     /* (N,nM) s; both NULL = no relaxation (sims.py:68)  */
+  mrphy_param gamma;                      /* (N,nM) Hz/G                                       */
+  mrphy_param dt;                         /* (N,) s  (sm ignored)                              */
+
+  void* Mo;        /* fwd: out (N,nM,3) contiguous.  bwd: in, the forward output               */
+  void* ckpt;      /* fwd: out, bwd: in.  mrphy_fused_ckpt_elems() elements of T               */
+  void* wave;      /* scratch, mrphy_fused_wave_elems() elements of T (packed waveform)        */
+
+  /* backward only */
+  const void* gMo; int64_t gMo_sn, gMo_sm; /* dL/dMo (N,nM,3), inner stride 1                  */
+  void* gMi;       /* out (N,nM,3) contiguous when MRPHY_NEED_GMI                              */
+  void* grf;       /* out (N,2,nT[,nC]) contiguous                                             */
+  void* ggr;       /* out (N,3,nT) contiguous                                                  */
+  void* partials;  /* scratch, mrphy_fused_partial_elems() elements of T                       */
+} mrphy_fused_args;
+
+int mrphy_abi_version(void);
+const char* mrphy_last_error(void);
+
+/* Device facts the host side needs for sizing (queried once per device, cached). */
+int mrphy_device_sm_count(int device);
+
+/* Workspace sizes, in ELEMENTS of T.  They depend only on dtype, N, nM, nT, nC, K, b1 != NULL. */
+size_t mrphy_fused_ckpt_elems(const mrphy_fused_args* a);
+size_t mrphy_fused_wave_elems(const mrphy_fused_args* a);
+size_t mrphy_fused_partial_elems(const mrphy_fused_args* a);
+
+/* Forward: writes Mo and ckpt.  Launches: pack_waveform, blochsim_fused_fwd.                    */
+int mrphy_blochsim_fused_fwd(const mrphy_fused_args* a, void* cuda_stream);
+/* Backward: reads Mo, ckpt, gMo; writes grf, ggr (and gMi).  Launches: pack_waveform (unless
+ * `wave` still holds the packed waveform of the matching forward: pass wave_is_packed != 0),
+ * blochsim_fused_bwd, grad_reduce_finalize.                                                     */
+int mrphy_blochsim_fused_bwd(const mrphy_fused_args* a, int wave_is_packed, void* cuda_stream);
+
+/* Arguments of the explicit-field path: the API-faithful replacement of sims.BlochSim
+ * (sims.py:24-269) for callers that hand in a dense Beff (N,nM,nT,3), e.g. tests/test_sims.py:88
+ * upstream.  Backward returns dL/dMi and the dense dL/dBeff like the reference.                  */
+typedef struct mrphy_beff_args {
+  int32_t dtype;  /* mrphy_dtype */
+  int32_t flags;  /* MRPHY_TRIG_PRECISE | MRPHY_NEED_GMI | MRPHY_NEED_GBEFF */
+  int32_t N, nM, nT;
+  int32_t K;      /* checkpoint interval (>= 1) */
+  const void* Mi; int64_t Mi_sn, Mi_sm;          /* (N,nM,3), inner stride 1 */
+  const void* Beff; int64_t B_sn, B_sm, B_st;    /* (N,nM,nT,3), inner stride 1 */
+  mrphy_param T1, T2, gamma, dt;
+  void* Mo;        /* fwd out / bwd in, (N,nM,3) contiguous */
+  void* ckpt;      /* fwd out / bwd in, mrphy_beff_ckpt_elems() elements of T */
+  const void* gMo; int64_t gMo_sn, gMo_sm;
+  void* gMi;       /* bwd out (N,nM,3) contiguous when MRPHY_NEED_GMI */
+  void* gBeff;     /* bwd out (N,nM,nT,3) contiguous when MRPHY_NEED_GBEFF */
+} mrphy_beff_args;
+
+size_t mrphy_beff_ckpt_elems(const mrphy_beff_args* a);
+int mrphy_blochsim_beff_fwd(const mrphy_beff_args* a, void* cuda_stream);
+int mrphy_blochsim_beff_bwd(const mrphy_beff_args* a, void* cuda_stream);
+
+/* Number of kernel launches the last forward / backward call on this thread issued. */
+int mrphy_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRPHY_B200_H */

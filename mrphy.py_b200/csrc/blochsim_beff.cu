@@ -1,0 +1,245 @@
+// Explicit-field Bloch simulation for sm_100a: the API-faithful replacement of sims.BlochSim
+// (sims.py:24-269) for callers that pass a dense Beff (N,nM,nT,3).  HBM-bound: 12 B/spin.step
+// read forward; 12 B read + 12 B written backward (fp32).  Each warp owns 32 spins and moves
+// [32 spins] x [TB steps x 3] tiles between HBM and shared memory with 128-byte coalesced row
+// accesses; one thread then walks its own row (odd pitch => conflict-free).  The backward pass
+// overwrites the tile in place with dL/dBeff and streams it back out the same way.  States are
+// not stored: time-reversed reconstruction + checkpoints every K steps, as in the fused path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/mrphy_b200.h"
+#include "abi_common.cuh"
+#include "bloch_math.cuh"
+
+namespace mrphy {
+
+constexpr int EBLK = 128;
+constexpr int EWARP = EBLK / 32;
+
+template <typename T> struct ECfg {
+  static constexpr int TB = 128 / (int)sizeof(T);   // steps per tile: 32 (fp32), 16 (fp64)
+  static constexpr int PITCH = 3 * TB + 1;
+  static constexpr size_t smem = (size_t)EWARP * 32 * PITCH * sizeof(T);
+};
+
+template <typename T> struct EArgs {
+  int N, nM, nT, K, nCk;
+  const T* Mi; int64_t Mi_sn, Mi_sm;
+  const T* B; int64_t B_sn, B_sm;
+  mrphy_param T1, T2, gamma, dt;
+  T* Mo; T* ckpt;
+  const T* gMo; int64_t gMo_sn, gMo_sm;
+  T* gMi; T* gB;
+};
+
+template <typename T, bool RELAX>
+__device__ __forceinline__ void load_consts(const EArgs<T>& a, int n, int i, SpinConst<T, 1>& k, T& g) {
+  const double gam = ld_param(a.gamma, n, i), dt = ld_param(a.dt, n, 0);
+  const double t1 = RELAX ? ld_param(a.T1, n, i) : 1.0, t2 = RELAX ? ld_param(a.T2, n, i) : 1.0;
+  make_consts<T, 1>(k, gam, dt, RELAX, t1, t2, 0.0, (T)0, (T)0, (T)0, nullptr, nullptr);
+  g = (T)(6.283185307179586476925286766559 * gam * dt);   // sims.py:62
+}
+
+// warp-cooperative tile copy HBM -> smem: row r holds steps [t0, t0+len) of spin (i0 + r)
+template <typename T>
+__device__ __forceinline__ void tile_load(const T* __restrict__ B, int64_t B_sm, int i0, int nM, int t0, int len,
+                                          T* tile, int lane) {
+  constexpr int PITCH = ECfg<T>::PITCH;
+  const int cols = 3 * len;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int i = min(i0 + r, nM - 1);
+    const T* src = B + (int64_t)i * B_sm + (int64_t)t0 * 3;
+    for (int c = lane; c < cols; c += 32) tile[r * PITCH + c] = src[c];
+  }
+}
+template <typename T>
+__device__ __forceinline__ void tile_store(T* __restrict__ G, int64_t G_sm, int i0, int nM, int t0, int len,
+                                           const T* tile, int lane) {
+  constexpr int PITCH = ECfg<T>::PITCH;
+  const int cols = 3 * len;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int i = i0 + r;
+    if (i >= nM) break;
+    T* dst = G + (int64_t)i * G_sm + (int64_t)t0 * 3;
+    for (int c = lane; c < cols; c += 32) dst[c] = tile[r * PITCH + c];
+  }
+}
+
+template <typename T, int POL, bool RELAX>
+__global__ void __launch_bounds__(EBLK) beff_fwd_kernel(const EArgs<T> a) {
+  constexpr int TB = ECfg<T>::TB, PITCH = ECfg<T>::PITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
+  T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * PITCH;
+  const int nM = a.nM, nT = a.nT, K = a.K;
+  const int i0 = (blockIdx.x * EWARP + warp) * 32;
+  if (i0 >= nM) return;
+  const bool ok = i0 + lane < nM;
+  const int i = ok ? i0 + lane : nM - 1;
+  SpinConst<T, 1> k;
+  T g;
+  load_consts<T, RELAX>(a, n, i, k, g);
+  const T* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)i * a.Mi_sm;
+  T mx = mp[0], my = mp[1], mz = mp[2];
+  const T* Bn = a.B + (int64_t)n * a.B_sn;
+  const T* row = tile + lane * PITCH;
+  for (int t0 = 0; t0 < nT; t0 += TB) {
+    const int len = min(TB, nT - t0);
+    tile_load<T>(Bn, a.B_sm, i0, nM, t0, len, tile, lane);
+    __syncwarp();
+    for (int j = 0; j < len; ++j) {
+      step_fwd<T, POL, RELAX>(g * row[3 * j], g * row[3 * j + 1], g * row[3 * j + 2], k.e1, k.e2, mx, my, mz);
+      const int t1 = t0 + j + 1;
+      if (t1 % K == 0 && t1 < nT && ok) {
+        T* cp = a.ckpt + ((size_t)n * a.nCk + (t1 / K - 1)) * 3 * (size_t)nM;
+        cp[i] = mx; cp[(size_t)nM + i] = my; cp[2 * (size_t)nM + i] = mz;
+      }
+    }
+    __syncwarp();
+  }
+  if (ok) {
+    T* op = a.Mo + ((size_t)n * nM + i) * 3;
+    op[0] = mx; op[1] = my; op[2] = mz;
+  }
+}
+
+template <typename T, int POL, bool RELAX>
+__global__ void __launch_bounds__(EBLK) beff_bwd_kernel(const EArgs<T> a, const int need_gmi, const int need_gb) {
+  constexpr int TB = ECfg<T>::TB, PITCH = ECfg<T>::PITCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
+  T* tile = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * PITCH;
+  const int nM = a.nM, nT = a.nT, K = a.K;
+  const int i0 = (blockIdx.x * EWARP + warp) * 32;
+  if (i0 >= nM) return;
+  const bool ok = i0 + lane < nM;
+  const int i = ok ? i0 + lane : nM - 1;
+  SpinConst<T, 1> k;
+  T g;
+  load_consts<T, RELAX>(a, n, i, k, g);
+  const T* mp = a.Mo + ((size_t)n * nM + i) * 3;
+  T mx = mp[0], my = mp[1], mz = mp[2];
+  const T* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)i * a.gMo_sm;
+  T hx = gp[0], hy = gp[1], hz = gp[2];
+  const T* Bn = a.B + (int64_t)n * a.B_sn;
+  T* Gn = a.gB + (size_t)n * nM * (size_t)nT * 3;
+  T* row = tile + lane * PITCH;
+  const T ng = -g;
+  for (int t0 = ((nT - 1) / TB) * TB; t0 >= 0; t0 -= TB) {
+    const int len = min(TB, nT - t0);
+    tile_load<T>(Bn, a.B_sm, i0, nM, t0, len, tile, lane);
+    __syncwarp();
+    for (int j = len - 1; j >= 0; --j) {
+      T Fx, Fy, Fz;
+      step_bwd<T, POL, RELAX, 1>(k, g * row[3 * j], g * row[3 * j + 1], g * row[3 * j + 2], mx, my, mz, hx, hy, hz,
+                                 Fx, Fy, Fz);
+      row[3 * j] = ng * Fx;       // dL/dBeff = -2*pi*gamma*dt * F   (sims.py:194, 234-259)
+      row[3 * j + 1] = ng * Fy;
+      row[3 * j + 2] = ng * Fz;
+      const int t = t0 + j;
+      if (t % K == 0 && t > 0) {   // resynchronise with the forward checkpoint (state after t steps)
+        const T* cp = a.ckpt + ((size_t)n * a.nCk + (t / K - 1)) * 3 * (size_t)nM;
+        mx = cp[i]; my = cp[(size_t)nM + i]; mz = cp[2 * (size_t)nM + i];
+      }
+    }
+    __syncwarp();
+    if (need_gb) tile_store<T>(Gn, (int64_t)nT * 3, i0, nM, t0, len, tile, lane);
+    __syncwarp();
+  }
+  if (need_gmi && ok) {
+    T* op = a.gMi + ((size_t)n * nM + i) * 3;
+    op[0] = hx; op[1] = hy; op[2] = hz;
+  }
+}
+
+}  // namespace mrphy
+
+using namespace mrphy;
+
+namespace {
+
+int check_beff(const mrphy_beff_args* a, bool bwd) {
+  if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
+  if (a->dtype != MRPHY_F32 && a->dtype != MRPHY_F64) return fail(MRPHY_ERR_ARG, "dtype must be MRPHY_F32 or MRPHY_F64%s");
+  if (a->N < 1 || a->nM < 1 || a->nT < 1 || a->N > 65535) return fail(MRPHY_ERR_ARG, "need 1 <= N <= 65535, nM >= 1, nT >= 1%s");
+  if (a->K < 1) return fail(MRPHY_ERR_ARG, "checkpoint interval K must be >= 1%s");
+  if (!a->Beff || !a->gamma.ptr || !a->dt.ptr || !a->Mo || !a->ckpt) return fail(MRPHY_ERR_ARG, "Beff, gamma, dt, Mo, ckpt are required%s");
+  if ((a->T1.ptr == nullptr) != (a->T2.ptr == nullptr)) return fail(MRPHY_ERR_ARG, "T1 and T2: both or neither (sims.py:68)%s");
+  if (a->B_st != 3) return fail(MRPHY_ERR_ARG, "Beff must be contiguous over (nT, xyz)%s");
+  if (!bwd && !a->Mi) return fail(MRPHY_ERR_ARG, "Mi is null%s");
+  if (bwd && !a->gMo) return fail(MRPHY_ERR_ARG, "gMo is null%s");
+  if (bwd && (a->flags & MRPHY_NEED_GMI) && !a->gMi) return fail(MRPHY_ERR_ARG, "gMi is null but MRPHY_NEED_GMI is set%s");
+  if (bwd && (a->flags & MRPHY_NEED_GBEFF) && !a->gBeff) return fail(MRPHY_ERR_ARG, "gBeff is null but MRPHY_NEED_GBEFF is set%s");
+  return MRPHY_OK;
+}
+
+template <typename T>
+EArgs<T> make_eargs(const mrphy_beff_args* a) {
+  EArgs<T> e;
+  memset(&e, 0, sizeof(e));
+  e.N = a->N; e.nM = a->nM; e.nT = a->nT; e.K = a->K; e.nCk = (a->nT - 1) / a->K;
+  e.Mi = (const T*)a->Mi; e.Mi_sn = a->Mi_sn; e.Mi_sm = a->Mi_sm;
+  e.B = (const T*)a->Beff; e.B_sn = a->B_sn; e.B_sm = a->B_sm;
+  e.T1 = a->T1; e.T2 = a->T2; e.gamma = a->gamma; e.dt = a->dt;
+  e.Mo = (T*)a->Mo; e.ckpt = (T*)a->ckpt;
+  e.gMo = (const T*)a->gMo; e.gMo_sn = a->gMo_sn; e.gMo_sm = a->gMo_sm;
+  e.gMi = (T*)a->gMi; e.gB = (T*)a->gBeff;
+  return e;
+}
+
+template <typename T, int POL, bool RELAX>
+int launch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
+  const EArgs<T> e = make_eargs<T>(a);
+  dim3 grid((a->nM + EBLK - 1) / EBLK, a->N);
+  constexpr size_t smem = ECfg<T>::smem;
+  if (bwd) {
+    auto kern = beff_bwd_kernel<T, POL, RELAX>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, EBLK, smem, st>>>(e, (a->flags & MRPHY_NEED_GMI) ? 1 : 0, (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0);
+  } else {
+    auto kern = beff_fwd_kernel<T, POL, RELAX>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, EBLK, smem, st>>>(e);
+  }
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+template <typename T>
+int dispatch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
+  const bool relax = a->T1.ptr != nullptr;
+  const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0 && sizeof(T) == 4;
+  if (precise) return relax ? launch_e<T, TRIG_PRECISE, true>(bwd, a, st) : launch_e<T, TRIG_PRECISE, false>(bwd, a, st);
+  return relax ? launch_e<T, TRIG_FAST, true>(bwd, a, st) : launch_e<T, TRIG_FAST, false>(bwd, a, st);
+}
+
+}  // namespace
+
+extern "C" size_t mrphy_beff_ckpt_elems(const mrphy_beff_args* a) {
+  if (!a || a->K < 1 || a->nT < 1) return 0;
+  const size_t n = (size_t)a->N * (size_t)((a->nT - 1) / a->K) * 3 * (size_t)a->nM;
+  return n ? n : 1;
+}
+
+extern "C" int mrphy_blochsim_beff_fwd(const mrphy_beff_args* a, void* cuda_stream) {
+  launch_count() = 0;
+  err_buf()[0] = 0;
+  int rc = check_beff(a, false);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return a->dtype == MRPHY_F64 ? dispatch_e<double>(false, a, st) : dispatch_e<float>(false, a, st);
+}
+
+extern "C" int mrphy_blochsim_beff_bwd(const mrphy_beff_args* a, void* cuda_stream) {
+  launch_count() = 0;
+  err_buf()[0] = 0;
+  int rc = check_beff(a, true);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return a->dtype == MRPHY_F64 ? dispatch_e<double>(true, a, st) : dispatch_e<float>(true, a, st);
+}

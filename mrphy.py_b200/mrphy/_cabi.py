@@ -1,0 +1,105 @@
+"""ctypes binding of libmrphy_b200.so (C ABI declared in include/mrphy_b200.h).
+
+No torch types cross this boundary: tensors are passed as ``data_ptr()`` + element strides, the
+stream as ``torch.cuda.current_stream().cuda_stream``.  The library is loaded lazily; if it is
+missing the hot path raises -- there is no other implementation to fall back to.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libmrphy_b200.so')
+
+MRPHY_F32, MRPHY_F64 = 0, 1
+FLAG_TRIG_PRECISE, FLAG_NEED_GMI, FLAG_RF_COIL_DIM, FLAG_NEED_GBEFF = 1, 2, 4, 8
+ABI_VERSION = 1
+
+c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+
+class Param(ctypes.Structure):
+    _fields_ = [('ptr', c_vp), ('sn', c_i64), ('sm', c_i64), ('f64', c_i32), ('_pad', c_i32)]
+
+
+class FusedArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('nC', c_i32),
+        ('K', c_i32), ('_pad', c_i32),
+        ('Mi', c_vp), ('Mi_sn', c_i64), ('Mi_sm', c_i64),
+        ('rf', c_vp), ('rf_sn', c_i64), ('rf_sx', c_i64), ('rf_st', c_i64), ('rf_sc', c_i64),
+        ('gr', c_vp), ('gr_sn', c_i64), ('gr_sx', c_i64), ('gr_st', c_i64),
+        ('loc', c_vp), ('loc_sn', c_i64), ('loc_sm', c_i64),
+        ('b1', c_vp), ('b1_sn', c_i64), ('b1_sm', c_i64),
+        ('df', Param), ('T1', Param), ('T2', Param), ('gamma', Param), ('dt', Param),
+        ('Mo', c_vp), ('ckpt', c_vp), ('wave', c_vp),
+        ('gMo', c_vp), ('gMo_sn', c_i64), ('gMo_sm', c_i64),
+        ('gMi', c_vp), ('grf', c_vp), ('ggr', c_vp), ('partials', c_vp),
+    ]
+
+
+class BeffArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('K', c_i32),
+        ('Mi', c_vp), ('Mi_sn', c_i64), ('Mi_sm', c_i64),
+        ('Beff', c_vp), ('B_sn', c_i64), ('B_sm', c_i64), ('B_st', c_i64),
+        ('T1', Param), ('T2', Param), ('gamma', Param), ('dt', Param),
+        ('Mo', c_vp), ('ckpt', c_vp),
+        ('gMo', c_vp), ('gMo_sn', c_i64), ('gMo_sm', c_i64),
+        ('gMi', c_vp), ('gBeff', c_vp),
+    ]
+
+
+EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mrphy_b200.h declares
+    'mrphy_abi_version': (ctypes.c_int, []),
+    'mrphy_last_error': (ctypes.c_char_p, []),
+    'mrphy_last_launch_count': (ctypes.c_int, []),
+    'mrphy_device_sm_count': (ctypes.c_int, [ctypes.c_int]),
+    'mrphy_fused_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),
+    'mrphy_fused_wave_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),
+    'mrphy_fused_partial_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),
+    'mrphy_blochsim_fused_fwd': (ctypes.c_int, [ctypes.POINTER(FusedArgs), c_vp]),
+    'mrphy_blochsim_fused_bwd': (ctypes.c_int, [ctypes.POINTER(FusedArgs), ctypes.c_int, c_vp]),
+    'mrphy_beff_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(BeffArgs)]),
+    'mrphy_blochsim_beff_fwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
+    'mrphy_blochsim_beff_bwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """The loaded library; raises RuntimeError (never falls back) when it is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f'mrphy (B200): {LIB_PATH} is not built. Run `python mrphy.py_b200/build.py` '
+                        '(nvcc, sm_100a). There is no CPU or PyTorch fallback for the Bloch-simulation path.')
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in EXPORTS.items():
+                    fn = getattr(L, name)
+                    fn.restype, fn.argtypes = res, args
+                if L.mrphy_abi_version() != ABI_VERSION:
+                    raise RuntimeError(f'mrphy (B200): ABI version mismatch: library {L.mrphy_abi_version()} '
+                                       f'!= binding {ABI_VERSION}; rebuild with mrphy.py_b200/build.py')
+                _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mrphy_last_error().decode(errors='replace')
+        raise RuntimeError(f'mrphy (B200): {what} failed with status {rc}: {msg}')
+
+
+# launches issued by this process through the C ABI (bench.py reports it as gpu_launches)
+launch_counter = 0
+
+
+def count_launches():
+    global launch_counter
+    launch_counter += lib().mrphy_last_launch_count()

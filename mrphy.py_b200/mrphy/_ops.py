@@ -1,0 +1,322 @@
+"""torch.library custom ops over the C ABI (the only place tensors meet libmrphy_b200.so).
+
+``mrphy_b200::blochsim_fused_fwd / _bwd`` implement, in one kernel each, what the reference does
+with ``beffective.rfgr2beff`` (beffective.py:107-168) followed by ``sims.BlochSim.forward`` /
+``.backward`` (sims.py:31-269) and the autograd of ``rfgr2beff``.  ``fused_applypulse`` is the
+Python-level entry used by ``mobjs.SpinArray.applypulse`` (mobjs.py:394-450).
+"""
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from mrphy import _cabi
+
+_F = (torch.float32, torch.float64)
+K_MAX = 64                  # checkpoint interval cap == staged chunk length (csrc: TCMAX)
+_AMPLIFY_BUDGET = 0.4       # resync before exp(K*dt/T2) exceeds e^0.4 ~ 1.5 (time-reversed states)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('mrphy (B200): the Bloch-simulation path is CUDA-only (sm_100a); got a '
+                               f'{t.device} tensor. There is no CPU fallback.')
+
+
+def _param(t: Optional[Tensor], N: int, nM: int, per_batch_only=False) -> _cabi.Param:
+    """(N|1, nM|1) (or any shape broadcastable to it) -> pointer + element strides, no copy."""
+    p = _cabi.Param()
+    if t is None:
+        return p
+    if t.dtype not in _F:
+        raise TypeError(f'mrphy (B200): float32/float64 expected, got {t.dtype}')
+    v = t
+    while v.ndim > 2 and v.shape[-1] == 1:   # (N,nM,1,1) style tails from sims.blochsim
+        v = v[..., 0]
+    if per_batch_only:
+        v = v.reshape(-1)
+        assert v.numel() in (1, N), 'dt must be () or (N|1,)'
+        p.ptr, p.sn, p.sm = v.data_ptr(), (v.stride(0) if v.numel() == N and N > 1 else 0), 0
+    else:
+        while v.ndim < 2:
+            v = v[None] if v.ndim == 0 else v[:, None]
+        assert v.ndim == 2 and v.shape[0] in (1, N) and v.shape[1] in (1, nM), \
+            f'per-spin constant of shape {tuple(t.shape)} does not broadcast to ({N},{nM})'
+        p.ptr = v.data_ptr()
+        p.sn = v.stride(0) if v.shape[0] == N and N > 1 else 0
+        p.sm = v.stride(1) if v.shape[1] == nM and nM > 1 else 0
+    p.f64 = int(v.dtype == torch.float64)
+    return p
+
+
+def _inner_contig(t: Tensor, inner: int) -> Tensor:
+    """Make the trailing `inner` dims densely packed (leading strides stay free)."""
+    exp = 1
+    for d in range(t.ndim - 1, t.ndim - 1 - inner, -1):
+        if t.shape[d] != 1 and t.stride(d) != exp:
+            return t.contiguous()
+        exp *= t.shape[d]
+    return t
+
+
+def _bstride(t: Tensor, d: int) -> int:
+    return t.stride(d) if t.shape[d] > 1 else 0
+
+
+def _fill_common(a, Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
+    N, nM = loc.shape[0], loc.shape[1]
+    a.dtype = _cabi.MRPHY_F64 if loc.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.N, a.nM, a.nT = N, nM, rf.shape[2]
+    a.nC = rf.shape[3] if rf.ndim == 4 else 1
+    a.K = K
+    a.flags = flags | (_cabi.FLAG_RF_COIL_DIM if rf.ndim == 4 else 0)
+    if Mi is not None:
+        a.Mi, a.Mi_sn, a.Mi_sm = Mi.data_ptr(), _bstride(Mi, 0), _bstride(Mi, 1)
+    a.rf, a.rf_sn, a.rf_sx, a.rf_st = rf.data_ptr(), _bstride(rf, 0), rf.stride(1), rf.stride(2)
+    a.rf_sc = rf.stride(3) if rf.ndim == 4 else 0
+    a.gr, a.gr_sn, a.gr_sx, a.gr_st = gr.data_ptr(), _bstride(gr, 0), gr.stride(1), gr.stride(2)
+    a.loc, a.loc_sn, a.loc_sm = loc.data_ptr(), _bstride(loc, 0), _bstride(loc, 1)
+    if b1 is not None:
+        a.b1, a.b1_sn, a.b1_sm = b1.data_ptr(), _bstride(b1, 0), _bstride(b1, 1)
+    a.df = _param(df, N, nM)
+    a.T1, a.T2 = _param(T1, N, nM), _param(T2, N, nM)
+    a.gamma = _param(gamma, N, nM)
+    a.dt = _param(dt, N, nM, per_batch_only=True)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@torch.library.custom_op('mrphy_b200::blochsim_fused_fwd', mutates_args=(), device_types='cuda')
+def blochsim_fused_fwd(Mi: Tensor, rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b1: Optional[Tensor],
+                       T1: Optional[Tensor], T2: Optional[Tensor], gamma: Tensor, dt: Tensor, K: int,
+                       flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (Mo (N,nM,3), ckpt, wave): final magnetisation, K-step checkpoints, packed waveform."""
+    L = _cabi.lib()
+    a = _cabi.FusedArgs()
+    _fill_common(a, Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
+    kw = {'dtype': Mi.dtype, 'device': Mi.device}
+    Mo = torch.empty((a.N, a.nM, 3), **kw)
+    ckpt = torch.empty(L.mrphy_fused_ckpt_elems(a), **kw)
+    wave = torch.empty(L.mrphy_fused_wave_elems(a), **kw)
+    a.Mo, a.ckpt, a.wave = Mo.data_ptr(), ckpt.data_ptr(), wave.data_ptr()
+    with torch.cuda.device(Mi.device):
+        _cabi.check(L.mrphy_blochsim_fused_fwd(a, _stream()), 'blochsim_fused_fwd')
+    _cabi.count_launches()
+    return Mo, ckpt, wave
+
+
+@blochsim_fused_fwd.register_fake
+def _(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
+    N, nM, nT = loc.shape[0], loc.shape[1], rf.shape[2]
+    nck = max((nT + K - 1) // K - 1, 0)
+    return (Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * nck * 3 * nM, 1),)),
+            Mi.new_empty((N * ((nT + K - 1) // K) * 5 * ((K + 3) // 4 * 4),)))
+
+
+@torch.library.custom_op('mrphy_b200::blochsim_fused_bwd', mutates_args=(), device_types='cuda')
+def blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
+                       df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
+                       gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (gMi (N,nM,3) or empty, grf like rf, ggr (N,3,nT))."""
+    L = _cabi.lib()
+    a = _cabi.FusedArgs()
+    _fill_common(a, None, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
+    kw = {'dtype': Mo.dtype, 'device': Mo.device}
+    need_gmi = bool(flags & _cabi.FLAG_NEED_GMI)
+    gMi = torch.empty((a.N, a.nM, 3) if need_gmi else (0,), **kw)
+    grf = torch.empty(rf.shape, **kw)
+    ggr = torch.empty((a.N, 3, a.nT), **kw)
+    partials = torch.empty(L.mrphy_fused_partial_elems(a), **kw)
+    a.Mo, a.ckpt, a.wave = Mo.data_ptr(), ckpt.data_ptr(), wave.data_ptr()
+    a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
+    a.gMi, a.grf, a.ggr, a.partials = (gMi.data_ptr() if need_gmi else None), grf.data_ptr(), ggr.data_ptr(), \
+        partials.data_ptr()
+    with torch.cuda.device(Mo.device):
+        _cabi.check(L.mrphy_blochsim_fused_bwd(a, 1, _stream()), 'blochsim_fused_bwd')
+    _cabi.count_launches()
+    return gMi, grf, ggr
+
+
+@blochsim_fused_bwd.register_fake
+def _(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
+    return (Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)), Mo.new_empty(rf.shape),
+            Mo.new_empty((rf.shape[0], 3, rf.shape[2])))
+
+
+def _fused_setup(ctx, inputs, output):
+    Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags = inputs
+    Mo, ckpt, wave = output
+    ctx.K, ctx.flags = K, flags
+    ctx.has = [x is not None for x in (df, b1, T1, T2)]
+    ctx.save_for_backward(Mo, ckpt, wave, rf, gr, loc, gamma, dt, *[x for x in (df, b1, T1, T2) if x is not None])
+
+
+def _fused_backward(ctx, gMo, _gckpt, _gwave):
+    Mo, ckpt, wave, rf, gr, loc, gamma, dt, *opt = ctx.saved_tensors
+    opt = list(opt)
+    df, b1, T1, T2 = (opt.pop(0) if h else None for h in ctx.has)
+    need = ctx.needs_input_grad
+    if not any(need[0:3]):
+        return (None,) * 12
+    if gMo is None:
+        gMo = torch.zeros_like(Mo)
+    if gMo.stride(-1) != 1 or gMo.dtype != Mo.dtype:
+        gMo = gMo.to(Mo.dtype).contiguous()
+    flags = ctx.flags | (_cabi.FLAG_NEED_GMI if need[0] else 0)
+    gMi, grf, ggr = blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags)
+    return (gMi if need[0] else None, grf if need[1] else None, ggr if need[2] else None) + (None,) * 9
+
+
+torch.library.register_autograd('mrphy_b200::blochsim_fused_fwd', _fused_backward, setup_context=_fused_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# explicit-field ops: sims.BlochSim.forward / backward on a dense Beff (sims.py:31-269)
+def _fill_beff(a, Mi, Beff, T1, T2, gamma, dt, K, flags):
+    N, nM, nT = Beff.shape[0], Beff.shape[1], Beff.shape[2]
+    a.dtype = _cabi.MRPHY_F64 if Beff.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.flags, a.N, a.nM, a.nT, a.K = flags, N, nM, nT, K
+    if Mi is not None:
+        a.Mi, a.Mi_sn, a.Mi_sm = Mi.data_ptr(), _bstride(Mi, 0), _bstride(Mi, 1)
+    a.Beff, a.B_sn, a.B_sm, a.B_st = Beff.data_ptr(), _bstride(Beff, 0), _bstride(Beff, 1), 3
+    a.T1, a.T2 = _param(T1, N, nM), _param(T2, N, nM)
+    a.gamma = _param(gamma, N, nM)
+    a.dt = _param(dt, N, nM, per_batch_only=True)
+
+
+@torch.library.custom_op('mrphy_b200::blochsim_beff_fwd', mutates_args=(), device_types='cuda')
+def blochsim_beff_fwd(Mi: Tensor, Beff: Tensor, T1: Optional[Tensor], T2: Optional[Tensor], gamma: Tensor,
+                      dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
+    """Mi (N,nM,3), Beff (N,nM,nT,3) -> (Mo (N,nM,3), ckpt)."""
+    L = _cabi.lib()
+    a = _cabi.BeffArgs()
+    _fill_beff(a, Mi, Beff, T1, T2, gamma, dt, K, flags)
+    kw = {'dtype': Mi.dtype, 'device': Mi.device}
+    Mo = torch.empty((a.N, a.nM, 3), **kw)
+    ckpt = torch.empty(L.mrphy_beff_ckpt_elems(a), **kw)
+    a.Mo, a.ckpt = Mo.data_ptr(), ckpt.data_ptr()
+    with torch.cuda.device(Mi.device):
+        _cabi.check(L.mrphy_blochsim_beff_fwd(a, _stream()), 'blochsim_beff_fwd')
+    _cabi.count_launches()
+    return Mo, ckpt
+
+
+@blochsim_beff_fwd.register_fake
+def _(Mi, Beff, T1, T2, gamma, dt, K, flags):
+    N, nM, nT = Beff.shape[0], Beff.shape[1], Beff.shape[2]
+    return Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * ((nT - 1) // K) * 3 * nM, 1),))
+
+
+@torch.library.custom_op('mrphy_b200::blochsim_beff_bwd', mutates_args=(), device_types='cuda')
+def blochsim_beff_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, Beff: Tensor, T1: Optional[Tensor],
+                      T2: Optional[Tensor], gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
+    """-> (gMi (N,nM,3) or empty, gBeff (N,nM,nT,3) or empty)."""
+    L = _cabi.lib()
+    a = _cabi.BeffArgs()
+    _fill_beff(a, None, Beff, T1, T2, gamma, dt, K, flags)
+    kw = {'dtype': Mo.dtype, 'device': Mo.device}
+    need_gmi, need_gb = bool(flags & _cabi.FLAG_NEED_GMI), bool(flags & _cabi.FLAG_NEED_GBEFF)
+    gMi = torch.empty((a.N, a.nM, 3) if need_gmi else (0,), **kw)
+    gB = torch.empty((a.N, a.nM, a.nT, 3) if need_gb else (0,), **kw)
+    a.Mo, a.ckpt = Mo.data_ptr(), ckpt.data_ptr()
+    a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
+    a.gMi = gMi.data_ptr() if need_gmi else None
+    a.gBeff = gB.data_ptr() if need_gb else None
+    with torch.cuda.device(Mo.device):
+        _cabi.check(L.mrphy_blochsim_beff_bwd(a, _stream()), 'blochsim_beff_bwd')
+    _cabi.count_launches()
+    return gMi, gB
+
+
+@blochsim_beff_bwd.register_fake
+def _(gMo, Mo, ckpt, Beff, T1, T2, gamma, dt, K, flags):
+    return (Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)),
+            Mo.new_empty(Beff.shape if flags & _cabi.FLAG_NEED_GBEFF else (0,)))
+
+
+def beff_ckpt_interval(K: int) -> int:
+    """The explicit-field kernels take K in {1..32} or 64 (tile-aligned)."""
+    return K if K <= 32 else (64 if K >= 64 else 32)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side policy: checkpoint interval from the conditioning of the inverse relaxation
+_ratio_cache = {}
+
+
+def _collapse(x: Tensor) -> Tensor:
+    """Drop stride-0 (expanded) dims so a reduction touches each stored element once."""
+    for d in range(x.ndim):
+        if x.shape[d] > 1 and x.stride(d) == 0:
+            x = x.select(d, 0).unsqueeze(d)
+    return x
+
+
+def _tensor_key(t: Tensor):
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype)
+
+
+def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -> int:
+    """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at K_MAX.  One device->host read per distinct
+    (dt, T1, T2) storage/version, cached afterwards (keeps applypulse asynchronous in a design loop)."""
+    env = os.environ.get('MRPHY_B200_CKPT')
+    if env:
+        return max(1, min(K_MAX, int(env)))
+    if T1 is None:
+        return K_MAX
+    key = (_tensor_key(dt), _tensor_key(T1), _tensor_key(T2))
+    K = _ratio_cache.get(key)
+    if K is None:
+        with torch.no_grad():
+            tmin = torch.minimum(_collapse(T1).min(), _collapse(T2).min()).double()
+            r = float((dt.max().double() / tmin).item())
+        K = K_MAX if not (r > 0) else int(max(1, min(K_MAX, _AMPLIFY_BUDGET / r)))
+        if K >= 16:
+            K -= K % 16
+        if len(_ratio_cache) > 256:
+            _ratio_cache.clear()
+        _ratio_cache[key] = K
+    return K
+
+
+def default_flags() -> int:
+    return _cabi.FLAG_TRIG_PRECISE if os.environ.get('MRPHY_B200_TRIG', 'fast') == 'precise' else 0
+
+
+def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: Optional[Tensor] = None,
+                     b1Map_: Optional[Tensor] = None, T1_: Optional[Tensor] = None, T2_: Optional[Tensor] = None,
+                     γ_: Tensor, dt: Tensor, ckpt: Optional[int] = None, flags: Optional[int] = None) -> Tensor:
+    """Fused waveform -> magnetisation op on compact arrays; differentiable wrt ``M_``, ``rf``, ``gr``.
+
+    ``M_`` (N,nM,3), ``rf`` (N,2,nT[,nCoils]), ``gr`` (N,3,nT), ``loc_`` (N,nM,3), ``Δf_`` (N,nM),
+    ``b1Map_`` (N,nM,2[,nCoils]), ``T1_/T2_/γ_`` broadcastable to (N,nM), ``dt`` () or (N|1,).
+    """
+    _require_cuda(M_, rf, gr, loc_, Δf_, b1Map_, T1_, T2_)
+    dtype, dev = M_.dtype, M_.device
+    if dtype not in _F:
+        raise TypeError(f'mrphy (B200): M must be float32 or float64, got {dtype}')
+    assert (T1_ is None) == (T2_ is None)      # both or neither (sims.py:68)
+    N, nM = loc_.shape[0], loc_.shape[1]
+    assert M_.shape == (N, nM, 3) and loc_.shape == (N, nM, 3)
+    assert rf.shape[0] == N and rf.shape[1] == 2 and gr.shape == (N, 3, rf.shape[2])
+    cast = lambda x: None if x is None else x.to(device=dev, dtype=dtype)
+    move = lambda x: None if x is None else (x.to(device=dev) if x.dtype in _F else x.to(device=dev, dtype=dtype))
+    rf, gr = cast(rf), cast(gr)
+    Mi = _inner_contig(cast(M_), 1)
+    loc = _inner_contig(cast(loc_), 1)
+    b1 = cast(b1Map_)
+    if b1 is not None:
+        if b1.ndim == 3:
+            b1 = b1[..., None]
+        nC = rf.shape[3] if rf.ndim == 4 else 1
+        assert b1.shape[2] == 2 and b1.shape[3] == nC, 'b1Map and rf disagree on nCoils'
+        b1 = _inner_contig(b1.expand(N, nM, 2, nC) if b1.shape[:2] != (N, nM) else b1, 2)
+    df, T1, T2, gam, dtt = (move(x) for x in (Δf_, T1_, T2_, γ_, dt))
+    K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2)
+    fl = default_flags() if flags is None else flags
+    Mo, _, _ = blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gam, dtt, K, fl)
+    return Mo

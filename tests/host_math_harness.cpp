@@ -1,0 +1,71 @@
+// Host-side check of csrc/bloch_math.cuh (TEST INFRASTRUCTURE).  Compiles the very same step
+// functions the CUDA kernels inline, runs them spin by spin on the CPU with the kernels' loop
+// structure (checkpoint every K steps, time-reversed state reconstruction in the backward
+// sweep), so tests can compare the formulation with the oracle without a GPU.
+#include <vector>
+#include <cstring>
+#include "../mrphy.py_b200/csrc/bloch_math.cuh"
+
+using namespace mrphy;
+
+template <typename T, int POL, bool RELAX>
+static void run(int nM, int nT, int K, const T* M0, const T* rf /*[2][nT]*/, const T* gr /*[3][nT]*/,
+                const T* loc, const T* b1 /*[nM][2] or null*/, const double* df, const double* T1, const double* T2,
+                const double* gamma, double dt, const T* gMo, T* Mo, T* gM0, double* grf, double* ggr, T* resync_err) {
+  for (int t = 0; t < nT; ++t) { grf[t] = grf[nT + t] = 0; ggr[t] = ggr[nT + t] = ggr[2 * nT + t] = 0; }
+  T maxerr = 0;
+  for (int i = 0; i < nM; ++i) {
+    SpinConst<T, 1> k;
+    T br = b1 ? b1[2 * i] : (T)1, bi = b1 ? b1[2 * i + 1] : (T)0;
+    make_consts<T, 1>(k, gamma[i], dt, RELAX, RELAX ? T1[i] : 1.0, RELAX ? T2[i] : 1.0, df ? df[i] : 0.0,
+                      loc[3 * i], loc[3 * i + 1], loc[3 * i + 2], &br, &bi);
+    T mx = M0[3 * i], my = M0[3 * i + 1], mz = M0[3 * i + 2];
+    std::vector<T> ck;
+    for (int t = 0; t < nT; ++t) {
+      if (t > 0 && t % K == 0) { ck.push_back(mx); ck.push_back(my); ck.push_back(mz); }
+      T bx, by, bz;
+      field<T, 1>(k, &rf[t], &rf[nT + t], gr[t], gr[nT + t], gr[2 * nT + t], bx, by, bz);
+      step_fwd<T, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
+    }
+    Mo[3 * i] = mx; Mo[3 * i + 1] = my; Mo[3 * i + 2] = mz;
+    T hx = gMo[3 * i], hy = gMo[3 * i + 1], hz = gMo[3 * i + 2];
+    for (int t = nT - 1; t >= 0; --t) {
+      T bx, by, bz, Fx, Fy, Fz;
+      field<T, 1>(k, &rf[t], &rf[nT + t], gr[t], gr[nT + t], gr[2 * nT + t], bx, by, bz);
+      step_bwd<T, POL, RELAX, 1>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+      grf[t] -= (double)(k.cbr[0] * Fx + k.cbi[0] * Fy);
+      grf[nT + t] -= (double)(k.cbr[0] * Fy - k.cbi[0] * Fx);
+      ggr[t] -= (double)(k.glx * Fz);
+      ggr[nT + t] -= (double)(k.gly * Fz);
+      ggr[2 * nT + t] -= (double)(k.glz * Fz);
+      if (t > 0 && t % K == 0) {
+        int c = t / K - 1;
+        T ex = fabs(mx - ck[3 * c]), ey = fabs(my - ck[3 * c + 1]), ez = fabs(mz - ck[3 * c + 2]);
+        T e = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
+        if (e > maxerr) maxerr = e;
+        mx = ck[3 * c]; my = ck[3 * c + 1]; mz = ck[3 * c + 2];
+      }
+    }
+    gM0[3 * i] = hx; gM0[3 * i + 1] = hy; gM0[3 * i + 2] = hz;
+  }
+  *resync_err = maxerr;
+}
+
+#define ARGS(T) int nM, int nT, int K, const T* M0, const T* rf, const T* gr, const T* loc, const T* b1, \
+  const double* df, const double* T1, const double* T2, const double* gamma, double dt, const T* gMo, T* Mo, T* gM0, \
+  double* grf, double* ggr, T* resync_err
+#define PASS nM, nT, K, M0, rf, gr, loc, b1, df, T1, T2, gamma, dt, gMo, Mo, gM0, grf, ggr, resync_err
+
+extern "C" void host_sim_f32(int pol, int relax, ARGS(float)) {
+  if (pol == 0) { if (relax) run<float, 0, true>(PASS); else run<float, 0, false>(PASS); }
+  else          { if (relax) run<float, 1, true>(PASS); else run<float, 1, false>(PASS); }
+}
+extern "C" void host_sim_f64(int pol, int relax, ARGS(double)) {
+  if (relax) run<double, 0, true>(PASS); else run<double, 0, false>(PASS);
+}
+extern "C" void host_sincos_f32(int n, const float* x, float* s, float* c) {
+  for (int i = 0; i < n; ++i) Fn<float, TRIG_PRECISE>::sc(x[i], s[i], c[i]);
+}
+extern "C" void host_rsq_f32(int n, const float* x, float* r) {
+  for (int i = 0; i < n; ++i) r[i] = Fn<float, TRIG_PRECISE>::rsq(x[i]);
+}
