@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- spin·steps/s of the fused Bloch simulation, forward + adjoint backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+                    [--dtype f32|f64]
+
+One "step" = one pass of the hot path over one batch of synthetic input (BASELINE.md / SURVEY.md 8d):
+``M = cube.applypulse(pulse, b1Map_=...)``; ``loss = ((M - target)**2).sum()``; ``loss.backward()`` giving
+``pulse.rf.grad``, ``pulse.gr.grad`` (+ one NCCL all-reduce of the waveform gradient when N > 1).
+Default workload at N=1 is BASELINE config C2: SpinCube 64^3 (262 144 spins), nT=1000, dt=4us, fp32.
+With N GPUs every rank owns one such slab of a (64*N) x 64 x 64 cube (weak scaling; waveform replicated).
+
+Prints ONE JSON line (rank 0).  ``value`` is measured with inputs resident in HBM (CUDA events around each
+step, L2 flushed between steps); ``e2e`` goes through the same public API but copies every input from
+pinned host memory and reads the loss and gradients back, inside the timed region.
+``--impl reference`` times the CPU port of the reference's algorithm (oracle/bloch_oracle.py: torch CPU ops,
+one handful per time step like the reference) on the host cores -- the reference itself is Python and cannot
+travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'mrphy.py_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'spin_steps_per_sec_fwd_bwd'
+UNIT = 'spin·steps/s'
+FLOP_PER_SPIN_STEP = 223.0        # fwd 62 + bwd 161 algorithmic flop (fp32, 1 coil, relax, b1, df)
+FLOP_FWD, FLOP_BWD = 62.0, 161.0
+WORKLOADS = {   # name: (N, n, nT)
+    'c2': (1, 64, 1000), 'c3': (1, 128, 2000), 'c4': (64, 40, 1000), 'small': (1, 16, 200),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            mp = json.load(f)
+        return float(mp['hbm_gbs']), float(mp['sm_max_mhz']), 'measured'
+    except Exception:
+        return 6650.0, 1965.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mxs = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == 'active'})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mxs) if mxs else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def synth(N, n_x, n, nT, dtype, seed=0, x_off=0, n_x_total=None):
+    """Seeded synthetic slab (SURVEY 8d distributions), generated in fp64 then rounded to `dtype`.
+    Slab = x-indices [x_off, x_off+n_x) of a (n_x_total, n, n) grid with 24 cm fov per 64 voxels."""
+    n_x_total = n_x if n_x_total is None else n_x_total
+    gen = torch.Generator().manual_seed(seed + 1000 * x_off)
+    U = lambda *s: torch.rand(s, generator=gen, dtype=torch.float64) * 2 - 1
+    fov = torch.tensor([24.0 * n_x_total / n, 24.0, 24.0], dtype=torch.float64)
+    ax = [(torch.arange(x_off, x_off + n_x, dtype=torch.float64) - n_x_total // 2) / n_x_total,
+          (torch.arange(n, dtype=torch.float64) - n // 2) / n, (torch.arange(n, dtype=torch.float64) - n // 2) / n]
+    g = torch.meshgrid(*ax, indexing='ij')
+    loc = torch.stack([fov[i] * g[i].reshape(-1) for i in range(3)], dim=-1)[None].expand(N, -1, 3).contiguous()
+    nM = loc.shape[1]
+    wgen = torch.Generator().manual_seed(seed)          # the waveform is the same on every rank
+    W = lambda *s: torch.rand(s, generator=wgen, dtype=torch.float64) * 2 - 1
+    rf, gr = W(N, 2, nT) * 0.1, W(N, 3, nT) * 2
+    df = U(N, nM) * 200
+    b1 = U(N, nM, 2) * 0.1
+    b1[:, :, 0] += 1
+    M0 = torch.tensor([0., 0., 1.], dtype=torch.float64).expand(N, nM, 3).contiguous()
+    return {k: v.to(dtype) for k, v in dict(rf=rf, gr=gr, loc=loc, df=df, b1=b1, M0=M0).items()}
+
+
+def run_ours(args):
+    from mrphy import mobjs, parallel, _cabi
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    N, n, nT = WORKLOADS[args.workload]
+    dtype = torch.float32 if args.dtype == 'f32' else torch.float64
+    kw = {'dtype': dtype, 'device': dev}
+    host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    nM = host['loc'].shape[1]
+    tgt = torch.tensor([0., 1., 0.], **kw)
+
+    def make_objects(src, non_blocking=False):
+        d = {k: v.to(dev, non_blocking=non_blocking) for k, v in src.items()}
+        sp = mobjs.SpinArray((N, nM), M_=d['M0'], **kw)
+        pulse = mobjs.Pulse(rf=d['rf'].requires_grad_(True), gr=d['gr'].requires_grad_(True), **kw)
+        return sp, pulse, d
+
+    def step(sp, pulse, d):
+        M = sp.applypulse(pulse, loc_=d['loc'], Δf_=d['df'], b1Map_=d['b1'])
+        loss = ((M - tgt) ** 2).sum()
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_waveform_grads(pulse.rf, pulse.gr, loss.detach().reshape(1))
+        return loss
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    sp, pulse, d = make_objects(host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        pulse.rf.grad = pulse.gr.grad = None
+        step(sp, pulse, d)
+    barrier()
+    # ---- timed region: resident inputs, per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.launch_counter
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        pulse.rf.grad = pulse.gr.grad = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(sp, pulse, d)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    launches = _cabi.launch_counter - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end: pinned host inputs -> device every step, loss + gradients read back
+    for _ in range(2):
+        sp2, pulse2, d2 = make_objects(pinned, non_blocking=True)
+        float(step(sp2, pulse2, d2).item())
+    barrier()
+    t_e2e = []
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sp2, pulse2, d2 = make_objects(pinned, non_blocking=True)
+        loss = step(sp2, pulse2, d2)
+        out = (loss.item(), pulse2.rf.grad.cpu(), pulse2.gr.grad.cpu())
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    barrier()
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = out[1].numel() * out[1].element_size() + out[2].numel() * out[2].element_size() + 4
+    # ---- per-kernel durations (events inside the C ABI, on the launching stream)
+    L = _cabi.lib()
+    L.mrphy_kernel_timing(1)
+    k_fwd, k_bwd = [], []
+    for _ in range(min(args.steps, 10)):
+        flush.fill_(1.0)
+        pulse.rf.grad = pulse.gr.grad = None
+        M = sp.applypulse(pulse, loc_=d['loc'], Δf_=d['df'], b1Map_=d['b1'])
+        k_fwd.append(L.mrphy_last_kernel_ms())
+        ((M - tgt) ** 2).sum().backward()
+        k_bwd.append(L.mrphy_last_kernel_ms())
+    L.mrphy_kernel_timing(0)
+    # ---- reduce over ranks (max time), aggregate
+    t = torch.tensor([ms_total, sum(t_e2e) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    units = float(N) * nM * nT * world            # spin·steps per step, all ranks
+    value = units * args.steps / (ms_total * 1e-3)
+    e2e = units * args.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        hbm_gbs, sm_mhz, src = peaks()
+        peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        ms_b, ms_f = float(np.mean(k_bwd)), float(np.mean(k_fwd))
+        per_launch = float(N) * nM * nT
+        ach_tf = per_launch * FLOP_BWD / (ms_b * 1e-3) / 1e12
+        esz = 4 if dtype == torch.float32 else 8
+        K = 64
+        ck_bytes = per_launch / K * 3 * esz + N * nM * (3 + 3 + 3 + 2 + 1 + 3) * esz   # bwd: ckpt reads + operands
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': f'{args.workload.upper()}: SpinCube {n}^3 x N={N} per GPU, nT={nT}, dt=4us, '
+                                   'b1Map+df+relaxation, fwd+adjoint bwd', 'spins_per_gpu': N * nM, 'nT': nT,
+                       'l2': 'flushed between steps (256 MB write)', 'sharding': f'spin slabs x{world}, waveform '
+                       'replicated, 1 allreduce of grads' if world > 1 else 'single GPU'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'bound': 'fp32_issue', 'kernel': 'fused_bwd_kernel', 'achieved': ach_tf, 'peak': peak_tf,
+                         'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf, 'traffic': None,
+                         'peak_source': f'148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({src} {sm_mhz:.0f} MHz); the path '
+                                        'is FP32-issue-bound (SURVEY 8d), not HBM- or tensor-bound',
+                         'ms_per_launch': ms_b, 'algorithmic_flop_per_spin_step': FLOP_BWD,
+                         'fwd_kernel': {'ms_per_launch': ms_f, 'achieved': per_launch * FLOP_FWD / (ms_f * 1e-3) / 1e12,
+                                        'frac': per_launch * FLOP_FWD / (ms_f * 1e-3) / 1e12 / peak_tf},
+                         'fwd_bwd_frac_of_issue_roofline': value / world / (148 * 128 * sm_mhz * 1e6 / 151.0),
+                         'hbm': {'achieved_gbs': ck_bytes / (ms_b * 1e-3) / 1e9, 'peak_gbs': hbm_gbs,
+                                 'frac': ck_bytes / (ms_b * 1e-3) / 1e9 / hbm_gbs, 'source': src}},
+        }
+        line['cpu_baseline'] = cpu_baseline(args, nT)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_port_step(n, nT, dtype, threads):
+    """One fwd+bwd of the oracle port on an n^3 proxy cube with the bench distributions."""
+    from oracle import bloch_oracle as orc
+    torch.set_num_threads(threads)
+    s = synth(1, n, n, nT, dtype)
+    t0 = time.perf_counter()
+    tgt = torch.tensor([0., 1., 0.], dtype=dtype)
+    orc.applypulse_fwd_bwd(s['M0'], s['rf'], s['gr'], s['loc'], lambda Mo: 2 * (Mo - tgt), df=s['df'], b1=s['b1'],
+                           T1=1.47, T2=0.07, dtype=dtype)
+    return time.perf_counter() - t0, n ** 3 * nT
+
+
+def cpu_baseline(args, nT):
+    cores = len(os.sched_getaffinity(0))
+    dtype = torch.float32 if args.dtype == 'f32' else torch.float64
+    n = 16
+    sec, units = cpu_port_step(n, nT, dtype, cores)
+    return {'value': units / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'oracle/bloch_oracle.py (torch CPU, {cores} threads) on a {n}^3 proxy cube, same nT={nT}, '
+                      f'{args.dtype}, 1 fwd+bwd pass, {sec:.1f} s; the reference needs 52 B/spin-step so the full '
+                      'cube does not fit / finish (BASELINE.md sec. 4)'}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path, restated (oracle port), all host threads."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    N, n, nT = WORKLOADS[args.workload]
+    dtype = torch.float32 if args.dtype == 'f32' else torch.float64
+    cores = len(os.sched_getaffinity(0))
+    budget = min(8.0, 150.0 / max(args.steps + args.warmup, 1))       # seconds per step
+    n_cpu = int(max(8, min(32, round((budget * 7e5 / nT) ** (1 / 3)))))
+    for _ in range(args.warmup):
+        cpu_port_step(n_cpu, nT, dtype, cores)
+    tot, units = 0.0, 0
+    for _ in range(args.steps):
+        s, u = cpu_port_step(n_cpu, nT, dtype, cores)
+        tot += s
+        units += u
+    v = units / tot
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': tot / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': f'{args.workload.upper()} proxy: SpinCube {n_cpu}^3, nT={nT}, dt=4us (CPU sample of '
+                               f'the {n}^3 workload; spin·steps/s is size-insensitive at fixed nT, BASELINE.md sec. 2)'},
+        'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{n_cpu}^3 spins x {nT} steps per step, torch CPU {cores} threads'},
+        'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
+    (run_ours if a.impl == 'ours' else run_reference)(a)

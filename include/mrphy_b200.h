@@ -131,6 +131,14 @@ int mrphy_blochsim_beff_bwd(const mrphy_beff_args* a, void* cuda_stream);
 /* Number of kernel launches the last forward / backward call on this thread issued. */
 int mrphy_last_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline leg.  With timing enabled, each entry point brackets its
+ * MAIN kernel (fused_fwd / fused_bwd / beff_fwd / beff_bwd -- not pack/finalize) with CUDA events on
+ * the launching stream; mrphy_last_kernel_ms() synchronises on the stop event and returns the
+ * duration in milliseconds of the last such kernel launched by this process (< 0 if none).  Process-
+ * wide and not thread-safe: a measurement aid for single-stream benchmarks only.                 */
+int mrphy_kernel_timing(int enable);
+float mrphy_last_kernel_ms(void);
+
 #ifdef __cplusplus
 }
 #endif

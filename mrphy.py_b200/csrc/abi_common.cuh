@@ -8,6 +8,9 @@
 namespace mrphy {
 char* err_buf();           // thread-local, 512 bytes
 int& launch_count();       // thread-local
+// bench-only event bracket around the main kernel of an entry point (see mrphy_kernel_timing)
+void timing_begin(cudaStream_t st);
+void timing_end(cudaStream_t st);
 inline int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(err_buf(), 512, fmt, detail);
   return code;

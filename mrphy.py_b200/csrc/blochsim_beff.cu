@@ -199,11 +199,15 @@ int launch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
   if (bwd) {
     auto kern = beff_bwd_kernel<T, POL, RELAX>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(st);
     kern<<<grid, EBLK, smem, st>>>(e, (a->flags & MRPHY_NEED_GMI) ? 1 : 0, (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0);
+    timing_end(st);
   } else {
     auto kern = beff_fwd_kernel<T, POL, RELAX>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(st);
     kern<<<grid, EBLK, smem, st>>>(e);
+    timing_end(st);
   }
   ++launch_count();
   CK(cudaGetLastError());

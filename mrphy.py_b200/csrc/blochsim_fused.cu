@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mrphy_b200.h"
@@ -414,10 +415,44 @@ using namespace mrphy;
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+// bench-only, process-wide on purpose: backward runs on the autograd engine's thread
+static int g_timing = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static int g_ev_valid = 0;
 namespace mrphy {
 char* err_buf() { return g_err; }
 int& launch_count() { return g_launches; }
+void timing_begin(cudaStream_t st) {
+  if (!g_timing) return;
+  if (!g_ev0 && (cudaEventCreate(&g_ev0) != cudaSuccess || cudaEventCreate(&g_ev1) != cudaSuccess)) {
+    cudaGetLastError();
+    g_ev0 = g_ev1 = nullptr;
+    return;
+  }
+  g_ev_valid = 0;
+  cudaEventRecord(g_ev0, st);
+}
+void timing_end(cudaStream_t st) {
+  if (!g_timing || !g_ev0) return;
+  cudaEventRecord(g_ev1, st);
+  g_ev_valid = 1;
+}
 }  // namespace mrphy
+
+extern "C" int mrphy_kernel_timing(int enable) {
+  g_timing = enable ? 1 : 0;
+  g_ev_valid = 0;
+  return MRPHY_OK;
+}
+extern "C" float mrphy_last_kernel_ms(void) {
+  if (!g_ev_valid) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess || cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0f;
+  }
+  return ms;
+}
 
 extern "C" int mrphy_abi_version(void) { return MRPHY_ABI_VERSION; }
 extern "C" const char* mrphy_last_error(void) { return g_err; }
@@ -471,7 +506,11 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   p->S = 1;
   p->tiles = (a->nM + BLK * p->S - 1) / (BLK * p->S);
   // grid: one tile per CTA while that stays within 8 resident waves, else a grid-stride loop
-  const int cap = (need_device ? sm_count_cached() : 148) * 8 * 8;
+  int cap = (need_device ? sm_count_cached() : 148) * 8 * 8;
+  if (const char* e = getenv("MRPHY_B200_MAX_CTAS")) {   // tests use it to force the multi-tile path
+    const int v = atoi(e);
+    if (v > 0) cap = v;
+  }
   int P = p->tiles;
   if ((int64_t)P * a->N > cap) P = cap / a->N > 0 ? cap / a->N : 1;
   p->P = P;
@@ -542,7 +581,9 @@ int launch_pack(const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
 template <typename T, int POL, bool RELAX, int NC>
 int launch_fwd_s(const KArgs<T>& k, const Plan& p, cudaStream_t st) {
   dim3 grid(p.P, k.N);
+  timing_begin(st);
   fused_fwd_kernel<T, POL, RELAX, NC, 1><<<grid, BLK, 0, st>>>(k);
+  timing_end(st);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;
@@ -553,7 +594,9 @@ int launch_bwd_s(const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st
   constexpr size_t smem = BwdSmem<T, NC>::bytes;
   auto kern = fused_bwd_kernel<T, POL, RELAX, NC, 1>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  timing_begin(st);
   kern<<<grid, BLK, smem, st>>>(k, need_gmi);
+  timing_end(st);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;

@@ -55,6 +55,8 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_last_error': (ctypes.c_char_p, []),
     'mrphy_last_launch_count': (ctypes.c_int, []),
     'mrphy_device_sm_count': (ctypes.c_int, [ctypes.c_int]),
+    'mrphy_kernel_timing': (ctypes.c_int, [ctypes.c_int]),
+    'mrphy_last_kernel_ms': (ctypes.c_float, []),
     'mrphy_fused_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),
     'mrphy_fused_wave_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),
     'mrphy_fused_partial_elems': (ctypes.c_size_t, [ctypes.POINTER(FusedArgs)]),

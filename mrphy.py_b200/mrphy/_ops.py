@@ -284,7 +284,10 @@ def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -
 
 
 def default_flags() -> int:
-    return _cabi.FLAG_TRIG_PRECISE if os.environ.get('MRPHY_B200_TRIG', 'fast') == 'precise' else 0
+    """fp32 trigonometry policy.  Default 'precise' (Newton-refined rsqrt + polynomial sincos on the FMA pipe):
+    on the reference's own fixtures it is ~0.6x the reference's fp32 error, whereas raw MUFU.SIN/COS
+    ('fast', MRPHY_B200_TRIG=fast) doubles it at nT~1000.  Ignored for fp64."""
+    return 0 if os.environ.get('MRPHY_B200_TRIG', 'precise') == 'fast' else _cabi.FLAG_TRIG_PRECISE
 
 
 def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: Optional[Tensor] = None,

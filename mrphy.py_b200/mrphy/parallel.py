@@ -1,0 +1,61 @@
+r"""Spin sharding over the GPUs of one box (one process per GPU, ``torch.distributed``/NCCL).
+
+Spins never interact (sims.py:91-126 is elementwise over `(N,*Nd)`); the only cross-spin operation of
+forward+backward is the sum over spins that produces ``rf.grad``/``gr.grad`` (autograd of
+beffective.py:137-165).  So each rank owns a contiguous range of the COMPACT spin axis ``nM`` with its
+``loc_, Δf_, b1Map_, T1_, T2_, γ_, M_``; the waveform is replicated and the single collective is one
+all-reduce(sum) of the flat ``[rf.grad ‖ gr.grad ‖ extras]`` buffer (N·nT·(2·nCoils+3) elements, 80 KB
+for nT=4000).  Geometry stays global: the shard is a ``SpinArray`` with explicit ``loc_`` sliced from the
+global cube -- do not rebuild a smaller ``SpinCube`` (``_update_loc_`` centres on ``n//2``).
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from mrphy import mobjs
+
+__all__ = ['shard_range', 'shard_spins', 'allreduce_waveform_grads']
+
+
+def shard_range(nM: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``range(nM)``: the first ``nM % world`` ranks get one extra spin."""
+    base, extra = divmod(nM, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_spins(obj, rank: int, world: int, *, loc_: Optional[Tensor] = None, Δf_: Optional[Tensor] = None,
+                b1Map_: Optional[Tensor] = None, device: Optional[torch.device] = None):
+    """Rank ``rank``'s slab of a ``SpinCube``/``SpinArray``.
+
+    Returns ``(spinarray, kw)``: a compact all-True-mask ``SpinArray`` of shape `(N, nLocal)` and the keyword
+    arguments (``loc_``, ``Δf_``, ``b1Map_``) to pass to ``spinarray.applypulse(pulse, **kw)``.
+    """
+    sp = obj.spinarray if isinstance(obj, mobjs.SpinCube) else obj
+    lo, hi = shard_range(sp.nM, rank, world)
+    device = sp.device if device is None else device
+    if isinstance(obj, mobjs.SpinCube):
+        loc_ = obj.loc_ if loc_ is None else loc_
+        Δf_ = obj.Δf_ if Δf_ is None else Δf_
+    assert loc_ is not None, 'a SpinArray has no geometry: pass loc_'
+    cut = lambda x: None if x is None else (x[:, lo:hi] if x.shape[1] != 1 else x).to(device)
+    local = mobjs.SpinArray((sp.shape[0], hi - lo), T1_=cut(sp.T1_), T2_=cut(sp.T2_), γ_=cut(sp.γ_),
+                            M_=cut(sp.M_).contiguous(), device=device, dtype=sp.dtype)
+    return local, {'loc_': cut(loc_).contiguous(), 'Δf_': cut(Δf_), 'b1Map_': cut(b1Map_)}
+
+
+def allreduce_waveform_grads(rf: Tensor, gr: Tensor, *extras: Tensor, group=None) -> None:
+    """Sum ``rf.grad``, ``gr.grad`` (and any extra tensors, e.g. the scalar loss) over ranks, in place,
+    with ONE all-reduce on a flat buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    parts = [rf.grad, gr.grad, *extras]
+    flat = torch.cat([p.reshape(-1) for p in parts])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for p in parts:
+        n = p.numel()
+        p.copy_(flat[off:off + n].reshape(p.shape))
+        off += n
