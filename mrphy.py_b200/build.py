@@ -25,11 +25,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines`/`out` build a tuning variant (e.g. -DMRPHY_BWD_MINB=10) next to the default library."""
+    if out is not None:
+        return _compile(list(defines), out, verbose)
     if not force and not _stale():
         return LIB
+    return _compile([], LIB, verbose)
+
+
+def _compile(defines, LIB, verbose):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (['-Xptxas', '-v'] if verbose else []) + \
         [os.path.join(CSRC, s) for s in SOURCES] + ['-o', LIB + '.tmp']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -41,4 +48,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, defines=defs,
+                out=os.path.abspath(outs[0]) if outs else None))

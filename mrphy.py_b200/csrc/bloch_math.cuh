@@ -29,9 +29,68 @@ namespace mrphy {
 
 enum TrigPolicy { TRIG_FAST = 0, TRIG_PRECISE = 1 };
 
+// ---- f2: two spins side by side -----------------------------------------------------------
+// On sm_100 the arithmetic below is ONE packed instruction per pair (FFMA2 / FMUL2 / FADD2): half the
+// issue slots of scalar code for the same FP32-pipe work, which is what lets the non-FMA
+// instructions (MUFU, LDS, STS, integer) issue in the shadow of the FMA pipe.
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+struct f2 {
+  float2 v;
+  MRPHY_HD f2() {}
+  MRPHY_HD explicit f2(float s) { v = make_float2(s, s); }
+  MRPHY_HD f2(float a, float b) { v = make_float2(a, b); }
+};
+MRPHY_HD f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }
+MRPHY_HD f2 operator*(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  f2 r; r.v = __fmul2_rn(a.v, b.v); return r;
+#else
+  return f2(a.v.x * b.v.x, a.v.y * b.v.y);
+#endif
+}
+MRPHY_HD f2 operator+(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  f2 r; r.v = __fadd2_rn(a.v, b.v); return r;
+#else
+  return f2(a.v.x + b.v.x, a.v.y + b.v.y);
+#endif
+}
+MRPHY_HD f2 operator-(f2 a, f2 b) { return a + (-b); }
+
 template <typename T> MRPHY_HD T fma_(T a, T b, T c);
 template <> MRPHY_HD float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> MRPHY_HD double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> MRPHY_HD f2 fma_<f2>(f2 a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r;
+#else
+  return f2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
+#endif
+}
+// Negated forms.  FFMA2 has no operand-negate modifier (ptxas inserts two FADDs per negated pair), so
+// for f2 these are written as two scalar FFMAs, whose negate modifiers are free: same FMA-pipe time as
+// one FFMA2, one extra issue slot.  fnma_ = c - a*b ; fms_ = a*b - c.
+template <typename T> MRPHY_HD T fnma_(T a, T b, T c) { return fma_(-a, b, c); }
+template <> MRPHY_HD f2 fnma_<f2>(f2 a, f2 b, f2 c) { return f2(fmaf(-a.v.x, b.v.x, c.v.x), fmaf(-a.v.y, b.v.y, c.v.y)); }
+template <typename T> MRPHY_HD T fms_(T a, T b, T c) { return fma_(a, b, -c); }
+template <> MRPHY_HD f2 fms_<f2>(f2 a, f2 b, f2 c) { return f2(fmaf(a.v.x, b.v.x, -c.v.x), fmaf(a.v.y, b.v.y, -c.v.y)); }
+
+MRPHY_HD float max_(float a, float b) { return fmaxf(a, b); }
+MRPHY_HD double max_(double a, double b) { return fmax(a, b); }
+MRPHY_HD f2 max_(f2 a, f2 b) { return f2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y)); }
+
+// scalar type behind a (possibly packed) value type, and lane access
+template <typename T> struct Scalar { typedef T type; };
+template <> struct Scalar<f2> { typedef float type; };
+MRPHY_HD float lane0(float a) { return a; }
+MRPHY_HD double lane0(double a) { return a; }
+MRPHY_HD float lane0(f2 a) { return a.v.x; }
+MRPHY_HD float hsum(float a) { return a; }
+MRPHY_HD double hsum(double a) { return a; }
+MRPHY_HD float hsum(f2 a) { return a.v.x + a.v.y; }
 
 // ---- rsqrt / sincos policies ------------------------------------------------------------
 // float FAST   : MUFU.RSQ, MUFU.SIN, MUFU.COS (abs err ~2^-21.4 on sin/cos, 2 ulp on rsqrt)
@@ -74,6 +133,43 @@ template <> struct Fn<float, TRIG_FAST> {
   }
 };
 
+// Cody-Waite reduction by pi/2 with the round-to-nearest-via-magic-constant trick (valid for
+// 0 <= x < 2^22 * pi/2; two reduction terms are exact to < 1e-8 rad for x < ~1e4 rad), then the
+// minimax sin/cos polynomials on [-pi/4, pi/4].  ~21 FP32-pipe/ALU instructions, no XU, no branches.
+#define MRPHY_SC_MAGIC 12582912.0f   /* 1.5 * 2^23 */
+MRPHY_HD int f_as_i(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(x);
+#else
+  union { float f; int i; } u; u.f = x; return u.i;
+#endif
+}
+MRPHY_HD float i_as_f(int x) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(x);
+#else
+  union { float f; int i; } u; u.i = x; return u.f;
+#endif
+}
+// quadrant fix-up: (sr, cr) = sin/cos of the reduced argument, j = quadrant index bits
+MRPHY_HD void sc_quadrant(int j, float sr, float cr, float& s, float& c) {
+  const float ss = (j & 1) ? cr : sr;
+  const float cc = (j & 1) ? sr : cr;
+  s = i_as_f(f_as_i(ss) ^ ((j & 2) << 30));
+  c = i_as_f(f_as_i(cc) ^ (((j + 1) & 2) << 30));
+}
+template <typename V> MRPHY_HD void sc_poly(V r, V& sr, V& cr) {
+  const V r2 = r * r;
+  V sp = fma_(r2, V(2.86567956e-6f), V(-1.98559923e-4f));
+  sp = fma_(sp, r2, V(8.33338592e-3f));
+  sp = fma_(sp, r2, V(-1.66666672e-1f));
+  sr = fma_(sp * r2, r, r);
+  V cp = fma_(r2, V(2.44677067e-5f), V(-1.38877297e-3f));
+  cp = fma_(cp, r2, V(4.16666567e-2f));
+  cp = fma_(cp, r2, V(-0.5f));
+  cr = fma_(cp, r2, V(1.0f));
+}
+
 template <> struct Fn<float, TRIG_PRECISE> {
   static MRPHY_HD float rsq(float x) {
 #if defined(__CUDA_ARCH__)
@@ -81,31 +177,47 @@ template <> struct Fn<float, TRIG_PRECISE> {
 #else
     float r = (float)(1.0 / sqrt((double)x)) * (1.0f + 1.2e-7f);   // host: perturb so Newton does work
 #endif
-    // one Newton-Raphson step: r <- r * (1.5 - 0.5*x*r*r)
+    // one Newton-Raphson step: r <- r + r*(0.5 - 0.5*x*r*r)
     float h = 0.5f * x * r;
     return fmaf(r, fmaf(-h, r, 0.5f), r);
   }
   static MRPHY_HD void sc(float x, float& s, float& c) {
-    // j = nearest integer to x*2/pi ; r = x - j*pi/2 in three Cody-Waite pieces
-    float jf = rintf(x * 0.63661977236758134f);
+    const float t = fmaf(x, 0.63661977236758134f, MRPHY_SC_MAGIC);
+    const float jf = t - MRPHY_SC_MAGIC;
     float r = fmaf(jf, -1.57079601287841796875f, x);
     r = fmaf(jf, -3.1391647326017846353e-07f, r);
-    r = fmaf(jf, -5.3903029534742383927e-15f, r);
-    int j = (int)jf;
-    float r2 = r * r;
-    // sin(r), cos(r) on [-pi/4, pi/4]  (minimax, ~1 ulp)
-    float sp = fmaf(r2, 2.86567956e-6f, -1.98559923e-4f);
-    sp = fmaf(sp, r2, 8.33338592e-3f);
-    sp = fmaf(sp, r2, -1.66666672e-1f);
-    float sr = fmaf(sp * r2, r, r);
-    float cp = fmaf(r2, 2.44677067e-5f, -1.38877297e-3f);
-    cp = fmaf(cp, r2, 4.16666567e-2f);
-    cp = fmaf(cp, r2, -0.5f);
-    float cr = fmaf(cp, r2, 1.0f);
-    float ss = (j & 1) ? cr : sr;
-    float cc = (j & 1) ? sr : cr;
-    s = (j & 2) ? -ss : ss;
-    c = ((j + 1) & 2) ? -cc : cc;
+    float sr, cr;
+    sc_poly<float>(r, sr, cr);
+    sc_quadrant(f_as_i(t), sr, cr, s, c);
+  }
+};
+
+template <> struct Fn<f2, TRIG_FAST> {
+  static MRPHY_HD f2 rsq(f2 x) { return f2(Fn<float, TRIG_FAST>::rsq(x.v.x), Fn<float, TRIG_FAST>::rsq(x.v.y)); }
+  static MRPHY_HD void sc(f2 x, f2& s, f2& c) {
+    Fn<float, TRIG_FAST>::sc(x.v.x, s.v.x, c.v.x);
+    Fn<float, TRIG_FAST>::sc(x.v.y, s.v.y, c.v.y);
+  }
+};
+template <> struct Fn<f2, TRIG_PRECISE> {
+  static MRPHY_HD f2 rsq(f2 x) {
+#if defined(__CUDA_ARCH__)
+    f2 r(rsqrtf(x.v.x), rsqrtf(x.v.y));
+#else
+    f2 r((float)(1.0 / sqrt((double)x.v.x)) * (1.0f + 1.2e-7f), (float)(1.0 / sqrt((double)x.v.y)) * (1.0f + 1.2e-7f));
+#endif
+    const f2 nh = (f2(-0.5f) * x) * r;
+    return fma_(r, fma_(nh, r, f2(0.5f)), r);
+  }
+  static MRPHY_HD void sc(f2 x, f2& s, f2& c) {
+    const f2 t = fma_(x, f2(0.63661977236758134f), f2(MRPHY_SC_MAGIC));
+    const f2 jf = t + f2(-MRPHY_SC_MAGIC);
+    f2 r = fma_(jf, f2(-1.57079601287841796875f), x);
+    r = fma_(jf, f2(-3.1391647326017846353e-07f), r);
+    f2 sr, cr;
+    sc_poly<f2>(r, sr, cr);
+    sc_quadrant(f_as_i(t.v.x), sr.v.x, cr.v.x, s.v.x, c.v.x);
+    sc_quadrant(f_as_i(t.v.y), sr.v.y, cr.v.y, s.v.y, c.v.y);
   }
 };
 
@@ -147,13 +259,24 @@ MRPHY_HD void make_consts(SpinConst<T, NC>& k, double gamma, double dt, bool rel
   }
 }
 
+// two spins' constants side by side
+template <int NC>
+MRPHY_HD SpinConst<f2, NC> pack2(const SpinConst<float, NC>& a, const SpinConst<float, NC>& b) {
+  SpinConst<f2, NC> k;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { k.cbr[c] = f2(a.cbr[c], b.cbr[c]); k.cbi[c] = f2(a.cbi[c], b.cbi[c]); }
+  k.glx = f2(a.glx, b.glx); k.gly = f2(a.gly, b.gly); k.glz = f2(a.glz, b.glz); k.gbz0 = f2(a.gbz0, b.gbz0);
+  k.e1 = f2(a.e1, b.e1); k.e2 = f2(a.e2, b.e2); k.iE1 = f2(a.iE1, b.iE1); k.iE2 = f2(a.iE2, b.iE2);
+  return k;
+}
+
 // Rotation coefficients shared by forward and backward.
 template <typename T> struct RotCoef { T c, a, d, rs2; };
 
 template <typename T, int POL>
 MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
   T p2 = fma_(bx, bx, fma_(by, by, bz * bz));
-  p2 = p2 > (T)1e-24 ? p2 : (T)1e-24;
+  p2 = max_(p2, (T)1e-24f);
   T rs = Fn<T, POL>::rsq(p2);
   T phi = p2 * rs;
   T s, c;
@@ -162,7 +285,7 @@ MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
   r.c = c;
   r.a = s * rs;
   r.rs2 = rs * rs;
-  r.d = ((T)1 - c) * r.rs2;
+  r.d = fnma_(c, r.rs2, r.rs2);   // (1 - cos) / phi^2
   return r;
 }
 
@@ -171,44 +294,49 @@ template <typename T, int NC>
 MRPHY_HD void field(const SpinConst<T, NC>& k, const T* rx, const T* ry, T gx, T gy, T gz, T& bx, T& by, T& bz) {
   bx = k.cbr[0] * rx[0];
   by = k.cbr[0] * ry[0];
-  bx = fma_(-k.cbi[0], ry[0], bx);
+  bx = fnma_(k.cbi[0], ry[0], bx);
   by = fma_(k.cbi[0], rx[0], by);
 #pragma unroll
   for (int c = 1; c < NC; ++c) {
     bx = fma_(k.cbr[c], rx[c], bx);
     by = fma_(k.cbr[c], ry[c], by);
-    bx = fma_(-k.cbi[c], ry[c], bx);
+    bx = fnma_(k.cbi[c], ry[c], bx);
     by = fma_(k.cbi[c], rx[c], by);
   }
   bz = fma_(k.glx, gx, fma_(k.gly, gy, fma_(k.glz, gz, k.gbz0)));
 }
 
 // ---- forward step -------------------------------------------------------------------------
-template <typename T, int POL, bool RELAX>
-MRPHY_HD void step_fwd(T bx, T by, T bz, T e1, T e2, T& mx, T& my, T& mz) {
-  RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+// apply_fwd: the recurrent part (needs the previous state); rot_coef above is the part that only needs
+// the waveform, which the time-packed kernels evaluate for two consecutive steps in one f2.
+template <typename T, bool RELAX>
+MRPHY_HD void apply_fwd(const RotCoef<T>& r, T bx, T by, T bz, T e1, T e2, T& mx, T& my, T& mz) {
   T kk = r.d * fma_(bx, mx, fma_(by, my, bz * mz));
   T abx = r.a * bx, aby = r.a * by, abz = r.a * bz;
   // m~ = c*m + kk*b - (ab x m)
-  T nx = fma_(abz, my, fma_(-aby, mz, fma_(kk, bx, r.c * mx)));
-  T ny = fma_(abx, mz, fma_(-abz, mx, fma_(kk, by, r.c * my)));
-  T nz = fma_(aby, mx, fma_(-abx, my, fma_(kk, bz, r.c * mz)));
+  T nx = fma_(abz, my, fnma_(aby, mz, fma_(kk, bx, r.c * mx)));
+  T ny = fma_(abx, mz, fnma_(abz, mx, fma_(kk, by, r.c * my)));
+  T nz = fma_(aby, mx, fnma_(abx, my, fma_(kk, bz, r.c * mz)));
   if (RELAX) {   // E2*m~xy ; E1*m~z - (E1-1)  written with e = E-1 so no cancellation
     nx = fma_(e2, nx, nx);
     ny = fma_(e2, ny, ny);
-    nz = fma_(e1, nz - (T)1, nz);
+    nz = fma_(e1, nz + (T)(-1.0f), nz);
   }
   mx = nx; my = ny; mz = nz;
+}
+template <typename T, int POL, bool RELAX>
+MRPHY_HD void step_fwd(T bx, T by, T bz, T e1, T e2, T& mx, T& my, T& mz) {
+  const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+  apply_fwd<T, RELAX>(r, bx, by, bz, e1, e2, mx, my, mz);
 }
 
 // ---- backward step --------------------------------------------------------------------------
 // in : (mx,my,mz) state AFTER the step, (hx,hy,hz) = dL/d(state after the step)
 // out: state BEFORE the step, dL/d(state before), and F = -(1/g) dL/dBeff (sign/scale folded
 //      into the per-spin constants and the finalize kernel)
-template <typename T, int POL, bool RELAX, int NC>
-MRPHY_HD void step_bwd(const SpinConst<T, NC>& k, T bx, T by, T bz, T& mx, T& my, T& mz, T& hx, T& hy, T& hz,
-                       T& Fx, T& Fy, T& Fz) {
-  RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+template <typename T, bool RELAX, int NC>
+MRPHY_HD void apply_bwd(const SpinConst<T, NC>& k, const RotCoef<T>& r, T bx, T by, T bz, T& mx, T& my, T& mz,
+                        T& hx, T& hy, T& hz, T& Fx, T& Fy, T& Fz) {
   T tx = mx, ty = my, tz = mz;   // m~ (pre-relaxation state)
   T gx = hx, gy = hy, gz = hz;   // h~
   if (RELAX) {
@@ -224,28 +352,50 @@ MRPHY_HD void step_bwd(const SpinConst<T, NC>& k, T bx, T by, T bz, T& mx, T& my
   T kq = r.d * Q, kp = r.d * P;
   T abx = r.a * bx, aby = r.a * by, abz = r.a * bz;
   // m0 = c*m~ + kq*b + (ab x m~)
-  T px = fma_(-abz, ty, fma_(aby, tz, fma_(kq, bx, r.c * tx)));
-  T py = fma_(-abx, tz, fma_(abz, tx, fma_(kq, by, r.c * ty)));
-  T pz = fma_(-aby, tx, fma_(abx, ty, fma_(kq, bz, r.c * tz)));
+  T px = fnma_(abz, ty, fma_(aby, tz, fma_(kq, bx, r.c * tx)));
+  T py = fnma_(abx, tz, fma_(abz, tx, fma_(kq, by, r.c * ty)));
+  T pz = fnma_(aby, tx, fma_(abx, ty, fma_(kq, bz, r.c * tz)));
   // wb = b x h~
-  T wx = fma_(by, gz, -bz * gy);
-  T wy = fma_(bz, gx, -bx * gz);
-  T wz = fma_(bx, gy, -by * gx);
+  T wx = fms_(by, gz, bz * gy);
+  T wy = fms_(bz, gx, bx * gz);
+  T wz = fms_(bx, gy, by * gx);
   // F = a (m0 x h~) - d (Q h~ + P m0) - [ (m~ - a m0).wb - 2 d P Q ] rs^2 b
-  T nx = fma_(-r.a, px, tx), ny = fma_(-r.a, py, ty), nz = fma_(-r.a, pz, tz);
+  T nx = fnma_(r.a, px, tx), ny = fnma_(r.a, py, ty), nz = fnma_(r.a, pz, tz);
   T C = fma_(nx, wx, fma_(ny, wy, nz * wz));
-  C = fma_((T)-2 * kp, Q, C) * r.rs2;
-  T cx = fma_(py, gz, -pz * gy);
-  T cy = fma_(pz, gx, -px * gz);
-  T cz = fma_(px, gy, -py * gx);
-  Fx = fma_(-C, bx, fma_(r.a, cx, -fma_(kq, gx, kp * px)));
-  Fy = fma_(-C, by, fma_(r.a, cy, -fma_(kq, gy, kp * py)));
-  Fz = fma_(-C, bz, fma_(r.a, cz, -fma_(kq, gz, kp * pz)));
+  C = fma_((T)(-2.0f) * kp, Q, C) * r.rs2;
+  T cx = fms_(py, gz, pz * gy);
+  T cy = fms_(pz, gx, px * gz);
+  T cz = fms_(px, gy, py * gx);
+  Fx = fnma_(C, bx, fms_(r.a, cx, fma_(kq, gx, kp * px)));
+  Fy = fnma_(C, by, fms_(r.a, cy, fma_(kq, gy, kp * py)));
+  Fz = fnma_(C, bz, fms_(r.a, cz, fma_(kq, gz, kp * pz)));
   // h0 = c*h~ + kp*b + a*wb
   hx = fma_(r.a, wx, fma_(kp, bx, r.c * gx));
   hy = fma_(r.a, wy, fma_(kp, by, r.c * gy));
   hz = fma_(r.a, wz, fma_(kp, bz, r.c * gz));
   mx = px; my = py; mz = pz;
+}
+template <typename T, int POL, bool RELAX, int NC>
+MRPHY_HD void step_bwd(const SpinConst<T, NC>& k, T bx, T by, T bz, T& mx, T& my, T& mz, T& hx, T& hy, T& hz,
+                       T& Fx, T& Fy, T& Fz) {
+  const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+  apply_bwd<T, RELAX, NC>(k, r, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+}
+
+// ---- time-packed helpers: two consecutive time steps of ONE spin in an f2 ---------------------
+// The field and the rotation coefficients of a step depend only on the waveform, not on the state, so
+// steps (t, t+1) are evaluated together with packed arithmetic; per-spin constants enter as broadcast
+// scalars (FFMA2 ".F32" operand form, free).
+MRPHY_HD void field_tp(const SpinConst<float, 1>& k, f2 rx, f2 ry, f2 gx, f2 gy, f2 gz, f2& bx, f2& by, f2& bz) {
+  bx = fma_(f2(k.cbr[0]), rx, f2(-k.cbi[0]) * ry);
+  by = fma_(f2(k.cbr[0]), ry, f2(k.cbi[0]) * rx);
+  bz = fma_(f2(k.glx), gx, fma_(f2(k.gly), gy, fma_(f2(k.glz), gz, f2(k.gbz0))));
+}
+MRPHY_HD RotCoef<float> lane_x(const RotCoef<f2>& r) {
+  RotCoef<float> o; o.c = r.c.v.x; o.a = r.a.v.x; o.d = r.d.v.x; o.rs2 = r.rs2.v.x; return o;
+}
+MRPHY_HD RotCoef<float> lane_y(const RotCoef<f2>& r) {
+  RotCoef<float> o; o.c = r.c.v.y; o.a = r.a.v.y; o.d = r.d.v.y; o.rs2 = r.rs2.v.y; return o;
 }
 
 }  // namespace mrphy

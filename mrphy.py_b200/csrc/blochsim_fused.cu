@@ -28,24 +28,33 @@
 namespace mrphy {
 
 constexpr int TCMAX = 64;   // max steps per staged waveform chunk (== max checkpoint interval)
-constexpr int BLK = 128;    // threads per CTA
-constexpr int NWARP = BLK / 32;
+
+// value type of a thread: one spin (T) or two spins packed for FFMA2 (f2)
+template <typename T, int PK> struct Pack { typedef T type; };
+template <> struct Pack<float, 2> { typedef f2 type; };
 
 // steps per gradient-reduction tile: the per-warp transposition tile [W][TR][32] is kept <= 10 KB
+#ifndef MRPHY_RED_BUDGET
+#define MRPHY_RED_BUDGET 10240
+#endif
+#ifndef MRPHY_BWD_MINB
+#define MRPHY_BWD_MINB 9     // spin-packed backward: cap registers so that 9 CTAs (18 warps) fit per SM
+#endif
 constexpr int pick_tr(int W, int elem) {
   int tr = 16;
-  while (tr > 1 && W * tr * 32 * elem > 10240) tr >>= 1;
+  while (tr > 1 && W * tr * 32 * elem > MRPHY_RED_BUDGET) tr >>= 1;
   return tr;
 }
 
 // dynamic shared memory layout of the backward kernel
-template <typename T, int NC> struct BwdSmem {
+template <typename T, int NC, int BLKT> struct BwdSmem {
   static constexpr int W = 2 * NC + 3;
+  static constexpr int NW = BLKT / 32;
   static constexpr int TR = pick_tr(W, (int)sizeof(T));
   static constexpr size_t wbuf = 0;                                                // T[2][W*TCMAX]
-  static constexpr size_t red = (2 * W * TCMAX * sizeof(T) + 127) / 128 * 128;     // T[NWARP][W][TR][32]
-  static constexpr size_t cta = red + (size_t)NWARP * W * TR * 32 * sizeof(T);     // T[NWARP][W][TR]
-  static constexpr size_t bar = (cta + (size_t)NWARP * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
+  static constexpr size_t red = (2 * W * TCMAX * sizeof(T) + 127) / 128 * 128;     // T[NW][W][TR][32]
+  static constexpr size_t cta = red + (size_t)NW * W * TR * 32 * sizeof(T);        // T[NW][W][TR]
+  static constexpr size_t bar = (cta + (size_t)NW * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
   static constexpr size_t bytes = bar + 16;
 };
 
@@ -73,7 +82,15 @@ __device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-// per-spin prologue shared by forward and backward
+// lane access for scalar / packed values
+template <int Q> __device__ __forceinline__ float getq(f2 a) { return Q == 0 ? a.v.x : a.v.y; }
+template <int Q> __device__ __forceinline__ float getq(float a) { return a; }
+template <int Q> __device__ __forceinline__ double getq(double a) { return a; }
+__device__ __forceinline__ f2 mkv(float a, float b, f2*) { return f2(a, b); }
+__device__ __forceinline__ float mkv(float a, float, float*) { return a; }
+__device__ __forceinline__ double mkv(double a, double, double*) { return a; }
+
+// per-spin prologue shared by forward and backward: constants of one spin, in scalar T
 template <typename T, int NC, bool RELAX>
 __device__ __forceinline__ void load_spin(const KArgs<T>& a, int n, int i, SpinConst<T, NC>& k) {
   const T* lp = a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
@@ -92,6 +109,26 @@ __device__ __forceinline__ void load_spin(const KArgs<T>& a, int n, int i, SpinC
   const double t1 = RELAX ? ld_param(a.T1, n, i) : 1.0;
   const double t2 = RELAX ? ld_param(a.T2, n, i) : 1.0;
   make_consts<T, NC>(k, gam, dt, RELAX, t1, t2, df, lp[0], lp[1], lp[2], a.b1 ? br : nullptr, a.b1 ? bi : nullptr);
+}
+template <typename T, typename V, int NC, int PK, bool RELAX>
+__device__ __forceinline__ void load_consts_v(const KArgs<T>& a, int n, const int (&idx)[PK], SpinConst<V, NC>& k) {
+  if constexpr (PK == 1) {
+    load_spin<T, NC, RELAX>(a, n, idx[0], k);
+  } else {
+    SpinConst<float, NC> k0, k1;
+    load_spin<float, NC, RELAX>(a, n, idx[0], k0);
+    load_spin<float, NC, RELAX>(a, n, idx[1], k1);
+    k = pack2<NC>(k0, k1);
+  }
+}
+// three consecutive T's of PK spins -> three V's
+template <typename T, typename V, int PK>
+__device__ __forceinline__ void load_vec3(const T* base, int64_t stride, const int (&idx)[PK], V& x, V& y, V& z) {
+  const T* p0 = base + (int64_t)idx[0] * stride;
+  const T* p1 = base + (int64_t)idx[PK - 1] * stride;
+  x = mkv(p0[0], p1[0], (V*)nullptr);
+  y = mkv(p0[1], p1[1], (V*)nullptr);
+  z = mkv(p0[2], p1[2], (V*)nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -127,9 +164,10 @@ __global__ void pack_waveform_kernel(const T* __restrict__ rf, int64_t rf_sn, in
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
-template <typename T, int POL, bool RELAX, int NC, int S>
-__global__ void __launch_bounds__(BLK) fused_fwd_kernel(const KArgs<T> a) {
+// forward.  PK spins per thread (PK == 2: packed f2 arithmetic), BLKT threads per CTA.
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(const KArgs<T> a) {
+  typedef typename Pack<T, PK>::type V;
   constexpr int W = 2 * NC + 3;
   __shared__ __align__(128) T wbuf[2][W * TCMAX];
   __shared__ __align__(8) uint64_t full[2];
@@ -137,7 +175,7 @@ __global__ void __launch_bounds__(BLK) fused_fwd_kernel(const KArgs<T> a) {
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
   const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
   const T* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
-  const int tiles = (nM + BLK * S - 1) / (BLK * S);
+  const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);
   const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
   if (tid == 0) {
@@ -152,19 +190,18 @@ __global__ void __launch_bounds__(BLK) fused_fwd_kernel(const KArgs<T> a) {
   }
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    SpinConst<T, NC> k[S];
-    T mx[S], my[S], mz[S];
-    int idx[S];
-    bool ok[S];
+    SpinConst<V, NC> k;
+    V mx, my, mz;
+    int idx[PK];
+    bool ok[PK];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int i = (tile * S + s) * BLK + tid;
-      ok[s] = i < nM;
-      idx[s] = ok[s] ? i : nM - 1;
-      load_spin<T, NC, RELAX>(a, n, idx[s], k[s]);
-      const T* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)idx[s] * a.Mi_sm;
-      mx[s] = mp[0]; my[s] = mp[1]; mz[s] = mp[2];
+    for (int q = 0; q < PK; ++q) {
+      const int i = (tile * PK + q) * BLKT + tid;
+      ok[q] = i < nM;
+      idx[q] = ok[q] ? i : nM - 1;
     }
+    load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, k);
+    load_vec3<T, V, PK>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, idx, mx, my, mz);
     for (int c = 0; c < nChunks; ++c, ++it) {
       if (tid == 0 && it + 1 < total) {   // prefetch the next chunk (possibly chunk 0 of the next tile)
         const int cn = (c + 1 == nChunks) ? 0 : c + 1;
@@ -175,6 +212,13 @@ __global__ void __launch_bounds__(BLK) fused_fwd_kernel(const KArgs<T> a) {
       mbar_wait(&full[it & 1], (it >> 1) & 1);
       const T* wb = wbuf[it & 1];
       const int ns = min(K, nT - c * K);
+      auto one_step = [&](const T (&s)[W]) {
+        V rx[NC], ry[NC], bx, by, bz;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) { rx[q] = V(s[q]); ry[q] = V(s[NC + q]); }
+        field<V, NC>(k, rx, ry, V(s[2 * NC]), V(s[2 * NC + 1]), V(s[2 * NC + 2]), bx, by, bz);
+        step_fwd<V, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
+      };
       int j = 0;
       // 4 steps per iteration with 128-bit broadcast loads, while the staged samples fit ~40 registers
       constexpr bool VEC4 = W * sizeof(T) <= 44;
@@ -184,56 +228,51 @@ __global__ void __launch_bounds__(BLK) fused_fwd_kernel(const KArgs<T> a) {
         for (int w = 0; w < W; ++w) load4(wb + w * TCP + j, wv[w]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          T rx[NC], ry[NC];
+          T s[W];
 #pragma unroll
-          for (int q = 0; q < NC; ++q) { rx[q] = wv[q][u]; ry[q] = wv[NC + q][u]; }
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-            T bx, by, bz;
-            field<T, NC>(k[s], rx, ry, wv[2 * NC][u], wv[2 * NC + 1][u], wv[2 * NC + 2][u], bx, by, bz);
-            step_fwd<T, POL, RELAX>(bx, by, bz, k[s].e1, k[s].e2, mx[s], my[s], mz[s]);
-          }
+          for (int w = 0; w < W; ++w) s[w] = wv[w][u];
+          one_step(s);
         }
       }
       for (; j < ns; ++j) {
-        T rx[NC], ry[NC];
+        T s[W];
 #pragma unroll
-        for (int q = 0; q < NC; ++q) { rx[q] = wb[q * TCP + j]; ry[q] = wb[(NC + q) * TCP + j]; }
-        const T gx = wb[2 * NC * TCP + j], gy = wb[(2 * NC + 1) * TCP + j], gz = wb[(2 * NC + 2) * TCP + j];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          T bx, by, bz;
-          field<T, NC>(k[s], rx, ry, gx, gy, gz, bx, by, bz);
-          step_fwd<T, POL, RELAX>(bx, by, bz, k[s].e1, k[s].e2, mx[s], my[s], mz[s]);
-        }
+        for (int w = 0; w < W; ++w) s[w] = wb[w * TCP + j];
+        one_step(s);
       }
       if (c + 1 < nChunks) {   // checkpoint: state after (c+1)*K steps
         T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (ok[s]) {
-            cp[idx[s]] = mx[s];
-            cp[(size_t)nM + idx[s]] = my[s];
-            cp[2 * (size_t)nM + idx[s]] = mz[s];
-          }
+        if (ok[0]) {
+          cp[idx[0]] = getq<0>(mx);
+          cp[(size_t)nM + idx[0]] = getq<0>(my);
+          cp[2 * (size_t)nM + idx[0]] = getq<0>(mz);
+        }
+        if (PK == 2 && ok[PK - 1]) {
+          cp[idx[PK - 1]] = getq<1>(mx);
+          cp[(size_t)nM + idx[PK - 1]] = getq<1>(my);
+          cp[2 * (size_t)nM + idx[PK - 1]] = getq<1>(mz);
+        }
       }
       __syncthreads();   // everyone is done with wbuf[it&1] before it is refilled
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-      if (ok[s]) {
-        T* op = a.Mo + ((size_t)n * nM + idx[s]) * 3;
-        op[0] = mx[s]; op[1] = my[s]; op[2] = mz[s];
-      }
+    if (ok[0]) {
+      T* op = a.Mo + ((size_t)n * nM + idx[0]) * 3;
+      op[0] = getq<0>(mx); op[1] = getq<0>(my); op[2] = getq<0>(mz);
+    }
+    if (PK == 2 && ok[PK - 1]) {
+      T* op = a.Mo + ((size_t)n * nM + idx[PK - 1]) * 3;
+      op[0] = getq<1>(mx); op[1] = getq<1>(my); op[2] = getq<1>(mz);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // backward
-template <typename T, int POL, bool RELAX, int NC, int S>
-__global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
-  using L = BwdSmem<T, NC>;
-  constexpr int W = L::W, TR = L::TR;
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : 1)) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
+  typedef typename Pack<T, PK>::type V;
+  using L = BwdSmem<T, NC, BLKT>;
+  constexpr int W = L::W, TR = L::TR, NW = L::NW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T(*wbuf)[W * TCMAX] = reinterpret_cast<T(*)[W * TCMAX]>(smem_raw + L::wbuf);
   T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile
@@ -243,7 +282,7 @@ __global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const 
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
   const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
   const T* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
-  const int tiles = (nM + BLK * S - 1) / (BLK * S);
+  const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);
   const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
   T* part = a.partials + ((size_t)n * a.P + blockIdx.x) * W * (size_t)nT;
@@ -258,28 +297,29 @@ __global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const 
     bulk_g2s(wbuf[0], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[0]);
   }
   if (my_tiles == 0) {   // a CTA without work still owns a partial slot: zero it
-    for (int e = tid; e < W * nT; e += BLK) part[e] = (T)0;
+    for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
     return;
   }
   uint32_t it = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
-    SpinConst<T, NC> k[S];
-    T mx[S], my[S], mz[S], hx[S], hy[S], hz[S];
-    int idx[S];
-    bool ok[S];
+    SpinConst<V, NC> k;
+    V mx, my, mz, hx, hy, hz;
+    int idx[PK];
+    bool ok[PK];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int i = (tile * S + s) * BLK + tid;
-      ok[s] = i < nM;
-      idx[s] = ok[s] ? i : nM - 1;
-      load_spin<T, NC, RELAX>(a, n, idx[s], k[s]);
-      const T* mp = a.Mo + ((size_t)n * nM + idx[s]) * 3;
-      mx[s] = mp[0]; my[s] = mp[1]; mz[s] = mp[2];
-      const T* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)idx[s] * a.gMo_sm;
-      hx[s] = ok[s] ? gp[0] : (T)0;   // padding lanes carry a zero adjoint: they add nothing
-      hy[s] = ok[s] ? gp[1] : (T)0;
-      hz[s] = ok[s] ? gp[2] : (T)0;
+    for (int q = 0; q < PK; ++q) {
+      const int i = (tile * PK + q) * BLKT + tid;
+      ok[q] = i < nM;
+      idx[q] = ok[q] ? i : nM - 1;
+    }
+    load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, k);
+    load_vec3<T, V, PK>(a.Mo + (size_t)n * nM * 3, 3, idx, mx, my, mz);
+    load_vec3<T, V, PK>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, idx, hx, hy, hz);
+    {   // padding lanes carry a zero adjoint: they add nothing to the spin sums
+      const T z0 = ok[0] ? (T)1 : (T)0, z1 = ok[PK - 1] ? (T)1 : (T)0;
+      const V zm = mkv(z0, z1, (V*)nullptr);
+      hx = hx * zm; hy = hy * zm; hz = hz * zm;
     }
     for (int c = nChunks - 1; c >= 0; --c, ++it) {
       if (tid == 0 && it + 1 < total) {
@@ -289,45 +329,56 @@ __global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const 
         bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
       }
       // prefetch the checkpoint this chunk ends on (state after c*K steps) while we compute
-      T kx[S], ky[S], kz[S];
+      V kx = mx, ky = my, kz = mz;
       if (c > 0) {
         const T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + (c - 1)) * 3 * (size_t)nM;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          kx[s] = cp[idx[s]];
-          ky[s] = cp[(size_t)nM + idx[s]];
-          kz[s] = cp[2 * (size_t)nM + idx[s]];
-        }
+        kx = mkv(cp[idx[0]], cp[idx[PK - 1]], (V*)nullptr);
+        ky = mkv(cp[(size_t)nM + idx[0]], cp[(size_t)nM + idx[PK - 1]], (V*)nullptr);
+        kz = mkv(cp[2 * (size_t)nM + idx[0]], cp[2 * (size_t)nM + idx[PK - 1]], (V*)nullptr);
       }
       mbar_wait(&full[it & 1], (it >> 1) & 1);
       const T* wb = wbuf[it & 1];
       const int ns = min(K, nT - c * K);
+      // one adjoint step; the W per-thread gradient contributions go to row `row` of the warp's tile
+      auto one_step = [&](const T (&s)[W], int row) {
+        V rx[NC], ry[NC], bx, by, bz, Fx, Fy, Fz;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) { rx[q] = V(s[q]); ry[q] = V(s[NC + q]); }
+        field<V, NC>(k, rx, ry, V(s[2 * NC]), V(s[2 * NC + 1]), V(s[2 * NC + 2]), bx, by, bz);
+        step_bwd<V, POL, RELAX, NC>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          red[warp][q][row][lane] = hsum(fma_(k.cbr[q], Fx, k.cbi[q] * Fy));
+          red[warp][NC + q][row][lane] = hsum(fnma_(k.cbi[q], Fx, k.cbr[q] * Fy));
+        }
+        red[warp][2 * NC][row][lane] = hsum(k.glx * Fz);
+        red[warp][2 * NC + 1][row][lane] = hsum(k.gly * Fz);
+        red[warp][2 * NC + 2][row][lane] = hsum(k.glz * Fz);
+      };
       for (int j1 = ns; j1 > 0;) {
         const int j0 = ((j1 - 1) / TR) * TR;   // tile [j0, j1), at most TR steps
-        for (int j = j1 - 1; j >= j0; --j) {
-          T rx[NC], ry[NC];
+        constexpr bool VEC4 = W * sizeof(T) <= 44 && TR % 4 == 0;
+        if (VEC4 && j1 - j0 == TR) {
+#pragma unroll 1
+          for (int jj = TR - 4; jj >= 0; jj -= 4) {
+            T wv[W][4];
 #pragma unroll
-          for (int q = 0; q < NC; ++q) { rx[q] = wb[q * TCP + j]; ry[q] = wb[(NC + q) * TCP + j]; }
-          const T gx = wb[2 * NC * TCP + j], gy = wb[(2 * NC + 1) * TCP + j], gz = wb[(2 * NC + 2) * TCP + j];
-          T acc[W];
+            for (int w = 0; w < W; ++w) load4(wb + w * TCP + j0 + jj, wv[w]);
 #pragma unroll
-          for (int w = 0; w < W; ++w) acc[w] = (T)0;
+            for (int u = 3; u >= 0; --u) {
+              T s[W];
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            T bx, by, bz, Fx, Fy, Fz;
-            field<T, NC>(k[s], rx, ry, gx, gy, gz, bx, by, bz);
-            step_bwd<T, POL, RELAX, NC>(k[s], bx, by, bz, mx[s], my[s], mz[s], hx[s], hy[s], hz[s], Fx, Fy, Fz);
-#pragma unroll
-            for (int q = 0; q < NC; ++q) {
-              acc[q] = fma_(k[s].cbr[q], Fx, fma_(k[s].cbi[q], Fy, acc[q]));
-              acc[NC + q] = fma_(k[s].cbr[q], Fy, fma_(-k[s].cbi[q], Fx, acc[NC + q]));
+              for (int w = 0; w < W; ++w) s[w] = wv[w][u];
+              one_step(s, jj + u);
             }
-            acc[2 * NC] = fma_(k[s].glx, Fz, acc[2 * NC]);
-            acc[2 * NC + 1] = fma_(k[s].gly, Fz, acc[2 * NC + 1]);
-            acc[2 * NC + 2] = fma_(k[s].glz, Fz, acc[2 * NC + 2]);
           }
+        } else {
+          for (int j = j1 - 1; j >= j0; --j) {
+            T s[W];
 #pragma unroll
-          for (int w = 0; w < W; ++w) red[warp][w][j - j0][lane] = acc[w];
+            for (int w = 0; w < W; ++w) s[w] = wb[w * TCP + j];
+            one_step(s, j - j0);
+          }
         }
         __syncwarp();
         {   // lane l owns row r = l%TR and sums the TR source lanes of its group (rotated start:
@@ -344,12 +395,12 @@ __global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const 
           }
         }
         __syncthreads();
-        for (int e = tid; e < W * TR; e += BLK) {   // fixed-order combine of the warps
+        for (int e = tid; e < W * TR; e += BLKT) {   // fixed-order combine of the warps
           const int w = e / TR, r = e % TR;
           if (j0 + r < j1) {
             T sum = cta[0][w][r];
 #pragma unroll
-            for (int q = 1; q < NWARP; ++q) sum += cta[q][w][r];
+            for (int q = 1; q < NW; ++q) sum += cta[q][w][r];
             T* dst = part + (size_t)w * nT + (c * K + j0 + r);
             *dst = first ? sum : *dst + sum;
           }
@@ -358,17 +409,235 @@ __global__ void __launch_bounds__(BLK) fused_bwd_kernel(const KArgs<T> a, const 
         j1 = j0;
       }
       if (c > 0) {   // resynchronise the reconstructed state with the forward checkpoint
-#pragma unroll
-        for (int s = 0; s < S; ++s) { mx[s] = kx[s]; my[s] = ky[s]; mz[s] = kz[s]; }
+        mx = kx; my = ky; mz = kz;
       }
     }
     if (need_gmi) {
+      if (ok[0]) {
+        T* op = a.gMi + ((size_t)n * nM + idx[0]) * 3;
+        op[0] = getq<0>(hx); op[1] = getq<0>(hy); op[2] = getq<0>(hz);
+      }
+      if (PK == 2 && ok[PK - 1]) {
+        T* op = a.gMi + ((size_t)n * nM + idx[PK - 1]) * 3;
+        op[0] = getq<1>(hx); op[1] = getq<1>(hy); op[2] = getq<1>(hz);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Time-packed variants (fp32, single coil): ONE spin per thread -- so twice the resident warps of the
+// spin-packed kernels for the same register file -- but the state-independent half of every step
+// (field, |b|, rsqrt, sincos, rotation coefficients) is evaluated for two consecutive time steps in
+// one f2 (FFMA2).  Only the short recurrent part (apply_fwd / apply_bwd) runs once per step in scalar.
+template <int POL, bool RELAX, int BLKT>
+__global__ void __launch_bounds__(BLKT) fused_fwd_tp_kernel(const KArgs<float> a) {
+  constexpr int W = 5;
+  __shared__ __align__(128) float wbuf[2][W * TCMAX];
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x, n = blockIdx.y;
+  const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
+  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(float));
+  const float* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
+  const int tiles = (nM + BLKT - 1) / BLKT;
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && total > 0) {
+    mbar_arrive_expect_tx(&full[0], chunk_bytes);
+    bulk_g2s(wbuf[0], wave_n, chunk_bytes, &full[0]);
+  }
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    SpinConst<float, 1> k;
+    const int i = tile * BLKT + tid;
+    const bool ok = i < nM;
+    const int idx = ok ? i : nM - 1;
+    load_spin<float, 1, RELAX>(a, n, idx, k);
+    const float* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)idx * a.Mi_sm;
+    float mx = mp[0], my = mp[1], mz = mp[2];
+    for (int c = 0; c < nChunks; ++c, ++it) {
+      if (tid == 0 && it + 1 < total) {
+        const int cn = (c + 1 == nChunks) ? 0 : c + 1;
+        const uint32_t sn = (it + 1) & 1;
+        mbar_arrive_expect_tx(&full[sn], chunk_bytes);
+        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
+      }
+      mbar_wait(&full[it & 1], (it >> 1) & 1);
+      const float* wb = wbuf[it & 1];
+      const int ns = min(K, nT - c * K);
+      auto two_steps = [&](f2 rx, f2 ry, f2 gx, f2 gy, f2 gz) {   // .x = step t, .y = step t+1
+        f2 bx, by, bz;
+        field_tp(k, rx, ry, gx, gy, gz, bx, by, bz);
+        const RotCoef<f2> r = rot_coef<f2, POL>(bx, by, bz);
+        apply_fwd<float, RELAX>(lane_x(r), bx.v.x, by.v.x, bz.v.x, k.e1, k.e2, mx, my, mz);
+        apply_fwd<float, RELAX>(lane_y(r), bx.v.y, by.v.y, bz.v.y, k.e1, k.e2, mx, my, mz);
+      };
+      int j = 0;
+      for (; j + 4 <= ns; j += 4) {
+        float wv[W][4];
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (ok[s]) {
-          T* op = a.gMi + ((size_t)n * nM + idx[s]) * 3;
-          op[0] = hx[s]; op[1] = hy[s]; op[2] = hz[s];
+        for (int w = 0; w < W; ++w) load4(wb + w * TCP + j, wv[w]);
+        two_steps(f2(wv[0][0], wv[0][1]), f2(wv[1][0], wv[1][1]), f2(wv[2][0], wv[2][1]), f2(wv[3][0], wv[3][1]),
+                  f2(wv[4][0], wv[4][1]));
+        two_steps(f2(wv[0][2], wv[0][3]), f2(wv[1][2], wv[1][3]), f2(wv[2][2], wv[2][3]), f2(wv[3][2], wv[3][3]),
+                  f2(wv[4][2], wv[4][3]));
+      }
+      for (; j < ns; ++j) {
+        float bx, by, bz;
+        const float rx = wb[j], ry = wb[TCP + j];
+        field<float, 1>(k, &rx, &ry, wb[2 * TCP + j], wb[3 * TCP + j], wb[4 * TCP + j], bx, by, bz);
+        step_fwd<float, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
+      }
+      if (c + 1 < nChunks && ok) {
+        float* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
+        cp[idx] = mx; cp[(size_t)nM + idx] = my; cp[2 * (size_t)nM + idx] = mz;
+      }
+      __syncthreads();
+    }
+    if (ok) {
+      float* op = a.Mo + ((size_t)n * nM + idx) * 3;
+      op[0] = mx; op[1] = my; op[2] = mz;
+    }
+  }
+}
+
+template <int POL, bool RELAX, int BLKT>
+__global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a, const int need_gmi) {
+  using L = BwdSmem<float, 1, BLKT>;
+  constexpr int W = L::W, TR = L::TR, NW = L::NW;
+  static_assert(TR % 4 == 0, "time-packed backward expects 4-step groups");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float(*wbuf)[W * TCMAX] = reinterpret_cast<float(*)[W * TCMAX]>(smem_raw + L::wbuf);
+  float(*red)[W][TR][32] = reinterpret_cast<float(*)[W][TR][32]>(smem_raw + L::red);
+  float(*cta)[W][TR] = reinterpret_cast<float(*)[W][TR]>(smem_raw + L::cta);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::bar);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.y;
+  const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
+  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(float));
+  const float* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
+  const int tiles = (nM + BLKT - 1) / BLKT;
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
+  float* part = a.partials + ((size_t)n * a.P + blockIdx.x) * W * (size_t)nT;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0 && total > 0) {
+    mbar_arrive_expect_tx(&full[0], chunk_bytes);
+    bulk_g2s(wbuf[0], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[0]);
+  }
+  if (my_tiles == 0) {
+    for (int e = tid; e < W * nT; e += BLKT) part[e] = 0.f;
+    return;
+  }
+  uint32_t it = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
+    SpinConst<float, 1> k;
+    const int i = tile * BLKT + tid;
+    const bool ok = i < nM;
+    const int idx = ok ? i : nM - 1;
+    load_spin<float, 1, RELAX>(a, n, idx, k);
+    const float* mp = a.Mo + ((size_t)n * nM + idx) * 3;
+    float mx = mp[0], my = mp[1], mz = mp[2];
+    const float* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)idx * a.gMo_sm;
+    float hx = ok ? gp[0] : 0.f, hy = ok ? gp[1] : 0.f, hz = ok ? gp[2] : 0.f;
+    auto emit = [&](float Fx, float Fy, float Fz, int row) {
+      red[warp][0][row][lane] = fmaf(k.cbr[0], Fx, k.cbi[0] * Fy);
+      red[warp][1][row][lane] = fmaf(-k.cbi[0], Fx, k.cbr[0] * Fy);
+      red[warp][2][row][lane] = k.glx * Fz;
+      red[warp][3][row][lane] = k.gly * Fz;
+      red[warp][4][row][lane] = k.glz * Fz;
+    };
+    for (int c = nChunks - 1; c >= 0; --c, ++it) {
+      if (tid == 0 && it + 1 < total) {
+        const int cn = (c == 0) ? nChunks - 1 : c - 1;
+        const uint32_t sn = (it + 1) & 1;
+        mbar_arrive_expect_tx(&full[sn], chunk_bytes);
+        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
+      }
+      float kx = mx, ky = my, kz = mz;
+      if (c > 0) {   // prefetch the checkpoint this chunk ends on
+        const float* cp = a.ckpt + ((size_t)n * (nChunks - 1) + (c - 1)) * 3 * (size_t)nM;
+        kx = cp[idx]; ky = cp[(size_t)nM + idx]; kz = cp[2 * (size_t)nM + idx];
+      }
+      mbar_wait(&full[it & 1], (it >> 1) & 1);
+      const float* wb = wbuf[it & 1];
+      const int ns = min(K, nT - c * K);
+      // .x = step t (row_lo), .y = step t+1 (row_lo+1); time runs backwards: .y first
+      auto two_steps = [&](f2 rx, f2 ry, f2 gx, f2 gy, f2 gz, int row_lo) {
+        f2 bx, by, bz;
+        field_tp(k, rx, ry, gx, gy, gz, bx, by, bz);
+        const RotCoef<f2> r = rot_coef<f2, POL>(bx, by, bz);
+        float Fx, Fy, Fz;
+        apply_bwd<float, RELAX, 1>(k, lane_y(r), bx.v.y, by.v.y, bz.v.y, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+        emit(Fx, Fy, Fz, row_lo + 1);
+        apply_bwd<float, RELAX, 1>(k, lane_x(r), bx.v.x, by.v.x, bz.v.x, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+        emit(Fx, Fy, Fz, row_lo);
+      };
+      for (int j1 = ns; j1 > 0;) {
+        const int j0 = ((j1 - 1) / TR) * TR;
+        if (j1 - j0 == TR) {
+#pragma unroll 1
+          for (int jj = TR - 4; jj >= 0; jj -= 4) {
+            float wv[W][4];
+#pragma unroll
+            for (int w = 0; w < W; ++w) load4(wb + w * TCP + j0 + jj, wv[w]);
+            two_steps(f2(wv[0][2], wv[0][3]), f2(wv[1][2], wv[1][3]), f2(wv[2][2], wv[2][3]), f2(wv[3][2], wv[3][3]),
+                      f2(wv[4][2], wv[4][3]), jj + 2);
+            two_steps(f2(wv[0][0], wv[0][1]), f2(wv[1][0], wv[1][1]), f2(wv[2][0], wv[2][1]), f2(wv[3][0], wv[3][1]),
+                      f2(wv[4][0], wv[4][1]), jj);
+          }
+        } else {
+          for (int j = j1 - 1; j >= j0; --j) {
+            float bx, by, bz, Fx, Fy, Fz;
+            const float rx = wb[j], ry = wb[TCP + j];
+            field<float, 1>(k, &rx, &ry, wb[2 * TCP + j], wb[3 * TCP + j], wb[4 * TCP + j], bx, by, bz);
+            step_bwd<float, POL, RELAX, 1>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+            emit(Fx, Fy, Fz, j - j0);
+          }
         }
+        __syncwarp();
+        {
+          const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            float sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < TR; ++q) sum += red[warp][w][r][grp + ((q + lane) & (TR - 1))];
+#pragma unroll
+            for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane < TR) cta[warp][w][r] = sum;
+          }
+        }
+        __syncthreads();
+        for (int e = tid; e < W * TR; e += BLKT) {
+          const int w = e / TR, r = e % TR;
+          if (j0 + r < j1) {
+            float sum = cta[0][w][r];
+#pragma unroll
+            for (int q = 1; q < NW; ++q) sum += cta[q][w][r];
+            float* dst = part + (size_t)w * nT + (c * K + j0 + r);
+            *dst = first ? sum : *dst + sum;
+          }
+        }
+        __syncthreads();
+        j1 = j0;
+      }
+      if (c > 0) { mx = kx; my = ky; mz = kz; }
+    }
+    if (need_gmi && ok) {
+      float* op = a.gMi + ((size_t)n * nM + idx) * 3;
+      op[0] = hx; op[1] = hy; op[2] = hz;
     }
   }
 }
@@ -472,10 +741,12 @@ namespace {
 
 struct Plan {
   int NC;        // coils held in registers (1,2,4,8)
-  int S;         // spins per thread
+  int PK;        // spins per thread (2 = packed f2 arithmetic, fp32 single-coil only)
+  int BLKT;      // threads per CTA
   int K, TCP, nChunks, W;
   int sum_coils; // no b1Map
-  int tiles, P;
+  int tiles;     // spin tiles per batch entry (BLKT*PK spins each)
+  int Pmax;      // upper bound on CTAs per batch entry (sizes the partial-sum workspace)
 };
 
 int sm_count_cached() {
@@ -490,10 +761,17 @@ int sm_count_cached() {
   return sms;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return v > 0 ? v : dflt;
+}
+
 int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
   if (a->dtype != MRPHY_F32 && a->dtype != MRPHY_F64) return fail(MRPHY_ERR_ARG, "dtype must be MRPHY_F32 or MRPHY_F64%s");
-  if (a->N < 1 || a->nM < 1 || a->nT < 1 || a->nC < 1) return fail(MRPHY_ERR_ARG, "N, nM, nT, nC must be >= 1%s");
+  if (a->N < 1 || a->nM < 1 || a->nT < 1 || a->nC < 1 || a->N > 65535) return fail(MRPHY_ERR_ARG, "need 1 <= N <= 65535 and nM, nT, nC >= 1%s");
   if (a->K < 1 || a->K > TCMAX) return fail(MRPHY_ERR_ARG, "checkpoint interval K must be in [1, 64]%s");
   p->sum_coils = a->b1 == nullptr;
   const int nc = p->sum_coils ? 1 : a->nC;
@@ -503,18 +781,38 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   p->K = a->K;
   p->TCP = (a->K + 3) & ~3;
   p->nChunks = (a->nT + a->K - 1) / a->K;
-  p->S = 1;
-  p->tiles = (a->nM + BLK * p->S - 1) / (BLK * p->S);
-  // grid: one tile per CTA while that stays within 8 resident waves, else a grid-stride loop
-  int cap = (need_device ? sm_count_cached() : 148) * 8 * 8;
-  if (const char* e = getenv("MRPHY_B200_MAX_CTAS")) {   // tests use it to force the multi-tile path
-    const int v = atoi(e);
-    if (v > 0) cap = v;
-  }
+  // fp32 single-coil fast paths (FFMA2): 2 = two spins per thread (default, fastest measured); 3 = time-packed,
+  // one spin per thread; MRPHY_B200_PACK=1 forces the scalar kernels that also serve fp64 and multi-coil
+  const int want = env_int("MRPHY_B200_PACK", 2);
+  p->PK = (a->dtype == MRPHY_F32 && p->NC == 1 && (want == 2 || want == 3)) ? want : 1;
+  p->BLKT = p->PK == 2 ? 64 : 128;
+  p->tiles = (a->nM + p->BLKT * (p->PK == 2 ? 2 : 1) - 1) / (p->BLKT * (p->PK == 2 ? 2 : 1));
+  const int sms = need_device ? sm_count_cached() : 148;
+  const int cap = env_int("MRPHY_B200_MAX_CTAS", sms * 32);   // 32 CTAs/SM is the hardware limit
   int P = p->tiles;
   if ((int64_t)P * a->N > cap) P = cap / a->N > 0 ? cap / a->N : 1;
-  p->P = P;
+  p->Pmax = P;
   return MRPHY_OK;
+}
+
+// CTAs per batch entry: all CTAs co-resident (one wave), c CTAs per SM chosen so that the tiles split
+// evenly -- minimise passes(c) * c over c in [occ/2, occ]; e.g. 64^3 spins on 148 SMs: c = 7, 2 passes.
+int pick_ctas(const Plan& p, int N, int occ) {
+  const int sms = sm_count_cached();
+  occ = occ < 1 ? 1 : occ;
+  const int forced = env_int("MRPHY_B200_CTAS_PER_SM", 0);
+  int best_P = 1, best_cost = 1 << 30;
+  for (int c = occ; c >= (occ + 1) / 2; --c) {
+    if (forced) c = forced < occ ? forced : occ;
+    int P = (int)((int64_t)sms * c / N);
+    if (P < 1) P = 1;
+    if (P > p.Pmax) P = p.Pmax;
+    const int passes = (p.tiles + P - 1) / P;
+    const int cost = passes * c;
+    if (cost < best_cost) { best_cost = cost; best_P = P; }
+    if (forced) break;
+  }
+  return best_P;
 }
 
 }  // namespace
@@ -533,7 +831,7 @@ extern "C" size_t mrphy_fused_wave_elems(const mrphy_fused_args* a) {
 extern "C" size_t mrphy_fused_partial_elems(const mrphy_fused_args* a) {
   Plan p;
   if (make_plan(a, &p, true) != MRPHY_OK) return 0;
-  return (size_t)a->N * p.P * p.W * (size_t)a->nT;
+  return (size_t)a->N * p.Pmax * p.W * (size_t)a->nT;
 }
 
 namespace {
@@ -554,7 +852,7 @@ template <typename T>
 KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
   KArgs<T> k;
   memset(&k, 0, sizeof(k));
-  k.N = a->N; k.nM = a->nM; k.nT = a->nT; k.K = p.K; k.TCP = p.TCP; k.nChunks = p.nChunks; k.P = p.P;
+  k.N = a->N; k.nM = a->nM; k.nT = a->nT; k.K = p.K; k.TCP = p.TCP; k.nChunks = p.nChunks; k.P = p.Pmax;
   k.Mi = (const T*)a->Mi; k.Mi_sn = a->Mi_sn; k.Mi_sm = a->Mi_sm;
   k.loc = (const T*)a->loc; k.loc_sn = a->loc_sn; k.loc_sm = a->loc_sm;
   k.b1 = (const T*)a->b1; k.b1_sn = a->b1_sn; k.b1_sm = a->b1_sm; k.nC = a->nC;
@@ -578,25 +876,68 @@ int launch_pack(const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
   return MRPHY_OK;
 }
 
-template <typename T, int POL, bool RELAX, int NC>
-int launch_fwd_s(const KArgs<T>& k, const Plan& p, cudaStream_t st) {
-  dim3 grid(p.P, k.N);
+// P (CTAs per batch entry) actually launched by the last backward kernel; the finalize kernel needs it
+thread_local int g_last_P = 0;
+
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+int launch_fwd_s(KArgs<T> k, const Plan& p, cudaStream_t st) {
+  auto kern = fused_fwd_kernel<T, POL, RELAX, NC, PK, BLKT>;
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, 0));
+  k.P = pick_ctas(p, k.N, occ);
+  dim3 grid(k.P, k.N);
   timing_begin(st);
-  fused_fwd_kernel<T, POL, RELAX, NC, 1><<<grid, BLK, 0, st>>>(k);
+  kern<<<grid, BLKT, 0, st>>>(k);
   timing_end(st);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;
 }
-template <typename T, int POL, bool RELAX, int NC>
-int launch_bwd_s(const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
-  dim3 grid(p.P, k.N);
-  constexpr size_t smem = BwdSmem<T, NC>::bytes;
-  auto kern = fused_bwd_kernel<T, POL, RELAX, NC, 1>;
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
+  constexpr size_t smem = BwdSmem<T, NC, BLKT>::bytes;
+  auto kern = fused_bwd_kernel<T, POL, RELAX, NC, PK, BLKT>;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
+  k.P = pick_ctas(p, k.N, occ);
+  g_last_P = k.P;
+  dim3 grid(k.P, k.N);
   timing_begin(st);
-  kern<<<grid, BLK, smem, st>>>(k, need_gmi);
+  kern<<<grid, BLKT, smem, st>>>(k, need_gmi);
   timing_end(st);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+int launch_any(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
+  return bwd ? launch_bwd_s<T, POL, RELAX, NC, PK, BLKT>(k, p, need_gmi, st)
+             : launch_fwd_s<T, POL, RELAX, NC, PK, BLKT>(k, p, st);
+}
+
+template <int POL, bool RELAX, int BLKT>
+int launch_tp(bool bwd, KArgs<float> k, const Plan& p, int need_gmi, cudaStream_t st) {
+  int occ = 0;
+  if (bwd) {
+    constexpr size_t smem = BwdSmem<float, 1, BLKT>::bytes;
+    auto kern = fused_bwd_tp_kernel<POL, RELAX, BLKT>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
+    k.P = pick_ctas(p, k.N, occ);
+    g_last_P = k.P;
+    timing_begin(st);
+    kern<<<dim3(k.P, k.N), BLKT, smem, st>>>(k, need_gmi);
+    timing_end(st);
+  } else {
+    auto kern = fused_fwd_tp_kernel<POL, RELAX, BLKT>;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, 0));
+    k.P = pick_ctas(p, k.N, occ);
+    timing_begin(st);
+    kern<<<dim3(k.P, k.N), BLKT, 0, st>>>(k);
+    timing_end(st);
+  }
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;
@@ -604,11 +945,15 @@ int launch_bwd_s(const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st
 
 template <typename T, int POL, bool RELAX>
 int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    if (p.PK == 3) return launch_tp<POL, RELAX, 128>(bwd, k, p, need_gmi, st);
+    if (p.PK == 2) return launch_any<T, POL, RELAX, 1, 2, 64>(bwd, k, p, need_gmi, st);
+  }
   switch (p.NC) {
-    case 1: return bwd ? launch_bwd_s<T, POL, RELAX, 1>(k, p, need_gmi, st) : launch_fwd_s<T, POL, RELAX, 1>(k, p, st);
-    case 2: return bwd ? launch_bwd_s<T, POL, RELAX, 2>(k, p, need_gmi, st) : launch_fwd_s<T, POL, RELAX, 2>(k, p, st);
-    case 4: return bwd ? launch_bwd_s<T, POL, RELAX, 4>(k, p, need_gmi, st) : launch_fwd_s<T, POL, RELAX, 4>(k, p, st);
-    case 8: return bwd ? launch_bwd_s<T, POL, RELAX, 8>(k, p, need_gmi, st) : launch_fwd_s<T, POL, RELAX, 8>(k, p, st);
+    case 1: return launch_any<T, POL, RELAX, 1, 1, 128>(bwd, k, p, need_gmi, st);
+    case 2: return launch_any<T, POL, RELAX, 2, 1, 128>(bwd, k, p, need_gmi, st);
+    case 4: return launch_any<T, POL, RELAX, 4, 1, 128>(bwd, k, p, need_gmi, st);
+    case 8: return launch_any<T, POL, RELAX, 8, 1, 128>(bwd, k, p, need_gmi, st);
   }
   return fail(MRPHY_ERR_ARG, "internal: bad NC%s");
 }
@@ -646,7 +991,7 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, cudaStream_t st) {
   if (!wave_is_packed && (rc = launch_pack<T>(a, p, st))) return rc;
   if ((rc = dispatch<T>(true, a, p, st))) return rc;
   dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 8);
-  grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, p.P, p.W, p.NC, a->nC, a->nT,
+  grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT,
                                                   (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T*)a->grf,
                                                   (T*)a->ggr);
   ++g_launches;

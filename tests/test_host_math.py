@@ -27,7 +27,7 @@ def ptr(a):
 
 def run(lib, dtype, pol, g, K, relax=True):
     """g: fixture dict with in_* keys for a single-coil N=1 case."""
-    T = np.float32 if dtype == 'f32' else np.float64
+    T = np.float64 if dtype == 'f64' else np.float32
     M0 = np.ascontiguousarray(g['in_M0'][0], dtype=T)
     nM = M0.shape[0]
     rf = np.ascontiguousarray(g['in_rf'][0].reshape(2, -1), dtype=T)
@@ -45,7 +45,7 @@ def run(lib, dtype, pol, g, K, relax=True):
     Mo, gM0 = np.zeros((nM, 3), T), np.zeros((nM, 3), T)
     grf, ggr = np.zeros((2, nT)), np.zeros((3, nT))
     err = np.zeros(1, T)
-    fn = lib.host_sim_f32 if dtype == 'f32' else lib.host_sim_f64
+    fn = {'f32': lib.host_sim_f32, 'f32x2': lib.host_sim_f32x2, 'f64': lib.host_sim_f64}[dtype]
     fn(ctypes.c_int(pol), ctypes.c_int(int(relax and T1 is not None)), ctypes.c_int(nM), ctypes.c_int(nT),
        ctypes.c_int(K), ptr(M0), ptr(rf), ptr(gr), ptr(loc), ptr(b1), ptr(df), ptr(T1), ptr(T2), ptr(gam),
        ctypes.c_double(float(np.asarray(g['in_dt']).reshape(-1)[0])), ptr(gMo), ptr(Mo), ptr(gM0), ptr(grf), ptr(ggr),
@@ -100,6 +100,20 @@ def test_f32_formulation_noise_floor(lib, golden, pol):
               f'grf rel={rel(grf, g["grf_f64"][0].reshape(2, -1)):.2e} ggr rel={rel(ggr, g["ggr_f64"][0]):.2e}')
         assert dM < max(1e-5, 1.5 * floor)
         assert rel(grf, g['grf_f64'][0].reshape(2, -1)) < 1e-4 and rel(ggr, g['ggr_f64'][0]) < 1e-4
+
+
+@pytest.mark.parametrize('pol', [0, 1])
+def test_packed_f2_path_equals_scalar_path(lib, golden, pol):
+    """The two-spins-per-thread formulation (FFMA2 on the device) is the same arithmetic as the scalar one."""
+    g = golden('bench8')
+    g = dict(g, in_w=2 * (g['Mo_f64'] - np.array([0., 1., 0.])))
+    a = run(lib, 'f32', pol, g, 64)
+    b = run(lib, 'f32x2', pol, g, 64)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert rel(b[2], a[2]) < 1e-6 and rel(b[3], a[3]) < 1e-6
+    g2 = golden('rand_norelax')
+    a, b = run(lib, 'f32', pol, g2, 16), run(lib, 'f32x2', pol, g2, 16)
+    assert np.array_equal(a[0][:32], b[0][:32]) and np.array_equal(a[1][:32], b[1][:32])
 
 
 def test_kat3_through_formulation(lib, golden):
