@@ -128,6 +128,42 @@ size_t mrphy_beff_ckpt_elems(const mrphy_beff_args* a);
 int mrphy_blochsim_beff_fwd(const mrphy_beff_args* a, void* cuda_stream);
 int mrphy_blochsim_beff_bwd(const mrphy_beff_args* a, void* cuda_stream);
 
+/* Standalone field synthesis, replacing beffective.rfgr2beff (beffective.py:107-168) for callers that
+ * want the dense field: Beff (N,nM,nT,3) contiguous out.  HBM-bound: 12 B/spin.step written (fp32). */
+typedef struct mrphy_rfgr2beff_args {
+  int32_t dtype, flags;  /* MRPHY_RF_COIL_DIM */
+  int32_t N, nM, nT, nC;
+  const void* rf; int64_t rf_sn, rf_sx, rf_st, rf_sc;
+  const void* gr; int64_t gr_sn, gr_sx, gr_st;
+  const void* loc; int64_t loc_sn, loc_sm;            /* inner stride 1 */
+  const void* b1; int64_t b1_sn, b1_sm;               /* (N,nM,2,nC) inner contiguous, or NULL */
+  mrphy_param df, gamma;                              /* df.ptr NULL = no off-resonance */
+  void* Beff;
+} mrphy_rfgr2beff_args;
+int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream);
+
+/* Hargreaves A/B propagation, replacing beffective.beff2ab (beffective.py:40-104), forward only:
+ * A (N,nM,3,3), B (N,nM,3) contiguous out; E1, E2 are the per-step relaxation FACTORS as upstream. */
+typedef struct mrphy_beff2ab_args {
+  int32_t dtype, flags;
+  int32_t N, nM, nT, _pad;
+  const void* Beff; int64_t B_sn, B_sm;               /* (N,nM,nT,3), (nT,3) contiguous */
+  mrphy_param E1, E2, gamma, dt;
+  void* A; void* B;
+} mrphy_beff2ab_args;
+int mrphy_beff2ab(const mrphy_beff2ab_args* a, void* cuda_stream);
+
+/* Free precession, replacing sims.FreePrec.forward / .backward (sims.py:325-421): rotate about z by
+ * -2*pi*df*dur then relax over dur (adjoint != 0: the transposed map applied to dL/dMo).            */
+typedef struct mrphy_freeprec_args {
+  int32_t dtype, adjoint;
+  int32_t N, nM;
+  const void* Mi; int64_t Mi_sn, Mi_sm;               /* (N,nM,3) inner stride 1 */
+  mrphy_param dur, T1, T2, df;                        /* T1/T2 both NULL = no relaxation; df NULL = no precession */
+  void* Mo;                                           /* (N,nM,3) contiguous */
+} mrphy_freeprec_args;
+int mrphy_freeprec(const mrphy_freeprec_args* a, void* cuda_stream);
+
 /* Number of kernel launches the last forward / backward call on this thread issued. */
 int mrphy_last_launch_count(void);
 

@@ -1,0 +1,160 @@
+// Stand-alone operators around the fused path, sm_100a: rfgr2beff (dense field synthesis), beff2ab
+// (Hargreaves A/B propagation) and freeprec.  All are HBM-bound / one-shot; they exist so that every function of
+// the reference's path (a3, a5, f-1) has a native implementation behind the same C ABI.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/mrphy_b200.h"
+#include "abi_common.cuh"
+#include "bloch_math.cuh"
+
+namespace mrphy {
+
+// ---- rfgr2beff (beffective.py:107-168) -------------------------------------------------------------
+// Threads run along time for one spin: the three components of 32 consecutive steps are 384 contiguous
+// bytes, so stores are fully coalesced; the spin's constants are warp-uniform (broadcast loads).
+template <typename T>
+__global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
+  const int n = blockIdx.y;
+  const int64_t bid = blockIdx.x;
+  const int i = (int)(bid / tblocks);
+  const int t = (int)(bid % tblocks) * 256 + threadIdx.x;
+  if (t >= a.nT) return;
+  const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
+  const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
+  const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
+  T bx = 0, by = 0;
+  if (a.b1) {
+    const T* bp = (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;
+    for (int c = 0; c < a.nC; ++c) {     // Re/Im of b1*rf summed over coils (beffective.py:160-165)
+      const T rx = rf[c * a.rf_sc], ry = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
+      bx += br * rx - bi * ry;
+      by += br * ry + bi * rx;
+    }
+  } else {
+    for (int c = 0; c < a.nC; ++c) { bx += rf[c * a.rf_sc]; by += rf[a.rf_sx + c * a.rf_sc]; }
+  }
+  T bz = lp[0] * gr[0] + lp[1] * gr[a.gr_sx] + lp[2] * gr[2 * a.gr_sx];
+  if (a.df.ptr) bz += (T)(ld_param(a.df, n, i) / ld_param(a.gamma, n, i));
+  T* o = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + t) * 3;
+  o[0] = bx; o[1] = by; o[2] = bz;
+}
+
+// ---- beff2ab (beffective.py:40-104) ----------------------------------------------------------------
+// One spin per thread, [A|B] = 4 column vectors in registers, same rotation + relaxation per step as the
+// simulation (apply_fwd with the relaxation constants given as factors).
+template <typename T, int POL>
+__global__ void __launch_bounds__(128) beff2ab_kernel(const mrphy_beff2ab_args a) {
+  const int n = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= a.nM) return;
+  const double gam = ld_param(a.gamma, n, i), dt = ld_param(a.dt, n, 0);
+  const T g = (T)(6.283185307179586476925286766559 * gam * dt);
+  const T E1 = (T)ld_param(a.E1, n, i), E2 = (T)ld_param(a.E2, n, i);
+  const T e1 = E1 - (T)1, e2 = E2 - (T)1;
+  T cx[4] = {1, 0, 0, 0}, cy[4] = {0, 1, 0, 0}, cz[4] = {0, 0, 1, 0};   // columns of [A|B]
+  const T* B = (const T*)a.Beff + (int64_t)n * a.B_sn + (int64_t)i * a.B_sm;
+  for (int t = 0; t < a.nT; ++t) {
+    const T bx = g * B[3 * t], by = g * B[3 * t + 1], bz = g * B[3 * t + 2];
+    const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // rotate, then scale by (E2,E2,E1); only the B column receives the recovery term (1-E1)
+      apply_fwd<T, false>(r, bx, by, bz, (T)0, (T)0, cx[q], cy[q], cz[q]);
+      cx[q] = fma_(e2, cx[q], cx[q]);
+      cy[q] = fma_(e2, cy[q], cy[q]);
+      cz[q] = fma_(e1, cz[q], cz[q]);
+    }
+    cz[3] -= e1;
+  }
+  T* A = (T*)a.A + ((int64_t)n * a.nM + i) * 9;
+  T* Bo = (T*)a.B + ((int64_t)n * a.nM + i) * 3;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) { A[q] = cx[q]; A[3 + q] = cy[q]; A[6 + q] = cz[q]; }
+  Bo[0] = cx[3]; Bo[1] = cy[3]; Bo[2] = cz[3];
+}
+
+// ---- freeprec (sims.py:325-421) --------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) freeprec_kernel(const mrphy_freeprec_args a) {
+  const int n = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.nM) return;
+  const T* mp = (const T*)a.Mi + (int64_t)n * a.Mi_sn + (int64_t)i * a.Mi_sm;
+  double x = mp[0], y = mp[1], z = mp[2];
+  const double dur = ld_param(a.dur, n, 0);
+  double c = 1.0, s = 0.0, E1 = 1.0, E2 = 1.0, rec = 0.0;
+  if (a.df.ptr) sincos(-6.283185307179586476925286766559 * ld_param(a.df, n, i) * dur, &s, &c);
+  if (a.T1.ptr) {
+    const double x1 = -dur / ld_param(a.T1, n, i);
+    E1 = exp(x1); E2 = exp(-dur / ld_param(a.T2, n, i)); rec = -expm1(x1);
+  }
+  double ox, oy, oz;
+  if (!a.adjoint) {       // rotate then relax (sims.py:345-369)
+    ox = E2 * (c * x - s * y); oy = E2 * (s * x + c * y); oz = E1 * z + rec;
+  } else {                // transposed map on the incoming gradient (sims.py:403-419)
+    const double gx = E2 * x, gy = E2 * y;
+    ox = c * gx + s * gy; oy = c * gy - s * gx; oz = E1 * z;
+  }
+  T* op = (T*)a.Mo + ((int64_t)n * a.nM + i) * 3;
+  op[0] = (T)ox; op[1] = (T)oy; op[2] = (T)oz;
+}
+
+}  // namespace mrphy
+
+using namespace mrphy;
+
+#define BEGIN_CALL()       \
+  launch_count() = 0;      \
+  err_buf()[0] = 0;        \
+  if (!a) return fail(MRPHY_ERR_ARG, "null args%s")
+#define DTYPE_OK(a) ((a)->dtype == MRPHY_F32 || (a)->dtype == MRPHY_F64)
+
+extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1 || a->nT < 1 || a->nC < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (!a->rf || !a->gr || !a->loc || !a->Beff) return fail(MRPHY_ERR_ARG, "rf, gr, loc, Beff are required%s");
+  if (a->df.ptr && !a->gamma.ptr) return fail(MRPHY_ERR_ARG, "df needs gamma%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int tblocks = (a->nT + 255) / 256;
+  const int64_t gx = (int64_t)a->nM * tblocks;
+  if (gx > 2147483647LL) return fail(MRPHY_ERR_ARG, "nM*nT too large for one launch%s");
+  dim3 grid((unsigned)gx, a->N);
+  timing_begin(st);
+  if (a->dtype == MRPHY_F64) rfgr2beff_kernel<double><<<grid, 256, 0, st>>>(*a, tblocks);
+  else rfgr2beff_kernel<float><<<grid, 256, 0, st>>>(*a, tblocks);
+  timing_end(st);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+extern "C" int mrphy_beff2ab(const mrphy_beff2ab_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1 || a->nT < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (!a->Beff || !a->A || !a->B || !a->E1.ptr || !a->E2.ptr || !a->gamma.ptr || !a->dt.ptr) return fail(MRPHY_ERR_ARG, "Beff, A, B, E1, E2, gamma, dt are required%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  dim3 grid((a->nM + 127) / 128, a->N);
+  const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0;
+  timing_begin(st);
+  if (a->dtype == MRPHY_F64) beff2ab_kernel<double, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+  else if (precise) beff2ab_kernel<float, TRIG_PRECISE><<<grid, 128, 0, st>>>(*a);
+  else beff2ab_kernel<float, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+  timing_end(st);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+extern "C" int mrphy_freeprec(const mrphy_freeprec_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (!a->Mi || !a->Mo || !a->dur.ptr) return fail(MRPHY_ERR_ARG, "Mi, Mo, dur are required%s");
+  if ((a->T1.ptr == nullptr) != (a->T2.ptr == nullptr)) return fail(MRPHY_ERR_ARG, "T1 and T2: both or neither%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  dim3 grid((a->nM + 255) / 256, a->N);
+  if (a->dtype == MRPHY_F64) freeprec_kernel<double><<<grid, 256, 0, st>>>(*a);
+  else freeprec_kernel<float><<<grid, 256, 0, st>>>(*a);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}

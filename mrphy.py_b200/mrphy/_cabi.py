@@ -50,6 +50,36 @@ class BeffArgs(ctypes.Structure):
     ]
 
 
+class RfGr2BeffArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('nC', c_i32),
+        ('rf', c_vp), ('rf_sn', c_i64), ('rf_sx', c_i64), ('rf_st', c_i64), ('rf_sc', c_i64),
+        ('gr', c_vp), ('gr_sn', c_i64), ('gr_sx', c_i64), ('gr_st', c_i64),
+        ('loc', c_vp), ('loc_sn', c_i64), ('loc_sm', c_i64),
+        ('b1', c_vp), ('b1_sn', c_i64), ('b1_sm', c_i64),
+        ('df', Param), ('gamma', Param),
+        ('Beff', c_vp),
+    ]
+
+
+class Beff2abArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('_pad', c_i32),
+        ('Beff', c_vp), ('B_sn', c_i64), ('B_sm', c_i64),
+        ('E1', Param), ('E2', Param), ('gamma', Param), ('dt', Param),
+        ('A', c_vp), ('B', c_vp),
+    ]
+
+
+class FreePrecArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('adjoint', c_i32), ('N', c_i32), ('nM', c_i32),
+        ('Mi', c_vp), ('Mi_sn', c_i64), ('Mi_sm', c_i64),
+        ('dur', Param), ('T1', Param), ('T2', Param), ('df', Param),
+        ('Mo', c_vp),
+    ]
+
+
 EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mrphy_b200.h declares
     'mrphy_abi_version': (ctypes.c_int, []),
     'mrphy_last_error': (ctypes.c_char_p, []),
@@ -65,6 +95,9 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_beff_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(BeffArgs)]),
     'mrphy_blochsim_beff_fwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
     'mrphy_blochsim_beff_bwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
+    'mrphy_rfgr2beff': (ctypes.c_int, [ctypes.POINTER(RfGr2BeffArgs), c_vp]),
+    'mrphy_beff2ab': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),
+    'mrphy_freeprec': (ctypes.c_int, [ctypes.POINTER(FreePrecArgs), c_vp]),
 }
 
 _lib = None

@@ -51,6 +51,22 @@ def _param(t: Optional[Tensor], N: int, nM: int, per_batch_only=False) -> _cabi.
     return p
 
 
+def flat_param(x: Optional[Tensor], N: int, Nd: tuple, device) -> Optional[Tensor]:
+    """(), (N|1,), (N|1, *Nd|1.., [1, 1])-style constant -> (N|1, nM|1) view (copy only for partial broadcasts)."""
+    if x is None:
+        return None
+    x = x.to(device=device)
+    while x.ndim > 1 + len(Nd):
+        assert x.shape[-1] == 1
+        x = x[..., 0]
+    if x.ndim == 0:
+        return x.reshape(1, 1)
+    if all(s == 1 for s in x.shape[1:]):
+        return x.reshape(x.shape[0], 1)
+    x = x.reshape(x.shape + (1,) * (1 + len(Nd) - x.ndim))
+    return x.expand((x.shape[0],) + tuple(Nd)).reshape(x.shape[0], -1)
+
+
 def _inner_contig(t: Tensor, inner: int) -> Tensor:
     """Make the trailing `inner` dims densely packed (leading strides stay free)."""
     exp = 1
@@ -241,6 +257,87 @@ def _(gMo, Mo, ckpt, Beff, T1, T2, gamma, dt, K, flags):
 def beff_ckpt_interval(K: int) -> int:
     """The explicit-field kernels take K in {1..32} or 64 (tile-aligned)."""
     return K if K <= 32 else (64 if K >= 64 else 32)
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone operators: rfgr2beff, beff2ab (forward), freeprec
+@torch.library.custom_op('mrphy_b200::rfgr2beff', mutates_args=(), device_types='cuda')
+def rfgr2beff_cuda(rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b1: Optional[Tensor],
+                   gamma: Tensor) -> Tensor:
+    """rf (N,2,nT[,nC]), gr (N,3,nT), loc (N,nM,3), df (N|1,nM|1), b1 (N,nM,2,nC) -> Beff (N,nM,nT,3)."""
+    L = _cabi.lib()
+    a = _cabi.RfGr2BeffArgs()
+    N, nM, nT = loc.shape[0], loc.shape[1], rf.shape[2]
+    a.dtype = _cabi.MRPHY_F64 if loc.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.N, a.nM, a.nT, a.nC = N, nM, nT, (rf.shape[3] if rf.ndim == 4 else 1)
+    a.rf, a.rf_sn, a.rf_sx, a.rf_st = rf.data_ptr(), _bstride(rf, 0), rf.stride(1), rf.stride(2)
+    a.rf_sc = rf.stride(3) if rf.ndim == 4 else 0
+    a.gr, a.gr_sn, a.gr_sx, a.gr_st = gr.data_ptr(), _bstride(gr, 0), gr.stride(1), gr.stride(2)
+    a.loc, a.loc_sn, a.loc_sm = loc.data_ptr(), _bstride(loc, 0), _bstride(loc, 1)
+    if b1 is not None:
+        a.b1, a.b1_sn, a.b1_sm = b1.data_ptr(), _bstride(b1, 0), _bstride(b1, 1)
+    a.df, a.gamma = _param(df, N, nM), _param(gamma, N, nM)
+    out = torch.empty((N, nM, nT, 3), dtype=loc.dtype, device=loc.device)
+    a.Beff = out.data_ptr()
+    with torch.cuda.device(loc.device):
+        _cabi.check(L.mrphy_rfgr2beff(a, _stream()), 'rfgr2beff')
+    _cabi.count_launches()
+    return out
+
+
+@rfgr2beff_cuda.register_fake
+def _(rf, gr, loc, df, b1, gamma):
+    return loc.new_empty((loc.shape[0], loc.shape[1], rf.shape[2], 3))
+
+
+@torch.library.custom_op('mrphy_b200::beff2ab', mutates_args=(), device_types='cuda')
+def beff2ab_cuda(beff: Tensor, E1: Tensor, E2: Tensor, gamma: Tensor, dt: Tensor, flags: int) -> Tuple[Tensor, Tensor]:
+    """beff (N,nM,nT,3) -> A (N,nM,3,3), B (N,nM,3); E1/E2/gamma broadcastable to (N,nM), dt () or (N|1,)."""
+    L = _cabi.lib()
+    a = _cabi.Beff2abArgs()
+    N, nM, nT = beff.shape[0], beff.shape[1], beff.shape[2]
+    a.dtype = _cabi.MRPHY_F64 if beff.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.flags, a.N, a.nM, a.nT = flags, N, nM, nT
+    a.Beff, a.B_sn, a.B_sm = beff.data_ptr(), _bstride(beff, 0), _bstride(beff, 1)
+    a.E1, a.E2, a.gamma = _param(E1, N, nM), _param(E2, N, nM), _param(gamma, N, nM)
+    a.dt = _param(dt, N, nM, per_batch_only=True)
+    A = torch.empty((N, nM, 3, 3), dtype=beff.dtype, device=beff.device)
+    B = torch.empty((N, nM, 3), dtype=beff.dtype, device=beff.device)
+    a.A, a.B = A.data_ptr(), B.data_ptr()
+    with torch.cuda.device(beff.device):
+        _cabi.check(L.mrphy_beff2ab(a, _stream()), 'beff2ab')
+    _cabi.count_launches()
+    return A, B
+
+
+@beff2ab_cuda.register_fake
+def _(beff, E1, E2, gamma, dt, flags):
+    return beff.new_empty(beff.shape[:2] + (3, 3)), beff.new_empty(beff.shape[:2] + (3,))
+
+
+@torch.library.custom_op('mrphy_b200::freeprec', mutates_args=(), device_types='cuda')
+def freeprec_cuda(Mi: Tensor, dur: Tensor, T1: Optional[Tensor], T2: Optional[Tensor], df: Optional[Tensor],
+                  adjoint: bool) -> Tensor:
+    """Mi (N,nM,3) -> Mo (N,nM,3); with adjoint=True applies the transposed map to a gradient."""
+    L = _cabi.lib()
+    a = _cabi.FreePrecArgs()
+    N, nM = Mi.shape[0], Mi.shape[1]
+    a.dtype = _cabi.MRPHY_F64 if Mi.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.adjoint, a.N, a.nM = int(adjoint), N, nM
+    a.Mi, a.Mi_sn, a.Mi_sm = Mi.data_ptr(), _bstride(Mi, 0), _bstride(Mi, 1)
+    a.dur = _param(dur, N, nM, per_batch_only=True)
+    a.T1, a.T2, a.df = _param(T1, N, nM), _param(T2, N, nM), _param(df, N, nM)
+    Mo = torch.empty((N, nM, 3), dtype=Mi.dtype, device=Mi.device)
+    a.Mo = Mo.data_ptr()
+    with torch.cuda.device(Mi.device):
+        _cabi.check(L.mrphy_freeprec(a, _stream()), 'freeprec')
+    _cabi.count_launches()
+    return Mo
+
+
+@freeprec_cuda.register_fake
+def _(Mi, dur, T1, T2, df, adjoint):
+    return Mi.new_empty(Mi.shape)
 
 
 # ------------------------------------------------------------------------------------------------

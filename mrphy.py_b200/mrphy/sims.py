@@ -24,20 +24,7 @@ from mrphy import _cabi, _ops
 __all__ = ['blochsim']
 
 
-def _flat_param(x: Optional[Tensor], N: int, Nd: tuple, device) -> Optional[Tensor]:
-    """(N|1, *Nd|1.., 1, 1)-style constant -> (N|1, nM|1) view (copy only for partial broadcasts)."""
-    if x is None:
-        return None
-    x = x.to(device=device)
-    while x.ndim > 1 + len(Nd):
-        assert x.shape[-1] == 1
-        x = x[..., 0]
-    if x.ndim == 0:
-        return x.reshape(1, 1)
-    if all(s == 1 for s in x.shape[1:]):
-        return x.reshape(x.shape[0], 1)
-    x = x.reshape(x.shape + (1,) * (1 + len(Nd) - x.ndim))
-    return x.expand((x.shape[0],) + tuple(Nd)).reshape(x.shape[0], -1)
+_flat_param = _ops.flat_param
 
 
 class BlochSim(Function):
@@ -127,6 +114,14 @@ class FreePrec(Function):
     def forward(ctx, Mi: Tensor, dur: Tensor, T1: Optional[Tensor], T2: Optional[Tensor],
                 Δf: Optional[Tensor]) -> Tensor:
         assert (T1 is None) == (T2 is None)
+        ctx.cuda = Mi.is_cuda and Mi.dtype in _ops._F
+        if ctx.cuda:   # one elementwise CUDA kernel (mrphy_freeprec); backward applies the transposed map
+            N, Nd, dev = Mi.shape[0], tuple(Mi.shape[1:-1]), Mi.device
+            args = (dur.to(dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
+                    _flat_param(Δf, N, Nd, dev))
+            ctx.args, ctx.shape = args, Mi.shape
+            M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)
+            return _ops.freeprec_cuda(M, *args, False).reshape(Mi.shape)
         c = s = E1 = E2 = None
         x, y, z = Mi.unbind(-1)
         if Δf is not None:                           # positive Δf rotates clockwise
@@ -144,6 +139,9 @@ class FreePrec(Function):
     def backward(ctx, grad_Mo: Tensor):
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
+        if ctx.cuda:
+            g = _ops._inner_contig(grad_Mo.reshape(ctx.shape[0], -1, 3), 1)
+            return _ops.freeprec_cuda(g, *ctx.args, True).reshape(ctx.shape), None, None, None, None
         c, s, E1, E2 = ctx.saved_tensors
         gx, gy, gz = grad_Mo.unbind(-1)
         if E1 is not None:

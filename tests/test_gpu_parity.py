@@ -325,3 +325,78 @@ def test_full_size_properties_c2(dev, dtype):
         rm[0, 0, t0, 0] -= eps
         fd = (f(rp) - f(rm)) / (2 * eps)
         assert abs(fd - float(p.rf.grad[0, 0, t0, 0])) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_rfgr2beff_kernel_and_its_chain_rule(dev):
+    """CUDA rfgr2beff == the torch expressions of beffective.py:137-167, forward and every gradient
+    (rf, gr, loc, Δf, b1Map, γ), with and without b1Map / coil dim, and on a 3-D Nd."""
+    from mrphy import beffective
+    gen = torch.Generator().manual_seed(4)
+    U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
+    for Nd, nC, has_b1 in (((7,), 2, True), ((3, 2, 2), 0, False), ((5,), 3, False), ((6,), 0, True)):
+        N, nT = 2, 9
+        rf = U(N, 2, nT, nC) if nC else U(N, 2, nT)
+        ins = dict(rf=rf, gr=U(N, 3, nT), loc=U(N, *Nd, 3) * 5, df=U(N, *Nd) * 100,
+                   b1=(U(N, *Nd, 2, nC) if nC else U(N, *Nd, 2)) if has_b1 else None, gam=4257.6 * (1 + 0.1 * U(N, *Nd)))
+        w = U(N, *Nd, nT, 3)
+        res = {}
+        for where in ('cpu', 'cuda'):
+            t = {k: (None if v is None else v.detach().clone().to(where).requires_grad_(True)) for k, v in ins.items()}
+            beff = beffective.rfgr2beff(t['rf'], t['gr'], t['loc'], Δf=t['df'], b1Map=t['b1'], γ=t['gam'])
+            (beff * w.to(where)).sum().backward()
+            res[where] = [beff.detach().cpu()] + [None if v is None else v.grad.cpu() for v in t.values()]
+        for a, b in zip(res['cpu'], res['cuda']):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert a.shape == b.shape and rel(b, a) < 1e-12
+
+
+def test_beff2ab_kernel(dev, golden):
+    """CUDA beff2ab == reference A/B (tests/test_slowsims.py:60,77-84: blochsim_ab(M0, A, B) == Mo0)."""
+    from mrphy import beffective, slowsims
+    g = golden('kat3')
+    beff = beffective.rfgr2beff(T(g['rf'], dev, f64), T(g['gr'], dev, f64), T(g['loc'], dev, f64),
+                                Δf=T(g['df'], dev, f64), b1Map=T(g['b1'], dev, f64), γ=T(g['gamma'], dev, f64))
+    dt, T1, T2 = T(g['dt'], dev, f64), T(g['T1'], dev, f64), T(g['T2'], dev, f64)
+    A, B = beffective.beff2ab(beff, E1=torch.exp(-dt / T1), E2=torch.exp(-dt / T2), γ=T(g['gamma'], dev, f64), dt=dt)
+    assert mx(A, g['A']) < 1e-12 and mx(B, g['B']) < 1e-12
+    assert mx(slowsims.blochsim_ab(T(g['M0'], dev, f64), A, B), g['Mo_const']) < 1e-12
+    g2 = golden('rand_mc')
+    dtb = T(g2['in_dt'], dev, f64).reshape(-1, 1)
+    A, B = beffective.beff2ab(T(g2['beff_f64'], dev, f64), E1=torch.exp(-dtb / T(g2['in_T1'], dev, f64)),
+                              E2=torch.exp(-dtb / T(g2['in_T2'], dev, f64)), γ=T(g2['in_gam'], dev, f64),
+                              dt=T(g2['in_dt'], dev, f64))
+    assert mx(A, g2['A_f64']) < 1e-12 and mx(B, g2['B_f64']) < 1e-12
+    A32, B32 = beffective.beff2ab(T(g2['beff_f64'], dev, f32), E1=torch.exp(-dtb / T(g2['in_T1'], dev, f64)).float(),
+                                  E2=torch.exp(-dtb / T(g2['in_T2'], dev, f64)).float(), γ=T(g2['in_gam'], dev, f32),
+                                  dt=T(g2['in_dt'], dev, f32))
+    assert A32.dtype == f32 and mx(A32, g2['A_f64']) < 5e-5 and mx(B32, g2['B_f64']) < 5e-5
+    # with grad enabled on beff the differentiable (autograd) implementation is used and agrees
+    bg = T(g2['beff_f64'], dev, f64).requires_grad_(True)
+    A2, B2 = beffective.beff2ab(bg, E1=torch.exp(-dtb / T(g2['in_T1'], dev, f64)),
+                                E2=torch.exp(-dtb / T(g2['in_T2'], dev, f64)), γ=T(g2['in_gam'], dev, f64),
+                                dt=T(g2['in_dt'], dev, f64))
+    assert A2.requires_grad and mx(A2, A) < 1e-12 and mx(B2, B) < 1e-12
+
+
+def test_freeprec_kernel(dev, golden):
+    """tests/test_slowsims.py:100-122, tests/test_sims.py:145-198, tests/test_mobjs.py:133-158 on CUDA."""
+    from mrphy import sims, mobjs, γH
+    g = golden('freeprec')
+    Mo = sims.freeprec(T(g['a_Mi'], dev, f64), T(g['a_dur'], dev, f64), T1=T(g['a_T1'], dev, f64),
+                       T2=T(g['a_T2'], dev, f64), Δf=T(g['a_df'], dev, f64))
+    assert mx(Mo, [[[0., -0.5, 0.5], [-0.5, 0, 0.5], [0., 0., 1.]]]) < 1e-12
+    for dtype, tol in ((f64, 1e-13), (f32, 2e-6)):
+        Mi = T(g['b_Mi'], dev, dtype).requires_grad_(True)
+        Mo = sims.freeprec(Mi, T(g['b_dur'], dev, dtype), T1=T(g['b_T1'], dev, dtype), T2=T(g['b_T2'], dev, dtype),
+                           Δf=T(g['b_df'], dev, dtype))
+        (Mo * T(g['b_w'], dev, dtype)).sum().backward()
+        assert Mo.dtype == dtype and mx(Mo, g['b_Mo']) < tol and mx(Mi.grad, g['b_gMi']) < tol
+    Mo = sims.freeprec(T(g['b_Mi'], dev, f64), T(g['b_dur'], dev, f64))          # no relaxation, no precession
+    assert mx(Mo, g['b_Mi']) == 0.0
+    cube = mobjs.SpinCube((1, 3, 3, 3), tensor([[3., 3., 3.]]), T1_=tensor([[0.5 / np.log(2)]], dtype=f64),
+                          T2_=tensor([[0.5 / np.log(2)]], dtype=f64), γ=γH, dtype=f64, device=dev)
+    cube.M_ = tensor([0., 1., 0.])
+    cube.Δf = tensor([[[1 / 4 / 0.5], [-1 / 4 / 0.5], [1]]], dtype=f64).repeat(1, 3, 1, 3)
+    M = cube.freeprec(tensor(0.5, dtype=f64), doEmbed=True)
+    assert M[0, 1, :, 1, :].cpu().numpy() == pytest.approx(np.array([[0.5, 0., 0.5], [-0.5, 0., 0.5], [0., -0.5, 0.5]]), abs=1e-9)
