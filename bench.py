@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- spin·steps/s of the fused Bloch simulation, forward + adjoint backward.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5|small]
                     [--dtype f32|f64]
 
 One "step" = one pass of the hot path over one batch of synthetic input (BASELINE.md / SURVEY.md 8d):
@@ -38,7 +38,7 @@ UNIT = 'spin·steps/s'
 FLOP_PER_SPIN_STEP = 223.0        # fwd 62 + bwd 161 algorithmic flop (fp32, 1 coil, relax, b1, df)
 FLOP_FWD, FLOP_BWD = 62.0, 161.0
 WORKLOADS = {   # name: (N, n, nT)
-    'c2': (1, 64, 1000), 'c3': (1, 128, 2000), 'c4': (64, 40, 1000), 'small': (1, 16, 200),
+    'c2': (1, 64, 1000), 'c3': (1, 128, 2000), 'c4': (64, 40, 1000), 'c5': (1, 256, 4000), 'small': (1, 16, 200),
 }
 
 

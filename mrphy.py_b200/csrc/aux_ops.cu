@@ -14,31 +14,53 @@ namespace mrphy {
 // ---- rfgr2beff (beffective.py:107-168) -------------------------------------------------------------
 // Threads run along time for one spin: the three components of 32 consecutive steps are 384 contiguous
 // bytes, so stores are fully coalesced; the spin's constants are warp-uniform (broadcast loads).
-template <typename T>
+// A block owns RB consecutive steps of ONE spin (SPT steps per thread, so the spin's constants and the division
+// df/gamma are amortised); results are staged in shared memory and leave as 128-bit stores of a contiguous
+// 12*RB-byte run when rows are 16-byte aligned (ALIGNED), as scalar stores otherwise.
+template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
+  constexpr int SPT = 4, RB = 256 * SPT;
+  __shared__ __align__(16) T stage[3 * RB];
   const int n = blockIdx.y;
   const int64_t bid = blockIdx.x;
   const int i = (int)(bid / tblocks);
-  const int t = (int)(bid % tblocks) * 256 + threadIdx.x;
-  if (t >= a.nT) return;
-  const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
-  const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
+  const int tb0 = (int)(bid % tblocks) * RB;
   const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
-  T bx = 0, by = 0;
-  if (a.b1) {
-    const T* bp = (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;
-    for (int c = 0; c < a.nC; ++c) {     // Re/Im of b1*rf summed over coils (beffective.py:160-165)
-      const T rx = rf[c * a.rf_sc], ry = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
-      bx += br * rx - bi * ry;
-      by += br * ry + bi * rx;
+  const T lx = lp[0], ly = lp[1], lz = lp[2];
+  const T bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
+  const T* bp = a.b1 ? (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm : nullptr;
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int j = u * 256 + threadIdx.x;      // consecutive threads -> consecutive steps: coalesced waveform reads
+    const int t = tb0 + j;
+    T bx = 0, by = 0, bz = 0;
+    if (t < a.nT) {
+      const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
+      const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
+      if (bp) {
+        for (int c = 0; c < a.nC; ++c) {     // Re/Im of b1*rf summed over coils (beffective.py:160-165)
+          const T rx = rf[c * a.rf_sc], ry = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
+          bx += br * rx - bi * ry;
+          by += br * ry + bi * rx;
+        }
+      } else {
+        for (int c = 0; c < a.nC; ++c) { bx += rf[c * a.rf_sc]; by += rf[a.rf_sx + c * a.rf_sc]; }
+      }
+      bz = lx * gr[0] + ly * gr[a.gr_sx] + lz * gr[2 * a.gr_sx] + bz0;
     }
-  } else {
-    for (int c = 0; c < a.nC; ++c) { bx += rf[c * a.rf_sc]; by += rf[a.rf_sx + c * a.rf_sc]; }
+    stage[3 * j] = bx; stage[3 * j + 1] = by; stage[3 * j + 2] = bz;
   }
-  T bz = lp[0] * gr[0] + lp[1] * gr[a.gr_sx] + lp[2] * gr[2 * a.gr_sx];
-  if (a.df.ptr) bz += (T)(ld_param(a.df, n, i) / ld_param(a.gamma, n, i));
-  T* o = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + t) * 3;
-  o[0] = bx; o[1] = by; o[2] = bz;
+  __syncthreads();
+  const int cnt = min(RB, a.nT - tb0);
+  T* out = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + tb0) * 3;
+  if (ALIGNED) {
+    const int nvec = cnt * 3 * (int)sizeof(T) / 16;
+    float4* dst = reinterpret_cast<float4*>(out);
+    const float4* src = reinterpret_cast<const float4*>(stage);
+    for (int q = threadIdx.x; q < nvec; q += 256) dst[q] = src[q];
+  } else {
+    for (int q = threadIdx.x; q < 3 * cnt; q += 256) out[q] = stage[q];
+  }
 }
 
 // ---- beff2ab (beffective.py:40-104) ----------------------------------------------------------------
@@ -115,13 +137,20 @@ extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream)
   if (!a->rf || !a->gr || !a->loc || !a->Beff) return fail(MRPHY_ERR_ARG, "rf, gr, loc, Beff are required%s");
   if (a->df.ptr && !a->gamma.ptr) return fail(MRPHY_ERR_ARG, "df needs gamma%s");
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int tblocks = (a->nT + 255) / 256;
+  const int tblocks = (a->nT + 1023) / 1024;
   const int64_t gx = (int64_t)a->nM * tblocks;
   if (gx > 2147483647LL) return fail(MRPHY_ERR_ARG, "nM*nT too large for one launch%s");
   dim3 grid((unsigned)gx, a->N);
   timing_begin(st);
-  if (a->dtype == MRPHY_F64) rfgr2beff_kernel<double><<<grid, 256, 0, st>>>(*a, tblocks);
-  else rfgr2beff_kernel<float><<<grid, 256, 0, st>>>(*a, tblocks);
+  const size_t es = a->dtype == MRPHY_F64 ? 8 : 4;
+  const bool aligned = ((size_t)a->nT * 3 * es) % 16 == 0 && ((uintptr_t)a->Beff) % 16 == 0;
+  if (a->dtype == MRPHY_F64) {
+    if (aligned) rfgr2beff_kernel<double, true><<<grid, 256, 0, st>>>(*a, tblocks);
+    else rfgr2beff_kernel<double, false><<<grid, 256, 0, st>>>(*a, tblocks);
+  } else {
+    if (aligned) rfgr2beff_kernel<float, true><<<grid, 256, 0, st>>>(*a, tblocks);
+    else rfgr2beff_kernel<float, false><<<grid, 256, 0, st>>>(*a, tblocks);
+  }
   timing_end(st);
   ++launch_count();
   CK(cudaGetLastError());

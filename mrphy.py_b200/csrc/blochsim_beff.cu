@@ -7,6 +7,7 @@
 // not stored: time-reversed reconstruction + checkpoints every K steps, as in the fused path.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mrphy_b200.h"
@@ -156,6 +157,157 @@ __global__ void __launch_bounds__(EBLK) beff_bwd_kernel(const EArgs<T> a, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2 tile pipeline (used when every Beff row is 16-byte aligned: nT*3*sizeof(T) % 16 == 0).
+// A tile row is 192 data bytes (16 fp32 steps / 8 fp64 steps) + 16 bytes pad = 208-byte pitch, so that
+//  * the warp fills it with 16-byte cp.async (LDGSTS.128) straight from HBM, double-buffered: tile k+1 is in
+//    flight while tile k is consumed, no registers staged;
+//  * each thread reads its own row with LDS.128 without bank conflicts (20*r mod 32 hits 8 distinct quads);
+//  * the backward overwrites the row in place with dL/dBeff and the warp streams it out with 16-byte stores.
+constexpr int ROWB = 192, PITCHB = 208, CHUNKS = ROWB / 16;   // 12 chunks of 16 B per row
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// warp-cooperative async copy of rows [i0, i0+32) x bytes [t0*3*sizeof(T), +nbytes) into `tile`
+template <typename T>
+__device__ __forceinline__ void tile_load_async(const T* __restrict__ B, int64_t B_sm, int i0, int nM, int t0, int nbytes,
+                                                unsigned char* tile, int lane) {
+  const int nch = nbytes >> 4;             // chunks per row in this tile (<= 12)
+  for (int q = lane; q < 32 * nch; q += 32) {
+    const int r = q / nch, c = q - r * nch;
+    const int i = min(i0 + r, nM - 1);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(B + (int64_t)i * B_sm + (int64_t)t0 * 3) + c * 16;
+    cp_async16(tile + r * PITCHB + c * 16, src);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void tile_store16(T* __restrict__ G, int64_t G_sm, int i0, int nM, int t0, int nbytes,
+                                             const unsigned char* tile, int lane) {
+  const int nch = nbytes >> 4;
+  for (int q = lane; q < 32 * nch; q += 32) {
+    const int r = q / nch, c = q - r * nch;
+    const int i = i0 + r;
+    if (i < nM) {
+      const float4 v = *reinterpret_cast<const float4*>(tile + r * PITCHB + c * 16);
+      *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(G + (int64_t)i * G_sm + (int64_t)t0 * 3) + c * 16) = v;
+    }
+  }
+}
+
+template <typename T, int POL, bool RELAX, bool BWD>
+__global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const int need_gmi, const int need_gb) {
+  constexpr int TB = ROWB / (3 * (int)sizeof(T));      // steps per tile: 16 (fp32), 8 (fp64)
+  constexpr int PITCH = PITCHB / (int)sizeof(T);       // row pitch in elements
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
+  unsigned char* buf0 = smem_raw + (size_t)warp * 2 * 32 * PITCHB;
+  const int nM = a.nM, nT = a.nT, K = a.K;
+  const int i0 = (blockIdx.x * EWARP + warp) * 32;
+  if (i0 >= nM) return;
+  const bool ok = i0 + lane < nM;
+  const int i = ok ? i0 + lane : nM - 1;
+  SpinConst<T, 1> k;
+  T g;
+  load_consts<T, RELAX>(a, n, i, k, g);
+  T mx, my, mz, hx = 0, hy = 0, hz = 0;
+  if (BWD) {
+    const T* mp = a.Mo + ((size_t)n * nM + i) * 3;
+    mx = mp[0]; my = mp[1]; mz = mp[2];
+    const T* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)i * a.gMo_sm;
+    hx = gp[0]; hy = gp[1]; hz = gp[2];
+  } else {
+    const T* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)i * a.Mi_sm;
+    mx = mp[0]; my = mp[1]; mz = mp[2];
+  }
+  const T* Bn = a.B + (int64_t)n * a.B_sn;
+  T* Gn = BWD ? a.gB + (size_t)n * nM * (size_t)nT * 3 : nullptr;
+  const T ng = -g;
+  int next_ck = BWD ? ((nT - 1) / K) * K : K;   // next step index at which a checkpoint is read / written
+  const int ntiles = (nT + TB - 1) / TB;
+  auto tile_t0 = [&](int q) { return (BWD ? ntiles - 1 - q : q) * TB; };     // q-th tile in processing order
+  auto tile_len = [&](int q) { return min(TB, nT - tile_t0(q)); };
+  tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(0), tile_len(0) * 3 * (int)sizeof(T), buf0, lane);
+  cp_async_commit();
+  for (int q = 0; q < ntiles; ++q) {
+    unsigned char* cur = buf0 + (q & 1) * 32 * PITCHB;
+    if (q + 1 < ntiles) {
+      tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(q + 1), tile_len(q + 1) * 3 * (int)sizeof(T),
+                         buf0 + ((q + 1) & 1) * 32 * PITCHB, lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    T* row = reinterpret_cast<T*>(cur) + lane * PITCH;
+    const int t0 = tile_t0(q), len = tile_len(q);
+    // 48 bytes = GS steps per group, moved with three conflict-free 128-bit accesses
+    constexpr int GS = 16 / (int)sizeof(T);            // 4 (fp32) or 2 (fp64) steps
+    constexpr int GV = 3 * GS;                         // values per group
+    if (!BWD) {
+      for (int j0 = 0; j0 < len; j0 += GS) {
+        T v[GV];
+        float4* v4 = reinterpret_cast<float4*>(v);
+        const float4* src = reinterpret_cast<const float4*>(row + 3 * j0);
+        v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
+#pragma unroll
+        for (int u = 0; u < GS; ++u) {
+          step_fwd<T, POL, RELAX>(g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], k.e1, k.e2, mx, my, mz);
+          const int t1 = t0 + j0 + u + 1;
+          if (t1 == next_ck) {
+            if (t1 < nT && ok) {
+              T* cp = a.ckpt + ((size_t)n * a.nCk + (t1 / K - 1)) * 3 * (size_t)nM;
+              cp[i] = mx; cp[(size_t)nM + i] = my; cp[2 * (size_t)nM + i] = mz;
+            }
+            next_ck += K;
+          }
+        }
+      }
+    } else {
+      for (int j0 = len - GS; j0 >= 0; j0 -= GS) {
+        T v[GV];
+        float4* v4 = reinterpret_cast<float4*>(v);
+        float4* src = reinterpret_cast<float4*>(row + 3 * j0);
+        v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
+#pragma unroll
+        for (int u = GS - 1; u >= 0; --u) {
+          T Fx, Fy, Fz;
+          step_bwd<T, POL, RELAX, 1>(k, g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], mx, my, mz, hx, hy, hz,
+                                     Fx, Fy, Fz);
+          v[3 * u] = ng * Fx;       // dL/dBeff = -2*pi*gamma*dt * F   (sims.py:194, 234-259)
+          v[3 * u + 1] = ng * Fy;
+          v[3 * u + 2] = ng * Fz;
+          const int t = t0 + j0 + u;
+          if (t == next_ck) {
+            if (t > 0) {
+              const T* cp = a.ckpt + ((size_t)n * a.nCk + (t / K - 1)) * 3 * (size_t)nM;
+              mx = cp[i]; my = cp[(size_t)nM + i]; mz = cp[2 * (size_t)nM + i];
+            }
+            next_ck -= K;
+          }
+        }
+        src[0] = v4[0]; src[1] = v4[1]; src[2] = v4[2];
+      }
+      __syncwarp();
+      if (need_gb) tile_store16<T>(Gn, (int64_t)nT * 3, i0, nM, t0, len * 3 * (int)sizeof(T), cur, lane);
+    }
+    __syncwarp();   // the buffer is refilled two iterations later, after every lane has left it
+  }
+  if (!BWD && ok) {
+    T* op = a.Mo + ((size_t)n * nM + i) * 3;
+    op[0] = mx; op[1] = my; op[2] = mz;
+  }
+  if (BWD && need_gmi && ok) {
+    T* op = a.gMi + ((size_t)n * nM + i) * 3;
+    op[0] = hx; op[1] = hy; op[2] = hz;
+  }
+}
+
 }  // namespace mrphy
 
 using namespace mrphy;
@@ -191,10 +343,37 @@ EArgs<T> make_eargs(const mrphy_beff_args* a) {
   return e;
 }
 
+template <typename T>
+bool rows_aligned16(const mrphy_beff_args* a) {
+  const size_t es = sizeof(T);
+  return ((size_t)a->nT * 3 * es) % 16 == 0 && ((size_t)a->B_sm * es) % 16 == 0 && ((size_t)a->B_sn * es) % 16 == 0 &&
+         ((uintptr_t)a->Beff) % 16 == 0 && (!a->gBeff || ((uintptr_t)a->gBeff) % 16 == 0);
+}
+
 template <typename T, int POL, bool RELAX>
 int launch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
   const EArgs<T> e = make_eargs<T>(a);
   dim3 grid((a->nM + EBLK - 1) / EBLK, a->N);
+  if (rows_aligned16<T>(a) && !getenv("MRPHY_B200_BEFF_V1")) {   // cp.async double-buffered tiles
+    constexpr size_t smem2 = (size_t)EWARP * 2 * 32 * PITCHB;
+    const int gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0, gb = (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0;
+    if (bwd) {
+      auto kern = beff_v2_kernel<T, POL, RELAX, true>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      timing_begin(st);
+      kern<<<grid, EBLK, smem2, st>>>(e, gmi, gb);
+      timing_end(st);
+    } else {
+      auto kern = beff_v2_kernel<T, POL, RELAX, false>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      timing_begin(st);
+      kern<<<grid, EBLK, smem2, st>>>(e, 0, 0);
+      timing_end(st);
+    }
+    ++launch_count();
+    CK(cudaGetLastError());
+    return MRPHY_OK;
+  }
   constexpr size_t smem = ECfg<T>::smem;
   if (bwd) {
     auto kern = beff_bwd_kernel<T, POL, RELAX>;
