@@ -775,8 +775,8 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   if (a->K < 1 || a->K > TCMAX) return fail(MRPHY_ERR_ARG, "checkpoint interval K must be in [1, 64]%s");
   p->sum_coils = a->b1 == nullptr;
   const int nc = p->sum_coils ? 1 : a->nC;
-  if (nc > 8) return fail(MRPHY_ERR_ARG, "more than 8 transmit coils with a b1Map are not supported yet%s");
-  p->NC = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : 8;
+  if (nc > 16) return fail(MRPHY_ERR_ARG, "more than 16 transmit coils with a b1Map are not supported%s");
+  p->NC = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : nc <= 8 ? 8 : 16;
   p->W = 2 * p->NC + 3;
   p->K = a->K;
   p->TCP = (a->K + 3) & ~3;
@@ -954,6 +954,7 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
     case 2: return launch_any<T, POL, RELAX, 2, 1, 128>(bwd, k, p, need_gmi, st);
     case 4: return launch_any<T, POL, RELAX, 4, 1, 128>(bwd, k, p, need_gmi, st);
     case 8: return launch_any<T, POL, RELAX, 8, 1, 128>(bwd, k, p, need_gmi, st);
+    case 16: return launch_any<T, POL, RELAX, 16, 1, 128>(bwd, k, p, need_gmi, st);
   }
   return fail(MRPHY_ERR_ARG, "internal: bad NC%s");
 }

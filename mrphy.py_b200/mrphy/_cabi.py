@@ -110,6 +110,8 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
+                if not os.path.exists(LIB_PATH) and 'MRPHY_B200_LIB' not in os.environ:
+                    _try_build()
                 if not os.path.exists(LIB_PATH):
                     raise RuntimeError(
                         f'mrphy (B200): {LIB_PATH} is not built. Run `python mrphy.py_b200/build.py` '
@@ -123,6 +125,22 @@ def lib():
                                        f'!= binding {ABI_VERSION}; rebuild with mrphy.py_b200/build.py')
                 _lib = L
     return _lib
+
+
+def _try_build():
+    """Compile the library in-tree when it is missing and nvcc is on the box (never a non-CUDA substitute)."""
+    import importlib.util
+    import shutil
+    if not (shutil.which('nvcc') or os.path.exists('/usr/local/cuda/bin/nvcc')):
+        return
+    try:
+        spec = importlib.util.spec_from_file_location('mrphy_build', os.path.join(os.path.dirname(_HERE), 'build.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    except Exception as e:   # surfaced by the RuntimeError below
+        import warnings
+        warnings.warn(f'mrphy (B200): building {LIB_PATH} failed: {e}')
 
 
 def check(rc, what):

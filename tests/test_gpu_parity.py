@@ -400,3 +400,91 @@ def test_freeprec_kernel(dev, golden):
     cube.Δf = tensor([[[1 / 4 / 0.5], [-1 / 4 / 0.5], [1]]], dtype=f64).repeat(1, 3, 1, 3)
     M = cube.freeprec(tensor(0.5, dtype=f64), doEmbed=True)
     assert M[0, 1, :, 1, :].cpu().numpy() == pytest.approx(np.array([[0.5, 0., 0.5], [-0.5, 0., 0.5], [0., -0.5, 0.5]]), abs=1e-9)
+
+
+def test_spincube_api_batch_mask_multicoil(dev):
+    """The object API end to end on CUDA: N=2 batch, masked cube, 3 coils with a NON-compact b1Map (N,*Nd,xy,nCoils),
+    per-batch dt, doEmbed; against the oracle on the compact spins."""
+    from mrphy import mobjs
+    from oracle import bloch_oracle as orc
+    gen = torch.Generator().manual_seed(12)
+    U = lambda *s: torch.rand(s, generator=gen, dtype=f64) * 2 - 1
+    N, Nd, nT, nC = 2, (5, 4, 3), 77, 3
+    mask = torch.rand((1,) + Nd, generator=gen) > 0.3
+    kw = {'dtype': f64, 'device': dev}
+    cube = mobjs.SpinCube((N,) + Nd, tensor([[10., 8., 6.], [12., 8., 6.]]), mask=mask, ofst=tensor([[0., 1., 0.]]),
+                          T1=1 + 0.3 * U(N, *Nd).abs(), T2=0.05 + 0.02 * U(N, *Nd).abs(), **kw)
+    cube.Δf = U(N, *Nd) * 150
+    b1 = U(N, *Nd, 2, nC) * 0.5
+    rf, gr = (U(N, 2, nT, nC) * 0.2).to(dev).requires_grad_(True), (U(N, 3, nT) * 3).to(dev).requires_grad_(True)
+    p = mobjs.Pulse(rf=rf, gr=gr, dt=tensor([4e-6, 8e-6]), **kw)
+    M = cube.applypulse(p, b1Map=b1.to(dev), doEmbed=True)
+    assert M.shape == (N,) + Nd + (3,) and bool(torch.isnan(M[:, ~mask[0].to(dev)]).all())
+    M_ = cube.extract(M)
+    w = U(N, cube.nM, 3)
+    (M_ * w.to(dev)).sum().backward()
+    c = lambda x: x.detach().cpu()
+    ref = orc.applypulse_fwd_bwd(c(cube.M_), c(rf), c(gr), c(cube.loc_), w, df=c(cube.Δf_), b1=c(cube.extract(b1.to(dev))),
+                                 T1=c(cube.T1_), T2=c(cube.T2_), gamma=c(cube.γ_), dt=c(p.dt))
+    assert mx(M_, ref['Mo']) < ATOL64 and rel(rf.grad, ref['grf']) < RTOL_G64 and rel(gr.grad, ref['ggr']) < RTOL_G64
+    # moving objects between devices keeps the data (Pulse.to / SpinCube.to, untested upstream)
+    cpu_cube = cube.to(device=torch.device('cpu'), dtype=f64)
+    assert torch.equal(cpu_cube.loc_, c(cube.loc_)) and torch.equal(cpu_cube.T1_, c(cube.T1_)) and cpu_cube.nM == cube.nM
+    back = cpu_cube.to(device=dev, dtype=torch.float32)
+    assert back.dtype == torch.float32 and back.is_cuda and mx(back.Δf_, cube.Δf_) < 1e-4
+    assert mx(back.applypulse(p.to(device=dev, dtype=torch.float32), b1Map=b1.to(dev)), ref['Mo']) < 1e-4
+
+
+def test_sixteen_coils_and_too_many(dev):
+    from mrphy import _ops
+    from oracle import bloch_oracle as orc
+    p = _random_problem(31, 1, 40, 30, 11, has_b1=True, relax=True)
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'],
+                                 T2=p['T2'], gamma=p['gam'], dt=p['dt'])
+    g = {('in_' + k): v.numpy() for k, v in p.items() if v is not None}
+    Mo, gM0, grf, ggr = run_fused(g, dev, f64, p['w'].numpy())
+    assert mx(Mo, ref['Mo']) < ATOL64 and rel(grf, ref['grf']) < RTOL_G64 and rel(ggr, ref['ggr']) < RTOL_G64
+    q = _random_problem(32, 1, 8, 5, 17, has_b1=True, relax=False)
+    with pytest.raises(RuntimeError, match='16 transmit coils'):
+        run_fused({('in_' + k): v.numpy() for k, v in q.items() if v is not None}, dev, f64, q['w'].numpy())
+
+
+def test_strong_relaxation_shrinks_checkpoint_interval(dev):
+    """dt/T2 = 0.2: inverting the relaxation over 64 steps would amplify errors by e^12.8; the host policy picks
+    K = 2 and gradients stay exact."""
+    from mrphy import _ops
+    from oracle import bloch_oracle as orc
+    p = _random_problem(41, 1, 100, 90, 1, has_b1=True, relax=True)
+    p['dt'] = tensor([1e-3], dtype=f64)
+    p['T1'], p['T2'] = p['T1'] * 0 + 8e-3, p['T2'] * 0 + 5e-3
+    p['rf'], p['gr'] = p['rf'] * 0.01, p['gr'] * 0.01
+    assert _ops.pick_ckpt_interval(p['dt'].to(dev), p['T1'].to(dev), p['T2'].to(dev)) == 2
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'],
+                                 T2=p['T2'], gamma=p['gam'], dt=p['dt'])
+    g = {('in_' + k): v.numpy() for k, v in p.items() if v is not None}
+    Mo, gM0, grf, ggr = run_fused(g, dev, f64, p['w'].numpy())
+    assert mx(Mo, ref['Mo']) < ATOL64 and rel(grf, ref['grf']) < 1e-8 and rel(ggr, ref['ggr']) < 1e-8
+    assert rel(gM0, ref['gM0']) < 1e-8
+
+
+def test_geometry_gradients_route_through_explicit_field(dev):
+    """loc / Δf / b1Map that require grad: applypulse materialises Beff (CUDA rfgr2beff) and uses the explicit-Beff
+    kernels, so the reference's autograd behaviour is kept; checked by finite differences."""
+    from mrphy import mobjs
+    gen = torch.Generator().manual_seed(8)
+    U = lambda *s: torch.rand(s, generator=gen, dtype=f64) * 2 - 1
+    kw = {'dtype': f64, 'device': dev}
+    sp = mobjs.SpinArray((1, 6), **kw)
+    p = mobjs.Pulse(rf=(U(1, 2, 20) * 0.2).to(dev), gr=(U(1, 3, 20) * 3).to(dev), **kw)
+    loc, df = (U(1, 6, 3) * 5).to(dev).requires_grad_(True), (U(1, 6) * 100).to(dev).requires_grad_(True)
+    w = U(1, 6, 3).to(dev)
+    f = lambda l, d: (sp.applypulse(p, loc_=l, Δf_=d) * w).sum()
+    f(loc, df).backward()
+    eps = 1e-6
+    for t, idx in ((loc, (0, 2, 1)), (df, (0, 4))):
+        tp, tm = t.detach().clone(), t.detach().clone()
+        tp[idx] += eps
+        tm[idx] -= eps
+        args = (lambda x: (x, df.detach())) if t is loc else (lambda x: (loc.detach(), x))
+        fd = (float(f(*args(tp))) - float(f(*args(tm)))) / (2 * eps)
+        assert abs(fd - float(t.grad[idx])) < 1e-6 * max(1.0, abs(fd))
