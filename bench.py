@@ -242,7 +242,7 @@ def run_ours(args):
         try:   # dram__bytes_read+write per launch of the same kernel from the committed ncu capture (C2 fp32 only)
             if args.workload == 'c2' and args.dtype == 'f32':
                 with open(os.path.join(ROOT, 'profiles', 'r1_ncu_summary.json')) as f:
-                    m = json.load(f)['captures']['pk2_bwd']['metrics']
+                    m = json.load(f)['captures']['final_bwd']['metrics']
                 traffic = (m['dram__bytes_read.sum']['value'] + m['dram__bytes_write.sum']['value']) * 1e6
         except Exception:
             traffic = None

@@ -647,20 +647,21 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
 template <typename T>
 __global__ void grad_finalize_kernel(const T* __restrict__ partials, int P, int W, int NC, int nC, int nT,
                                      int coil_dim, int bcast_coils, T* __restrict__ grf, T* __restrict__ ggr) {
-  __shared__ T sm[8][33];
+  constexpr int NY = 32;   // slices of the partial index summed in parallel, then combined in fixed order
+  __shared__ T sm[NY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int t = blockIdx.x * 32 + tx, w = blockIdx.y, n = blockIdx.z;
   T sum = (T)0;
   if (t < nT) {
     const T* p = partials + ((size_t)n * P * W + w) * (size_t)nT + t;
-    for (int q = ty; q < P; q += 8) sum += p[(size_t)q * W * nT];
+    for (int q = ty; q < P; q += NY) sum += p[(size_t)q * W * nT];
   }
   sm[ty][tx] = sum;
   __syncthreads();
   if (ty == 0 && t < nT) {
     T tot = sm[0][tx];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) tot += sm[q][tx];
+    for (int q = 1; q < NY; ++q) tot += sm[q][tx];
     tot = -tot;
     if (w >= 2 * NC) {
       ggr[((size_t)n * 3 + (w - 2 * NC)) * nT + t] = tot;
@@ -991,7 +992,7 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, cudaStream_t st) {
   if ((rc = check_common<T>(a, true))) return rc;
   if (!wave_is_packed && (rc = launch_pack<T>(a, p, st))) return rc;
   if ((rc = dispatch<T>(true, a, p, st))) return rc;
-  dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 8);
+  dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 32);
   grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT,
                                                   (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T*)a->grf,
                                                   (T*)a->ggr);

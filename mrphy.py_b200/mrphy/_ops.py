@@ -6,6 +6,7 @@ with ``beffective.rfgr2beff`` (beffective.py:107-168) followed by ``sims.BlochSi
 Python-level entry used by ``mobjs.SpinArray.applypulse`` (mobjs.py:394-450).
 """
 import os
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -353,30 +354,39 @@ def _collapse(x: Tensor) -> Tensor:
     return x
 
 
-def _tensor_key(t: Tensor):
-    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype)
+def _root(t: Tensor) -> Tensor:
+    """The tensor object that owns the storage a view was taken from (stable across calls for views of user data)."""
+    return t._base if t._base is not None else t
 
 
 def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -> int:
-    """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at K_MAX.  One device->host read per distinct
-    (dt, T1, T2) storage/version, cached afterwards (keeps applypulse asynchronous in a design loop)."""
+    """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at K_MAX.
+
+    Needs max(dt)/min(T) on the host: one device->host read, then cached per (dt, T1, T2) tensor OBJECT and
+    in-place version (weak references guard against id reuse), so a design loop that keeps its SpinCube / Pulse
+    stays asynchronous.  MRPHY_B200_CKPT overrides."""
     env = os.environ.get('MRPHY_B200_CKPT')
     if env:
         return max(1, min(K_MAX, int(env)))
     if T1 is None:
         return K_MAX
-    key = (_tensor_key(dt), _tensor_key(T1), _tensor_key(T2))
-    K = _ratio_cache.get(key)
-    if K is None:
-        with torch.no_grad():
-            tmin = torch.minimum(_collapse(T1).min(), _collapse(T2).min()).double()
-            r = float((dt.max().double() / tmin).item())
-        K = K_MAX if not (r > 0) else int(max(1, min(K_MAX, _AMPLIFY_BUDGET / r)))
-        if K >= 16:
-            K -= K % 16
-        if len(_ratio_cache) > 256:
-            _ratio_cache.clear()
-        _ratio_cache[key] = K
+    roots = tuple(_root(x) for x in (dt, T1, T2))
+    key = tuple(id(r) for r in roots) + tuple(tuple(x.shape) + tuple(x.stride()) + (x.storage_offset(),)
+                                              for x in (dt, T1, T2))
+    hit = _ratio_cache.get(key)
+    if hit is not None:
+        refs, vers, K = hit
+        if all(w() is r for w, r in zip(refs, roots)) and vers == tuple(r._version for r in roots):
+            return K
+    with torch.no_grad():
+        tmin = torch.minimum(_collapse(T1).min(), _collapse(T2).min()).double()
+        r = float((dt.max().double() / tmin).item())
+    K = K_MAX if not (r > 0) else int(max(1, min(K_MAX, _AMPLIFY_BUDGET / r)))
+    if K >= 16:
+        K -= K % 16
+    if len(_ratio_cache) > 256:
+        _ratio_cache.clear()
+    _ratio_cache[key] = (tuple(weakref.ref(r) for r in roots), tuple(r._version for r in roots), K)
     return K
 
 
