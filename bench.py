@@ -121,7 +121,11 @@ def run_ours(args):
     N, n, nT = WORKLOADS[args.workload]
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
     kw = {'dtype': dtype, 'device': dev}
-    host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world)
+    if args.scaling == 'strong':      # the whole n^3 cube split into x-slabs (BASELINE config C5)
+        assert n % world == 0
+        host = synth(N, n // world, n, nT, dtype, x_off=rank * (n // world), n_x_total=n)
+    else:                             # weak: every rank owns an n^3 slab of an (n*world) x n x n cube
+        host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     nM = host['loc'].shape[1]
     tgt = torch.tensor([0., 1., 0.], **kw)
@@ -226,7 +230,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, alt_ms = float(t[0]), float(t[1]), float(t[2])
-    units = float(N) * nM * nT * world            # spin·steps per step, all ranks
+    units = float(N) * nM * nT * world            # spin·steps per step, all ranks (nM is per rank)
     value = units * args.steps / (ms_total * 1e-3)
     e2e = units * args.steps / (ms_e2e * 1e-3)
     if rank == 0:
@@ -249,8 +253,9 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': f'{args.workload.upper()}: SpinCube {n}^3 x N={N} per GPU, nT={nT}, dt=4us, '
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': f'{args.workload.upper()}: SpinCube {n}^3 x N={N} ' +
+                                   ('per GPU' if args.scaling == 'weak' else f'split over {world} GPUs') + f', nT={nT}, dt=4us, '
                                    'b1Map+df+relaxation, fwd+adjoint bwd', 'spins_per_gpu': N * nM, 'nT': nT,
                        'l2': 'flushed between steps (256 MB write)', 'sharding': f'spin slabs x{world}, waveform '
                        'replicated, 1 allreduce of grads' if world > 1 else 'single GPU'},
@@ -341,6 +346,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     (run_ours if a.impl == 'ours' else run_reference)(a)
