@@ -19,8 +19,21 @@ from mrphy import utils, beffective, sims, _ops
 __all__ = ['Pulse', 'SpinArray', 'SpinCube', 'Examples']
 
 
+_CONSTS = {id(c): c for c in (γH, dt0, gmax0, smax0, rfmax0, T1G, T2G)}
+_const_cache = {}
+
+
 def _as_tensor(v, device, dtype) -> Tensor:
-    return v.to(device=device, dtype=dtype) if isinstance(v, Tensor) else tensor(v, device=device, dtype=dtype)
+    if not isinstance(v, Tensor):
+        return tensor(v, device=device, dtype=dtype)
+    if id(v) in _CONSTS and device.type == 'cuda':
+        # package defaults: one (synchronising) host->device copy per device/dtype; objects get device-side clones
+        key = (id(v), device, dtype)
+        hit = _const_cache.get(key)
+        if hit is None:
+            hit = _const_cache[key] = v.to(device=device, dtype=dtype)
+        return hit.clone()
+    return v.to(device=device, dtype=dtype)
 
 
 class _Slotted(object):
