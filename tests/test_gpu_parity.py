@@ -488,3 +488,21 @@ def test_geometry_gradients_route_through_explicit_field(dev):
         args = (lambda x: (x, df.detach())) if t is loc else (lambda x: (loc.detach(), x))
         fd = (float(f(*args(tp))) - float(f(*args(tm)))) / (2 * eps)
         assert abs(fd - float(t.grad[idx])) < 1e-6 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize('pack', ['1', '2', '3'])
+@pytest.mark.parametrize('trig', ['fast', 'precise'])
+def test_all_fp32_kernel_variants_agree_with_oracle(dev, monkeypatch, pack, trig):
+    """The three fp32 single-coil code paths (scalar, two spins per thread, time-packed) x both trig policies on a
+    ragged problem: same tolerances as the default path."""
+    from oracle import bloch_oracle as orc
+    p = _random_problem(55, 2, 333, 203, 1, has_b1=True, relax=True, dtype=f32)
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'],
+                                 T2=p['T2'], gamma=p['gam'], dt=p['dt'])
+    g = {('in_' + k): v.numpy() for k, v in p.items() if v is not None}
+    monkeypatch.setenv('MRPHY_B200_PACK', pack)
+    monkeypatch.setenv('MRPHY_B200_TRIG', trig)
+    Mo, gM0, grf, ggr = run_fused(g, dev, f32, p['w'].numpy())
+    tol = 1e-5 if trig == 'precise' else 3e-5
+    assert mx(Mo, ref['Mo']) < tol
+    assert rel(grf, ref['grf']) < RTOL_G32 and rel(ggr, ref['ggr']) < RTOL_G32 and rel(gM0, ref['gM0']) < RTOL_G32
