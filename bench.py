@@ -291,6 +291,10 @@ def run_ours(args):
                            'note': 'opt-in: ~2x the fp32 error of the default polynomial trigonometry'}
         line['config']['trig'] = 'precise (default)' if dtype == torch.float32 else 'fp64 libm'
         line['cpu_baseline'] = cpu_baseline(args, nT)
+        try:
+            line['torch_eager_same_gpu'] = eager_cuda_baseline(args, nT)
+        except Exception as e:      # context only
+            line['torch_eager_same_gpu'] = {'error': str(e)[:100]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -306,6 +310,31 @@ def cpu_port_step(n, nT, dtype, threads):
     orc.applypulse_fwd_bwd(s['M0'], s['rf'], s['gr'], s['loc'], lambda Mo: 2 * (Mo - tgt), df=s['df'], b1=s['b1'],
                            T1=1.47, T2=0.07, dtype=dtype)
     return time.perf_counter() - t0, n ** 3 * nT
+
+
+def eager_cuda_baseline(args, nT):
+    """The reference's execution shape (a handful of torch ops per time step, dense Beff and per-step history in
+    HBM) run on THIS GPU: the oracle port with its tensors on cuda.  Context only -- not the product, not the target."""
+    from oracle import bloch_oracle as orc
+    dtype = torch.float32 if args.dtype == 'f32' else torch.float64
+    n = 32
+    s = {k: v.cuda() for k, v in synth(1, n, n, nT, dtype).items()}
+    tgt = torch.tensor([0., 1., 0.], dtype=dtype, device='cuda')
+    orc.DEVICE = 'cuda'
+    try:
+        best = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            orc.applypulse_fwd_bwd(s['M0'], s['rf'], s['gr'], s['loc'], lambda Mo: 2 * (Mo - tgt), df=s['df'], b1=s['b1'],
+                                   T1=1.47, T2=0.07, dtype=dtype)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    finally:
+        orc.DEVICE = 'cpu'
+    return {'value': n ** 3 * nT / best, 'unit': UNIT, 'kind': 'port of the reference algorithm in torch-eager CUDA on this GPU',
+            'sample': f'{n}^3 spins x {nT} steps, {best:.2f} s (about 60 kernel launches per time step)'}
 
 
 def cpu_baseline(args, nT):
