@@ -99,6 +99,39 @@ MRPHY_HD float hsum(f2 a) { return a.v.x + a.v.y; }
 // double       : rsqrt() and sincos() of the CUDA math library (FP64 pipe), both policies.
 template <typename T, int POL> struct Fn;
 
+// double: rsqrt() of the CUDA math library; sincos by a branch-free Cody-Waite reduction (three-part pi/2, exact for
+// |x| < 2^20 * pi/2) and the fdlibm kernel polynomials (< 1 ulp on [-pi/4, pi/4]).  The library sincos() costs about
+// twice as many FP64 instructions and carries a divergent slow path with a local-memory frame.
+MRPHY_HD void sincos_f64(double x, double& s, double& c) {
+  const double t = fma(x, 0.63661977236758138, 6755399441055744.0);   // x*2/pi + 1.5*2^52: low bits = quadrant
+  const double jf = t - 6755399441055744.0;
+  double r = fma(jf, -1.57079632673412561417e+00, x);
+  r = fma(jf, -6.07710050630396597660e-11, r);
+  r = fma(jf, -2.02226624879595063154e-21, r);
+  const double z = r * r;
+  double sp = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  sp = fma(sp, z, 2.75573137070700676789e-06);
+  sp = fma(sp, z, -1.98412698298579493134e-04);
+  sp = fma(sp, z, 8.33333333332248946124e-03);
+  sp = fma(sp, z, -1.66666666666666324348e-01);
+  const double sr = fma(sp * z, r, r);
+  double cp = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  cp = fma(cp, z, -2.75573143513906633035e-07);
+  cp = fma(cp, z, 2.48015872894767294178e-05);
+  cp = fma(cp, z, -1.38888888888741095749e-03);
+  cp = fma(cp, z, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, cp, fma(z, -0.5, 1.0));
+#if defined(__CUDA_ARCH__)
+  const int j = __double2loint(t);
+#else
+  union { double d; long long i; } u; u.d = t; const int j = (int)(u.i & 0xffffffffLL);
+#endif
+  const double ss = (j & 1) ? cr : sr;
+  const double cc = (j & 1) ? sr : cr;
+  s = (j & 2) ? -ss : ss;
+  c = ((j + 1) & 2) ? -cc : cc;
+}
+
 template <int POL> struct Fn<double, POL> {
   static MRPHY_HD double rsq(double x) {
 #if defined(__CUDA_ARCH__)
@@ -107,13 +140,7 @@ template <int POL> struct Fn<double, POL> {
     return 1.0 / sqrt(x);
 #endif
   }
-  static MRPHY_HD void sc(double x, double& s, double& c) {
-#if defined(__CUDA_ARCH__)
-    sincos(x, &s, &c);
-#else
-    s = sin(x); c = cos(x);
-#endif
-  }
+  static MRPHY_HD void sc(double x, double& s, double& c) { sincos_f64(x, s, c); }
 };
 
 template <> struct Fn<float, TRIG_FAST> {

@@ -119,6 +119,9 @@ extern "C" void host_sim_f64(int pol, int relax, ARGS(double)) {
 extern "C" void host_sincos_f32(int n, const float* x, float* s, float* c) {
   for (int i = 0; i < n; ++i) Fn<float, TRIG_PRECISE>::sc(x[i], s[i], c[i]);
 }
+extern "C" void host_sincos_f64(int n, const double* x, double* s, double* c) {
+  for (int i = 0; i < n; ++i) sincos_f64(x[i], s[i], c[i]);
+}
 extern "C" void host_rsq_f32(int n, const float* x, float* r) {
   for (int i = 0; i < n; ++i) r[i] = Fn<float, TRIG_PRECISE>::rsq(x[i]);
 }

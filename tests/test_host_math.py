@@ -64,6 +64,11 @@ def test_precise_sincos_rsqrt(lib):
     lib.host_sincos_f32(ctypes.c_int(x.size), ptr(x), ptr(s), ptr(c))
     xd = x.astype(np.float64)
     assert np.abs(s - np.sin(xd)).max() < 1.5e-7 and np.abs(c - np.cos(xd)).max() < 1.5e-7
+    xd = np.concatenate([np.linspace(0, 50, 400001), np.logspace(-12, 5, 40001)])
+    sd, cd = np.zeros_like(xd), np.zeros_like(xd)
+    lib.host_sincos_f64(ctypes.c_int(xd.size), ptr(xd), ptr(sd), ptr(cd))
+    xl = xd.astype(np.longdouble)
+    assert np.abs(sd - np.sin(xl)).max() < 3e-16 and np.abs(cd - np.cos(xl)).max() < 3e-16
     y = np.logspace(-24, 6, 100001).astype(np.float32)
     r = np.zeros_like(y)
     lib.host_rsq_f32(ctypes.c_int(y.size), ptr(y), ptr(r))
