@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
 // ------------------------------------------------------------------------------------------
 // backward
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
-__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : 1)) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) == 8 && NC == 1 ? 4 : 1))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
   typedef typename Pack<T, PK>::type V;
   using L = BwdSmem<T, NC, BLKT>;
   constexpr int W = L::W, TR = L::TR, NW = L::NW;
