@@ -904,6 +904,10 @@ int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   k.P = pick_ctas(p, k.N, occ);
   g_last_P = k.P;
   dim3 grid(k.P, k.N);
+  if (getenv("MRPHY_B200_DEBUG"))
+    fprintf(stderr, "[mrphy_b200] fused_bwd<%s,NC=%d,PK=%d,BLK=%d,%s> grid=(%d,%d) tiles=%d occ=%d smem=%zu K=%d\n",
+            sizeof(T) == 4 ? "f32" : "f64", NC, PK, BLKT, POL == TRIG_PRECISE ? "precise" : "fast", k.P, k.N, p.tiles, occ,
+            smem, p.K);
   timing_begin(st);
   kern<<<grid, BLKT, smem, st>>>(k, need_gmi);
   timing_end(st);

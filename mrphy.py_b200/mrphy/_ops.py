@@ -432,8 +432,9 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
         if b1.ndim == 3:
             b1 = b1[..., None]
         nC = rf.shape[3] if rf.ndim == 4 else 1
-        assert b1.shape[2] == 2 and b1.shape[3] == nC, 'b1Map and rf disagree on nCoils'
-        b1 = _inner_contig(b1.expand(N, nM, 2, nC) if b1.shape[:2] != (N, nM) else b1, 2)
+        assert b1.shape[2] == 2 and b1.shape[3] in (1, nC), 'b1Map and rf disagree on nCoils'
+        # a single-coil b1Map with multi-coil rf broadcasts over coils, as upstream (beffective.py:153-165)
+        b1 = _inner_contig(b1.expand(N, nM, 2, nC) if tuple(b1.shape) != (N, nM, 2, nC) else b1, 2)
     df, T1, T2, gam, dtt = (move(x) for x in (Δf_, T1_, T2_, γ_, dt))
     K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2)
     fl = default_flags() if flags is None else flags
