@@ -312,6 +312,8 @@ def test_full_size_properties_c2(dev, dtype):
                                  gamma=float(np.float32(4257.6)) if dtype == f32 else 4257.6,
                                  dt=float(np.float32(4e-6)) if dtype == f32 else 4e-6)
     tolM, tolG = (ATOL64, RTOL_G64) if dtype == f64 else (5e-5, RTOL_G32)
+    print(f'[C2 {dtype}] max|dM|={mx(Mo[:, sub.to(dev)], ref["Mo"]):.2e} grf rel={rel(p.rf.grad, ref["grf"]):.2e} '
+          f'ggr rel={rel(p.gr.grad, ref["ggr"]):.2e}')
     assert mx(Mo[:, sub.to(dev)], ref['Mo']) < tolM
     assert rel(p.rf.grad, ref['grf']) < tolG and rel(p.gr.grad, ref['ggr']) < tolG
     Mn = cube.applypulse(p, b1Map_=b1.to(dev), doRelax=False).detach()
