@@ -29,15 +29,22 @@ __global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_ar
   const T lx = lp[0], ly = lp[1], lz = lp[2];
   const T bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
   const T* bp = a.b1 ? (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm : nullptr;
+  // waveform pointers advance by 256 steps per unrolled iteration: no per-step 64-bit multiplies
+  const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)(tb0 + threadIdx.x) * a.rf_st;
+  const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)(tb0 + threadIdx.x) * a.gr_st;
+  const int64_t rf_step = 256 * a.rf_st, gr_step = 256 * a.gr_st;
+  const bool one = a.nC == 1;
+  const T br0 = bp ? bp[0] : (T)1, bi0 = bp ? bp[a.nC] : (T)0;
 #pragma unroll
-  for (int u = 0; u < SPT; ++u) {
+  for (int u = 0; u < SPT; ++u, rf += rf_step, gr += gr_step) {
     const int j = u * 256 + threadIdx.x;      // consecutive threads -> consecutive steps: coalesced waveform reads
-    const int t = tb0 + j;
     T bx = 0, by = 0, bz = 0;
-    if (t < a.nT) {
-      const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
-      const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
-      if (bp) {
+    if (tb0 + j < a.nT) {
+      if (one) {                              // single coil (with or without b1Map): the common case, no loop
+        const T rx = rf[0], ry = rf[a.rf_sx];
+        bx = br0 * rx - bi0 * ry;
+        by = br0 * ry + bi0 * rx;
+      } else if (bp) {
         for (int c = 0; c < a.nC; ++c) {     // Re/Im of b1*rf summed over coils (beffective.py:160-165)
           const T rx = rf[c * a.rf_sc], ry = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
           bx += br * rx - bi * ry;

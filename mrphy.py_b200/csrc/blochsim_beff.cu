@@ -178,24 +178,42 @@ template <typename T>
 __device__ __forceinline__ void tile_load_async(const T* __restrict__ B, int64_t B_sm, int i0, int nM, int t0, int nbytes,
                                                 unsigned char* tile, int lane) {
   const int nch = nbytes >> 4;             // chunks per row in this tile (<= 12)
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(B + (int64_t)t0 * 3);
+  const int64_t rowb = B_sm * (int64_t)sizeof(T);
+  if (nch == CHUNKS) {                     // full tile: compile-time divisor, 12 copies per lane
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int q = k * 32 + lane, r = q / CHUNKS, c = q - r * CHUNKS;
+      cp_async16(tile + r * PITCHB + c * 16, base + (int64_t)min(i0 + r, nM - 1) * rowb + c * 16);
+    }
+    return;
+  }
   for (int q = lane; q < 32 * nch; q += 32) {
     const int r = q / nch, c = q - r * nch;
-    const int i = min(i0 + r, nM - 1);
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(B + (int64_t)i * B_sm + (int64_t)t0 * 3) + c * 16;
-    cp_async16(tile + r * PITCHB + c * 16, src);
+    cp_async16(tile + r * PITCHB + c * 16, base + (int64_t)min(i0 + r, nM - 1) * rowb + c * 16);
   }
 }
 template <typename T>
 __device__ __forceinline__ void tile_store16(T* __restrict__ G, int64_t G_sm, int i0, int nM, int t0, int nbytes,
                                              const unsigned char* tile, int lane) {
   const int nch = nbytes >> 4;
+  unsigned char* base = reinterpret_cast<unsigned char*>(G + (int64_t)t0 * 3);
+  const int64_t rowb = G_sm * (int64_t)sizeof(T);
+  if (nch == CHUNKS) {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int q = k * 32 + lane, r = q / CHUNKS, c = q - r * CHUNKS;
+      if (i0 + r < nM)
+        *reinterpret_cast<float4*>(base + (int64_t)(i0 + r) * rowb + c * 16) =
+            *reinterpret_cast<const float4*>(tile + r * PITCHB + c * 16);
+    }
+    return;
+  }
   for (int q = lane; q < 32 * nch; q += 32) {
     const int r = q / nch, c = q - r * nch;
-    const int i = i0 + r;
-    if (i < nM) {
-      const float4 v = *reinterpret_cast<const float4*>(tile + r * PITCHB + c * 16);
-      *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(G + (int64_t)i * G_sm + (int64_t)t0 * 3) + c * 16) = v;
-    }
+    if (i0 + r < nM)
+      *reinterpret_cast<float4*>(base + (int64_t)(i0 + r) * rowb + c * 16) =
+          *reinterpret_cast<const float4*>(tile + r * PITCHB + c * 16);
   }
 }
 
