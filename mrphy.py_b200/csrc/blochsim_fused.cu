@@ -92,8 +92,7 @@ __device__ __forceinline__ double mkv(double a, double, double*) { return a; }
 
 // per-spin prologue shared by forward and backward: constants of one spin, in scalar T
 template <typename T, int NC, bool RELAX>
-__device__ __forceinline__ void load_spin(const KArgs<T>& a, int n, int i, SpinConst<T, NC>& k) {
-  const T* lp = a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
+__device__ __forceinline__ void load_spin(const KArgs<T>& a, int n, int i, T lx, T ly, T lz, SpinConst<T, NC>& k) {
   T br[NC], bi[NC];
   if (a.b1) {
     const T* bp = a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;
@@ -108,16 +107,17 @@ __device__ __forceinline__ void load_spin(const KArgs<T>& a, int n, int i, SpinC
   const double df = a.df.ptr ? ld_param(a.df, n, i) : 0.0;
   const double t1 = RELAX ? ld_param(a.T1, n, i) : 1.0;
   const double t2 = RELAX ? ld_param(a.T2, n, i) : 1.0;
-  make_consts<T, NC>(k, gam, dt, RELAX, t1, t2, df, lp[0], lp[1], lp[2], a.b1 ? br : nullptr, a.b1 ? bi : nullptr);
+  make_consts<T, NC>(k, gam, dt, RELAX, t1, t2, df, lx, ly, lz, a.b1 ? br : nullptr, a.b1 ? bi : nullptr);
 }
 template <typename T, typename V, int NC, int PK, bool RELAX>
-__device__ __forceinline__ void load_consts_v(const KArgs<T>& a, int n, const int (&idx)[PK], SpinConst<V, NC>& k) {
+__device__ __forceinline__ void load_consts_v(const KArgs<T>& a, int n, const int (&idx)[PK], V lx, V ly, V lz,
+                                              SpinConst<V, NC>& k) {
   if constexpr (PK == 1) {
-    load_spin<T, NC, RELAX>(a, n, idx[0], k);
+    load_spin<T, NC, RELAX>(a, n, idx[0], lx, ly, lz, k);
   } else {
     SpinConst<float, NC> k0, k1;
-    load_spin<float, NC, RELAX>(a, n, idx[0], k0);
-    load_spin<float, NC, RELAX>(a, n, idx[1], k1);
+    load_spin<float, NC, RELAX>(a, n, idx[0], getq<0>(lx), getq<0>(ly), getq<0>(lz), k0);
+    load_spin<float, NC, RELAX>(a, n, idx[1], getq<1>(lx), getq<1>(ly), getq<1>(lz), k1);
     k = pack2<NC>(k0, k1);
   }
 }
@@ -129,6 +129,31 @@ __device__ __forceinline__ void load_vec3(const T* base, int64_t stride, const i
   x = mkv(p0[0], p1[0], (V*)nullptr);
   y = mkv(p0[1], p1[1], (V*)nullptr);
   z = mkv(p0[2], p1[2], (V*)nullptr);
+}
+
+// Per-spin 3-vectors (Mi, Mo, dL/dMo, loc) of a whole tile are one contiguous run of 12*TILE bytes when the spin stride
+// is 3 elements: the CTA reads it ONCE with coalesced 128-bit loads into `scr`, then every thread picks its spins.
+// Ragged last tiles, foreign strides and unaligned bases take the direct (L1-coalesced) path.  CTA-uniform branch.
+template <typename T, typename V, int PK, int BLKT>
+__device__ __forceinline__ void load_vec3_tile(const T* base, int64_t stride, int tile, int nM, const int (&idx)[PK],
+                                               T* scr, V& x, V& y, V& z) {
+  constexpr int TILE = BLKT * PK;
+  const T* src = base + (int64_t)tile * TILE * 3;
+  const bool coop = stride == 3 && (tile + 1) * TILE <= nM && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  if (coop) {
+    constexpr int NVEC = TILE * 3 * (int)sizeof(T) / 16;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(scr);
+    for (int q = threadIdx.x; q < NVEC; q += BLKT) d4[q] = s4[q];
+    __syncthreads();
+    const int l0 = threadIdx.x, l1 = (PK - 1) * BLKT + threadIdx.x;
+    x = mkv(scr[3 * l0], scr[3 * l1], (V*)nullptr);
+    y = mkv(scr[3 * l0 + 1], scr[3 * l1 + 1], (V*)nullptr);
+    z = mkv(scr[3 * l0 + 2], scr[3 * l1 + 2], (V*)nullptr);
+    __syncthreads();
+  } else {
+    load_vec3<T, V, PK>(base, stride, idx, x, y, z);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -170,6 +195,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
   typedef typename Pack<T, PK>::type V;
   constexpr int W = 2 * NC + 3;
   __shared__ __align__(128) T wbuf[2][W * TCMAX];
+  __shared__ __align__(16) T scr[3 * BLKT * PK];
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
@@ -200,8 +226,12 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       ok[q] = i < nM;
       idx[q] = ok[q] ? i : nM - 1;
     }
-    load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, k);
-    load_vec3<T, V, PK>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, idx, mx, my, mz);
+    {
+      V lx, ly, lz;
+      load_vec3_tile<T, V, PK, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idx, scr, lx, ly, lz);
+      load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, lx, ly, lz, k);
+    }
+    load_vec3_tile<T, V, PK, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idx, scr, mx, my, mz);
     for (int c = 0; c < nChunks; ++c, ++it) {
       if (tid == 0 && it + 1 < total) {   // prefetch the next chunk (possibly chunk 0 of the next tile)
         const int cn = (c + 1 == nChunks) ? 0 : c + 1;
@@ -278,6 +308,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
   T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile
   T(*cta)[W][TR] = reinterpret_cast<T(*)[W][TR]>(smem_raw + L::cta);          // per-warp tile sums
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::bar);
+  __shared__ __align__(16) T scr[3 * BLKT * PK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
   const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
@@ -313,9 +344,13 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
       ok[q] = i < nM;
       idx[q] = ok[q] ? i : nM - 1;
     }
-    load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, k);
-    load_vec3<T, V, PK>(a.Mo + (size_t)n * nM * 3, 3, idx, mx, my, mz);
-    load_vec3<T, V, PK>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, idx, hx, hy, hz);
+    {
+      V lx, ly, lz;
+      load_vec3_tile<T, V, PK, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idx, scr, lx, ly, lz);
+      load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, lx, ly, lz, k);
+    }
+    load_vec3_tile<T, V, PK, BLKT>(a.Mo + (size_t)n * nM * 3, 3, tile, nM, idx, scr, mx, my, mz);
+    load_vec3_tile<T, V, PK, BLKT>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, tile, nM, idx, scr, hx, hy, hz);
     {   // padding lanes carry a zero adjoint: they add nothing to the spin sums
       const T z0 = ok[0] ? (T)1 : (T)0, z1 = ok[PK - 1] ? (T)1 : (T)0;
       const V zm = mkv(z0, z1, (V*)nullptr);
@@ -434,6 +469,7 @@ template <int POL, bool RELAX, int BLKT>
 __global__ void __launch_bounds__(BLKT) fused_fwd_tp_kernel(const KArgs<float> a) {
   constexpr int W = 5;
   __shared__ __align__(128) float wbuf[2][W * TCMAX];
+  __shared__ __align__(16) float scr[3 * BLKT];
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
@@ -458,9 +494,14 @@ __global__ void __launch_bounds__(BLKT) fused_fwd_tp_kernel(const KArgs<float> a
     const int i = tile * BLKT + tid;
     const bool ok = i < nM;
     const int idx = ok ? i : nM - 1;
-    load_spin<float, 1, RELAX>(a, n, idx, k);
-    const float* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)idx * a.Mi_sm;
-    float mx = mp[0], my = mp[1], mz = mp[2];
+    const int idxv[1] = {idx};
+    float mx, my, mz;
+    {
+      float lx, ly, lz;
+      load_vec3_tile<float, float, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idxv, scr, lx, ly, lz);
+      load_spin<float, 1, RELAX>(a, n, idx, lx, ly, lz, k);
+    }
+    load_vec3_tile<float, float, 1, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idxv, scr, mx, my, mz);
     for (int c = 0; c < nChunks; ++c, ++it) {
       if (tid == 0 && it + 1 < total) {
         const int cn = (c + 1 == nChunks) ? 0 : c + 1;
@@ -517,6 +558,7 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
   float(*red)[W][TR][32] = reinterpret_cast<float(*)[W][TR][32]>(smem_raw + L::red);
   float(*cta)[W][TR] = reinterpret_cast<float(*)[W][TR]>(smem_raw + L::cta);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::bar);
+  __shared__ __align__(16) float scr[3 * BLKT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
   const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(float));
@@ -546,11 +588,16 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
     const int i = tile * BLKT + tid;
     const bool ok = i < nM;
     const int idx = ok ? i : nM - 1;
-    load_spin<float, 1, RELAX>(a, n, idx, k);
-    const float* mp = a.Mo + ((size_t)n * nM + idx) * 3;
-    float mx = mp[0], my = mp[1], mz = mp[2];
-    const float* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)idx * a.gMo_sm;
-    float hx = ok ? gp[0] : 0.f, hy = ok ? gp[1] : 0.f, hz = ok ? gp[2] : 0.f;
+    const int idxv[1] = {idx};
+    float mx, my, mz, hx, hy, hz;
+    {
+      float lx, ly, lz;
+      load_vec3_tile<float, float, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idxv, scr, lx, ly, lz);
+      load_spin<float, 1, RELAX>(a, n, idx, lx, ly, lz, k);
+    }
+    load_vec3_tile<float, float, 1, BLKT>(a.Mo + (size_t)n * nM * 3, 3, tile, nM, idxv, scr, mx, my, mz);
+    load_vec3_tile<float, float, 1, BLKT>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, tile, nM, idxv, scr, hx, hy, hz);
+    if (!ok) hx = hy = hz = 0.f;
     auto emit = [&](float Fx, float Fy, float Fz, int row) {
       red[warp][0][row][lane] = fmaf(k.cbr[0], Fx, k.cbi[0] * Fy);
       red[warp][1][row][lane] = fmaf(-k.cbi[0], Fx, k.cbr[0] * Fy);
@@ -898,7 +945,7 @@ template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
 int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   constexpr size_t smem = BwdSmem<T, NC, BLKT>::bytes;
   auto kern = fused_bwd_kernel<T, POL, RELAX, NC, PK, BLKT>;
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
   k.P = pick_ctas(p, k.N, occ);
@@ -928,7 +975,7 @@ int launch_tp(bool bwd, KArgs<float> k, const Plan& p, int need_gmi, cudaStream_
   if (bwd) {
     constexpr size_t smem = BwdSmem<float, 1, BLKT>::bytes;
     auto kern = fused_bwd_tp_kernel<POL, RELAX, BLKT>;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
     k.P = pick_ctas(p, k.N, occ);
     g_last_P = k.P;
