@@ -19,54 +19,68 @@ namespace mrphy {
 // 12*RB-byte run when rows are 16-byte aligned (ALIGNED), as scalar stores otherwise.
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
-  constexpr int SPT = 4, RB = 256 * SPT;
-  __shared__ __align__(16) T stage[3 * RB];
+  constexpr int SPT = 4, RB = 256 * SPT, SPB = 8;   // steps per thread, steps per block, spins per block
+  __shared__ __align__(16) T stage[2][3 * RB];       // double-buffered: stores of spin s overlap the math of spin s+1
   const int n = blockIdx.y;
   const int64_t bid = blockIdx.x;
-  const int i = (int)(bid / tblocks);
+  const int sb = (int)(bid / tblocks);               // spin block
   const int tb0 = (int)(bid % tblocks) * RB;
-  const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
-  const T lx = lp[0], ly = lp[1], lz = lp[2];
-  const T bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
-  const T* bp = a.b1 ? (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm : nullptr;
-  // waveform pointers advance by 256 steps per unrolled iteration: no per-step 64-bit multiplies
-  const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)(tb0 + threadIdx.x) * a.rf_st;
-  const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)(tb0 + threadIdx.x) * a.gr_st;
-  const int64_t rf_step = 256 * a.rf_st, gr_step = 256 * a.gr_st;
-  const bool one = a.nC == 1;
-  const T br0 = bp ? bp[0] : (T)1, bi0 = bp ? bp[a.nC] : (T)0;
-#pragma unroll
-  for (int u = 0; u < SPT; ++u, rf += rf_step, gr += gr_step) {
-    const int j = u * 256 + threadIdx.x;      // consecutive threads -> consecutive steps: coalesced waveform reads
-    T bx = 0, by = 0, bz = 0;
-    if (tb0 + j < a.nT) {
-      if (one) {                              // single coil (with or without b1Map): the common case, no loop
-        const T rx = rf[0], ry = rf[a.rf_sx];
-        bx = br0 * rx - bi0 * ry;
-        by = br0 * ry + bi0 * rx;
-      } else if (bp) {
-        for (int c = 0; c < a.nC; ++c) {     // Re/Im of b1*rf summed over coils (beffective.py:160-165)
-          const T rx = rf[c * a.rf_sc], ry = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
-          bx += br * rx - bi * ry;
-          by += br * ry + bi * rx;
-        }
-      } else {
-        for (int c = 0; c < a.nC; ++c) { bx += rf[c * a.rf_sc]; by += rf[a.rf_sx + c * a.rf_sc]; }
-      }
-      bz = lx * gr[0] + ly * gr[a.gr_sx] + lz * gr[2 * a.gr_sx] + bz0;
-    }
-    stage[3 * j] = bx; stage[3 * j + 1] = by; stage[3 * j + 2] = bz;
-  }
-  __syncthreads();
   const int cnt = min(RB, a.nT - tb0);
-  T* out = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + tb0) * 3;
-  if (ALIGNED) {
-    const int nvec = cnt * 3 * (int)sizeof(T) / 16;
-    float4* dst = reinterpret_cast<float4*>(out);
-    const float4* src = reinterpret_cast<const float4*>(stage);
-    for (int q = threadIdx.x; q < nvec; q += 256) dst[q] = src[q];
-  } else {
-    for (int q = threadIdx.x; q < 3 * cnt; q += 256) out[q] = stage[q];
+  // the block's waveform samples live in registers across its SPB spins
+  T rx[SPT], ry[SPT], gx[SPT], gy[SPT], gz[SPT];
+  const bool one = a.nC == 1;
+#pragma unroll
+  for (int u = 0; u < SPT; ++u) {
+    const int t = tb0 + u * 256 + threadIdx.x;
+    rx[u] = ry[u] = gx[u] = gy[u] = gz[u] = (T)0;
+    if (t < a.nT) {
+      const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
+      gx[u] = gr[0]; gy[u] = gr[a.gr_sx]; gz[u] = gr[2 * a.gr_sx];
+      if (one || !a.b1) {   // single coil, or coils summed because there is no b1Map (beffective.py:147-151)
+        const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
+        for (int c = 0; c < a.nC; ++c) { rx[u] += rf[c * a.rf_sc]; ry[u] += rf[a.rf_sx + c * a.rf_sc]; }
+      }
+    }
+  }
+  for (int s = 0; s < SPB; ++s) {
+    const int i = sb * SPB + s;
+    if (i >= a.nM) break;
+    T* st = stage[s & 1];
+    const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
+    const T lx = lp[0], ly = lp[1], lz = lp[2];
+    const T bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
+    const T* bp = a.b1 ? (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm : nullptr;
+    const T br0 = bp ? bp[0] : (T)1, bi0 = bp ? bp[a.nC] : (T)0;
+#pragma unroll
+    for (int u = 0; u < SPT; ++u) {
+      const int j = u * 256 + threadIdx.x;
+      T bx, by;
+      if (one || !bp) {
+        bx = br0 * rx[u] - bi0 * ry[u];
+        by = br0 * ry[u] + bi0 * rx[u];
+      } else {              // several coils with a b1Map (beffective.py:160-165)
+        bx = by = (T)0;
+        if (tb0 + j < a.nT) {
+          const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)(tb0 + j) * a.rf_st;
+          for (int c = 0; c < a.nC; ++c) {
+            const T x = rf[c * a.rf_sc], y = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
+            bx += br * x - bi * y;
+            by += br * y + bi * x;
+          }
+        }
+      }
+      st[3 * j] = bx; st[3 * j + 1] = by; st[3 * j + 2] = lx * gx[u] + ly * gy[u] + lz * gz[u] + bz0;
+    }
+    __syncthreads();   // also orders buffer reuse: stage[s&1] was last read two iterations ago
+    T* out = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + tb0) * 3;
+    if (ALIGNED) {
+      const int nvec = cnt * 3 * (int)sizeof(T) / 16;
+      float4* dst = reinterpret_cast<float4*>(out);
+      const float4* src = reinterpret_cast<const float4*>(st);
+      for (int q = threadIdx.x; q < nvec; q += 256) dst[q] = src[q];
+    } else {
+      for (int q = threadIdx.x; q < 3 * cnt; q += 256) out[q] = st[q];
+    }
   }
 }
 
@@ -145,7 +159,7 @@ extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream)
   if (a->df.ptr && !a->gamma.ptr) return fail(MRPHY_ERR_ARG, "df needs gamma%s");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int tblocks = (a->nT + 1023) / 1024;
-  const int64_t gx = (int64_t)a->nM * tblocks;
+  const int64_t gx = (int64_t)((a->nM + 7) / 8) * tblocks;   // 8 spins per block (SPB)
   if (gx > 2147483647LL) return fail(MRPHY_ERR_ARG, "nM*nT too large for one launch%s");
   dim3 grid((unsigned)gx, a->N);
   timing_begin(st);
