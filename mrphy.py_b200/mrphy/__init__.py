@@ -15,41 +15,44 @@ C ABI (``include/mrphy_b200.h``, ``libmrphy_b200.so``).  There is no CPU impleme
 path: calling it with CPU tensors, or without the built library, raises ``RuntimeError``.
 """
 import ctypes
+from math import inf, pi as π  # noqa: F401
 
-from math import pi as π, inf  # noqa: F401
 import torch
 from torch import tensor
 
-γH = tensor(4257.6, dtype=torch.double)    # Hz/Gauss, water proton gyromagnetic ratio
-T1G = tensor(1.47, dtype=torch.double)     # s, grey-matter T1
-T2G = tensor(0.07, dtype=torch.double)     # s, grey-matter T2
 
-dt0 = tensor(4e-6, dtype=torch.double)     # s, default dwell time
-gmax0 = tensor(5, dtype=torch.double)      # Gauss/cm
-smax0 = tensor(12e3, dtype=torch.double)   # Gauss/cm/s
-rfmax0 = tensor(0.25, dtype=torch.double)  # Gauss
+def _f64(value) -> torch.Tensor:
+    """Package constants are float64 0-dim tensors: they are the default of every keyword argument of the API."""
+    return tensor(value, dtype=torch.float64)
+
+
+γH = _f64(4257.6)        # Hz/Gauss   gyromagnetic ratio of the water proton
+T1G, T2G = _f64(1.47), _f64(0.07)                     # s          grey matter
+dt0 = _f64(4e-6)         # s          default dwell time
+gmax0, smax0, rfmax0 = _f64(5), _f64(12e3), _f64(0.25)   # Gauss/cm, Gauss/cm/s, Gauss: default hardware limits
 
 _slice = slice(None)
 
 
 def cuda_is_available() -> bool:
-    r"""``True`` when a CUDA driver library can be loaded (same probe as the reference)."""
-    for name in ('libcuda.so', 'libcuda.so.1', 'libcuda.dylib', 'cuda.dll'):
+    r"""Whether a CUDA driver library can be dlopen-ed (the probe the reference uses, ``__init__.py:70-83``)."""
+    def loads(name):
         try:
             ctypes.CDLL(name)
-            return True
         except OSError:
-            pass
-    return False
+            return False
+        return True
+    return any(loads(n) for n in ('libcuda.so', 'libcuda.so.1', 'libcuda.dylib', 'cuda.dll'))
 
 
 __CUDA_IS_AVAILABLE__ = cuda_is_available()
 
-try:
+try:   # cupy is only used by utils.rf_c2r / rf_r2c on cupy arrays
     import cupy  # noqa: F401
-    __CUPY_IS_AVAILABLE__ = True
 except ImportError:
     __CUPY_IS_AVAILABLE__ = False
+else:
+    __CUPY_IS_AVAILABLE__ = True
 
 from mrphy import (utils, beffective, sims, slowsims, mobjs)  # noqa: E402
 from mrphy.version import __version__  # noqa: E402,F401
