@@ -53,8 +53,8 @@ template <typename T, int NC, int BLKT> struct BwdSmem {
   static constexpr int TR = pick_tr(W, (int)sizeof(T));
   static constexpr size_t wbuf = 0;                                                // T[2][W*TCMAX]
   static constexpr size_t red = (2 * W * TCMAX * sizeof(T) + 127) / 128 * 128;     // T[NW][W][TR][32]
-  static constexpr size_t cta = red + (size_t)NW * W * TR * 32 * sizeof(T);        // T[NW][W][TR]
-  static constexpr size_t bar = (cta + (size_t)NW * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
+  static constexpr size_t cta = red + (size_t)NW * W * TR * 32 * sizeof(T);        // T[2][NW][W][TR] (double-buffered)
+  static constexpr size_t bar = (cta + (size_t)2 * NW * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
   static constexpr size_t bytes = bar + 16;
 };
 
@@ -296,6 +296,33 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
   }
 }
 
+// Column sums of one warp's transposition tile red[W][TR][32]: lane l owns row r = l % TR and adds up the TR source
+// lanes of its group, then the 32/TR groups meet through shuffles; lanes < TR publish out[w][r].
+// fp32, TR == 16: four 128-bit loads per row (chunk order rotated by the row: at most 2-way bank conflicts) instead
+// of sixteen scalar ones.  Otherwise scalar loads with a rotated start (conflict-free).
+template <typename T, int W, int TR>
+__device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int lane, T (*out)[TR]) {
+  const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    T sum = (T)0;
+    if constexpr (sizeof(T) == 4 && TR == 16) {
+      const float4* row = reinterpret_cast<const float4*>(&tile[w][r][grp]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = row[(q + r) & 3];
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < TR; ++q) sum += tile[w][r][grp + ((q + lane) & (TR - 1))];
+    }
+#pragma unroll
+    for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane < TR) out[w][r] = sum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
     for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
     return;
   }
-  uint32_t it = 0;
+  uint32_t it = 0, red_par = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
     SpinConst<V, NC> k;
@@ -416,31 +443,22 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
           }
         }
         __syncwarp();
-        {   // lane l owns row r = l%TR and sums the TR source lanes of its group (rotated start:
-            // conflict-free), then the 32/TR groups meet through shuffles
-          const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            T sum = (T)0;
-#pragma unroll
-            for (int q = 0; q < TR; ++q) sum += red[warp][w][r][grp + ((q + lane) & (TR - 1))];
-#pragma unroll
-            for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane < TR) cta[warp][w][r] = sum;
-          }
-        }
-        __syncthreads();
+        T(*ctab)[W][TR] = cta + (size_t)(red_par & 1) * NW;   // this tile's half of the double buffer
+        warp_tile_reduce<T, W, TR>(red[warp], lane, ctab[warp]);
+        __syncthreads();   // the only CTA barrier per tile: `cta` alternates, `red` is re-written after it
         for (int e = tid; e < W * TR; e += BLKT) {   // fixed-order combine of the warps
           const int w = e / TR, r = e % TR;
           if (j0 + r < j1) {
-            T sum = cta[0][w][r];
+            T sum = ctab[0][w][r];
 #pragma unroll
-            for (int q = 1; q < NW; ++q) sum += cta[q][w][r];
+            for (int q = 1; q < NW; ++q) sum += ctab[q][w][r];
             T* dst = part + (size_t)w * nT + (c * K + j0 + r);
-            *dst = first ? sum : *dst + sum;
+            // the slot belongs to this CTA alone, so a fire-and-forget RED keeps the result bitwise
+            // reproducible and takes the L2 round trip of a read-modify-write off the critical path
+            if (first) *dst = sum; else atomicAdd(dst, sum);
           }
         }
-        __syncthreads();
+        ++red_par;
         j1 = j0;
       }
       if (c > 0) {   // resynchronise the reconstructed state with the forward checkpoint
@@ -581,7 +599,7 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
     for (int e = tid; e < W * nT; e += BLKT) part[e] = 0.f;
     return;
   }
-  uint32_t it = 0;
+  uint32_t it = 0, red_par = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
     SpinConst<float, 1> k;
@@ -654,30 +672,20 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
           }
         }
         __syncwarp();
-        {
-          const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            float sum = 0.f;
-#pragma unroll
-            for (int q = 0; q < TR; ++q) sum += red[warp][w][r][grp + ((q + lane) & (TR - 1))];
-#pragma unroll
-            for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane < TR) cta[warp][w][r] = sum;
-          }
-        }
+        float(*ctab)[W][TR] = cta + (size_t)(red_par & 1) * NW;
+        warp_tile_reduce<float, W, TR>(red[warp], lane, ctab[warp]);
         __syncthreads();
         for (int e = tid; e < W * TR; e += BLKT) {
           const int w = e / TR, r = e % TR;
           if (j0 + r < j1) {
-            float sum = cta[0][w][r];
+            float sum = ctab[0][w][r];
 #pragma unroll
-            for (int q = 1; q < NW; ++q) sum += cta[q][w][r];
+            for (int q = 1; q < NW; ++q) sum += ctab[q][w][r];
             float* dst = part + (size_t)w * nT + (c * K + j0 + r);
-            *dst = first ? sum : *dst + sum;
+            if (first) *dst = sum; else atomicAdd(dst, sum);
           }
         }
-        __syncthreads();
+        ++red_par;
         j1 = j0;
       }
       if (c > 0) { mx = kx; my = ky; mz = kz; }
