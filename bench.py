@@ -290,11 +290,14 @@ def run_ours(args):
                            'unit': UNIT, 'ms_per_step': alt_ms / args.steps,
                            'note': 'opt-in: ~2x the fp32 error of the default polynomial trigonometry'}
         line['config']['trig'] = 'precise (default)' if dtype == torch.float32 else 'fp64 libm'
-        line['cpu_baseline'] = cpu_baseline(args, nT)
-        try:
-            line['torch_eager_same_gpu'] = eager_cuda_baseline(args, nT)
-        except Exception as e:      # context only
-            line['torch_eager_same_gpu'] = {'error': str(e)[:100]}
+        if world == 1:      # CPU / eager baselines are timed at N=1 only; the other ranks must not wait on them
+            line['cpu_baseline'] = cpu_baseline(args, nT)
+            try:
+                line['torch_eager_same_gpu'] = eager_cuda_baseline(args, nT)
+            except Exception as e:      # context only
+                line['torch_eager_same_gpu'] = {'error': str(e)[:100]}
+        else:
+            line['cpu_baseline'] = None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
