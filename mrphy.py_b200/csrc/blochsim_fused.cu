@@ -5,7 +5,8 @@
 //
 // Kernels in this file
 //   pack_waveform_kernel      rf (N,2,nT[,nC]), gr (N,3,nT) -> wave[N][chunk][W][TCP]  (W = 2*NC+3)
-//   fused_fwd_kernel<T,..>    one spin (or S spins) per thread; checkpoint every K steps
+//   fused_fwd_kernel<T,..>    one spin, or two spins packed in an f2 (FFMA2), per thread; checkpoint every K steps
+//   fused_*_tp_kernel         time-packed fp32 variant (one spin per thread, two steps' coefficients per f2)
 //   fused_bwd_kernel<T,..>    time-reversed state reconstruction + adjoint + spin reduction
 //   grad_finalize_kernel<T>   deterministic sum of the per-CTA partials, reference layout out
 //
@@ -38,7 +39,7 @@ template <> struct Pack<float, 2> { typedef f2 type; };
 #define MRPHY_RED_BUDGET 10240
 #endif
 #ifndef MRPHY_BWD_MINB
-#define MRPHY_BWD_MINB 9     // spin-packed backward: cap registers so that 9 CTAs (18 warps) fit per SM
+#define MRPHY_BWD_MINB 8     // spin-packed backward: 128 registers, 8 CTAs (16 warps) per SM -- measured best of 6..10
 #endif
 constexpr int pick_tr(int W, int elem) {
   int tr = 16;
