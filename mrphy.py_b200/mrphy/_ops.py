@@ -127,9 +127,11 @@ def _impl_blochsim_fused_fwd(Mi: Tensor, rf: Tensor, gr: Tensor, loc: Tensor, df
 
 def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
     N, nM, nT = loc.shape[0], loc.shape[1], rf.shape[2]
-    nck = max((nT + K - 1) // K - 1, 0)
-    return (Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * nck * 3 * nM, 1),)),
-            Mi.new_empty((N * ((nT + K - 1) // K) * 5 * ((K + 3) // 4 * 4),)))
+    chunks = (nT + K - 1) // K
+    nc = 1 if b1 is None else (rf.shape[3] if rf.ndim == 4 else 1)
+    NC = next(c for c in (1, 2, 4, 8, 16) if nc <= c)           # coils held in registers (csrc: make_plan)
+    return (Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * (chunks - 1) * 3 * nM, 1),)),
+            Mi.new_empty((N * chunks * (2 * NC + 3) * ((K + 3) // 4 * 4),)))
 
 
 def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,

@@ -56,6 +56,26 @@ def test_sizing_entry_points(cabi):
     assert L.mrphy_fused_ckpt_elems(a) == 0 and b'K must be' in L.mrphy_last_error()
 
 
+@pytest.mark.parametrize('nC,K,nT', [(1, 64, 1000), (2, 16, 50), (3, 7, 33), (8, 64, 64), (16, 48, 100)])
+def test_fake_shapes_match_sizing_calls(cabi, nC, K, nT):
+    """The torch.library fake (shape-only) implementation must allocate what the C sizing entry points ask for."""
+    import torch
+    from mrphy import _ops
+    N, nM = 2, 300
+    a = cabi.FusedArgs()
+    a.dtype, a.N, a.nM, a.nT, a.nC, a.K = cabi.MRPHY_F32, N, nM, nT, nC, K
+    a.b1 = 1
+    L = cabi.lib()
+    m = dict(device='meta')
+    rf = torch.empty(N, 2, nT, nC, **m) if nC > 1 else torch.empty(N, 2, nT, **m)
+    b1 = torch.empty(N, nM, 2, nC, **m)
+    Mo, ckpt, wave = _ops._fake_blochsim_fused_fwd(torch.empty(N, nM, 3, **m), rf, torch.empty(N, 3, nT, **m),
+                                                   torch.empty(N, nM, 3, **m), None, b1, None, None, None, None, K, 0)
+    assert tuple(Mo.shape) == (N, nM, 3)
+    assert ckpt.numel() == max(L.mrphy_fused_ckpt_elems(a), 1)
+    assert wave.numel() == L.mrphy_fused_wave_elems(a)
+
+
 def test_fails_loudly_without_gpu_or_on_cpu_tensors(cabi):
     import torch
     import mrphy
