@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MRPHY_ABI_VERSION 1
+#define MRPHY_ABI_VERSION 2
 
 enum mrphy_dtype { MRPHY_F32 = 0, MRPHY_F64 = 1 };
 
@@ -142,16 +142,39 @@ typedef struct mrphy_rfgr2beff_args {
 } mrphy_rfgr2beff_args;
 int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream);
 
-/* Hargreaves A/B propagation, replacing beffective.beff2ab (beffective.py:40-104), forward only:
- * A (N,nM,3,3), B (N,nM,3) contiguous out; E1, E2 are the per-step relaxation FACTORS as upstream. */
+/* Hargreaves A/B propagation, replacing beffective.beff2ab (beffective.py:40-104) and its autograd:
+ * A (N,nM,3,3), B (N,nM,3) contiguous out; E1, E2 are the per-step relaxation FACTORS as upstream.
+ * With `ckpt` non-NULL the forward also stores the 12 entries of [A|B] every K steps
+ * (mrphy_beff2ab_ckpt_elems() elements) for mrphy_beff2ab_bwd, which takes dL/dA, dL/dB and writes
+ * dL/dBeff (N,nM,nT,3) and, per spin, gP (N,nM,3) = [dL/dE1, dL/dE2, dL/d(2*pi*gamma*dt)] for the caller to
+ * reduce onto the broadcast shapes of E1, E2, gamma, dt.  K == 1 never divides by E1/E2 (valid for E = 0). */
 typedef struct mrphy_beff2ab_args {
   int32_t dtype, flags;
-  int32_t N, nM, nT, _pad;
+  int32_t N, nM, nT, K;                               /* K: checkpoint interval (used when ckpt != NULL) */
   const void* Beff; int64_t B_sn, B_sm;               /* (N,nM,nT,3), (nT,3) contiguous */
   mrphy_param E1, E2, gamma, dt;
-  void* A; void* B;
+  void* A; void* B;                                   /* fwd out / bwd in */
+  void* ckpt;                                         /* fwd out (optional) / bwd in */
+  const void* gA; const void* gB;                     /* bwd in, contiguous like A, B */
+  void* gBeff; void* gP;                              /* bwd out, contiguous */
 } mrphy_beff2ab_args;
+size_t mrphy_beff2ab_ckpt_elems(const mrphy_beff2ab_args* a);
 int mrphy_beff2ab(const mrphy_beff2ab_args* a, void* cuda_stream);
+int mrphy_beff2ab_bwd(const mrphy_beff2ab_args* a, void* cuda_stream);
+
+/* Rotation axis / angle of a field, replacing beffective.beff2u-phi (beffective.py:14-37) and its autograd:
+ * U = beff / max(|beff|, 1e-12) (N,nM,3), Phi = -|beff| * g (N,nM), g = the caller's 2*pi*gamma*dt.
+ * adjoint != 0: from gU, gPhi write gbeff (N,nM,3) and, when gg != NULL, the per-spin dL/dg (N,nM). */
+typedef struct mrphy_beff2uphi_args {
+  int32_t dtype, adjoint;
+  int32_t N, nM;
+  const void* beff; int64_t b_sn, b_sm;               /* (N,nM,3) inner stride 1 */
+  mrphy_param g;
+  void* U; void* Phi;                                 /* forward out, contiguous */
+  const void* gU; const void* gPhi;                   /* adjoint in, contiguous (either may be NULL = zero) */
+  void* gbeff; void* gg;                              /* adjoint out, contiguous */
+} mrphy_beff2uphi_args;
+int mrphy_beff2uphi(const mrphy_beff2uphi_args* a, void* cuda_stream);
 
 /* Free precession, replacing sims.FreePrec.forward / .backward (sims.py:325-421): rotate about z by
  * -2*pi*df*dur then relax over dur (adjoint != 0: the transposed map applied to dL/dMo).            */

@@ -1,5 +1,5 @@
 // Stand-alone operators around the fused path, sm_100a: rfgr2beff (dense field synthesis), beff2ab
-// (Hargreaves A/B propagation) and freeprec.  All are HBM-bound / one-shot; they exist so that every function of
+// (Hargreaves A/B propagation, forward and adjoint), beff2u-phi and freeprec.  All are HBM-bound / one-shot; they exist so that every function of
 // the reference's path (a3, a5, f-1) has a native implementation behind the same C ABI.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(128) beff2ab_kernel(const mrphy_beff2ab_args a
   const T e1 = E1 - (T)1, e2 = E2 - (T)1;
   T cx[4] = {1, 0, 0, 0}, cy[4] = {0, 1, 0, 0}, cz[4] = {0, 0, 1, 0};   // columns of [A|B]
   const T* B = (const T*)a.Beff + (int64_t)n * a.B_sn + (int64_t)i * a.B_sm;
+  T* ck = a.ckpt ? (T*)a.ckpt + (size_t)n * ((a.nT - 1) / a.K) * 12 * (size_t)a.nM : nullptr;
   for (int t = 0; t < a.nT; ++t) {
     const T bx = g * B[3 * t], by = g * B[3 * t + 1], bz = g * B[3 * t + 2];
     const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
@@ -109,12 +110,132 @@ __global__ void __launch_bounds__(128) beff2ab_kernel(const mrphy_beff2ab_args a
       cz[q] = fma_(e1, cz[q], cz[q]);
     }
     cz[3] -= e1;
+    const int t1 = t + 1;
+    if (ck && t1 % a.K == 0 && t1 < a.nT) {   // [A|B] after t1 steps, component-major so spins coalesce
+      T* cp = ck + (size_t)(t1 / a.K - 1) * 12 * (size_t)a.nM + i;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cp[(size_t)(3 * q) * a.nM] = cx[q]; cp[(size_t)(3 * q + 1) * a.nM] = cy[q]; cp[(size_t)(3 * q + 2) * a.nM] = cz[q];
+      }
+    }
   }
   T* A = (T*)a.A + ((int64_t)n * a.nM + i) * 9;
   T* Bo = (T*)a.B + ((int64_t)n * a.nM + i) * 3;
 #pragma unroll
   for (int q = 0; q < 3; ++q) { A[q] = cx[q]; A[3 + q] = cy[q]; A[6 + q] = cz[q]; }
   Bo[0] = cx[3]; Bo[1] = cy[3]; Bo[2] = cz[3];
+}
+
+// Adjoint of beff2ab: the four columns of [A|B] are four magnetisation vectors driven by the same field, so a
+// step is apply_bwd (time-reversed state + adjoint + field gradient F) per column with the relaxation handled
+// here: only the B column carries the recovery term.  States come from un-relaxing the later state, re-
+// synchronised with the forward checkpoints every K steps; with K == 1 the state before the rotation is instead
+// recomputed from the previous checkpoint, so nothing is ever divided by E1/E2 (valid down to E = 0).
+template <typename T, int POL>
+__global__ void __launch_bounds__(128) beff2ab_bwd_kernel(const mrphy_beff2ab_args a) {
+  const int n = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= a.nM) return;
+  const int nT = a.nT, K = a.K;
+  const size_t nM = (size_t)a.nM;
+  const double gam = ld_param(a.gamma, n, i), dt = ld_param(a.dt, n, 0);
+  const T g = (T)(6.283185307179586476925286766559 * gam * dt);
+  const T E1 = (T)ld_param(a.E1, n, i), E2 = (T)ld_param(a.E2, n, i);
+  const T e1 = E1 - (T)1, e2 = E2 - (T)1;
+  const T iE1 = K > 1 ? (T)1 / E1 : (T)0, iE2 = K > 1 ? (T)1 / E2 : (T)0;
+  const T* Ap = (const T*)a.A + ((size_t)n * nM + i) * 9;
+  const T* Bp = (const T*)a.B + ((size_t)n * nM + i) * 3;
+  const T* gAp = (const T*)a.gA + ((size_t)n * nM + i) * 9;
+  const T* gBp = (const T*)a.gB + ((size_t)n * nM + i) * 3;
+  T cx[4], cy[4], cz[4], hx[4], hy[4], hz[4];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    cx[q] = Ap[q]; cy[q] = Ap[3 + q]; cz[q] = Ap[6 + q];
+    hx[q] = gAp[q]; hy[q] = gAp[3 + q]; hz[q] = gAp[6 + q];
+  }
+  cx[3] = Bp[0]; cy[3] = Bp[1]; cz[3] = Bp[2];
+  hx[3] = gBp[0]; hy[3] = gBp[1]; hz[3] = gBp[2];
+  const T* Bf = (const T*)a.Beff + (int64_t)n * a.B_sn + (int64_t)i * a.B_sm;
+  T* G = (T*)a.gBeff + ((size_t)n * nM + i) * (size_t)nT * 3;
+  const T* ck = (const T*)a.ckpt + (size_t)n * ((nT - 1) / K) * 12 * nM + i;
+  SpinConst<T, 1> kd;   // apply_bwd<RELAX=false> never reads it
+  kd.e1 = kd.e2 = (T)0; kd.iE1 = kd.iE2 = (T)1;
+  T sE1 = 0, sE2 = 0, sg = 0;
+  for (int t = nT - 1; t >= 0; --t) {
+    const T Bx = Bf[3 * t], By = Bf[3 * t + 1], Bz = Bf[3 * t + 2];
+    const T bx = g * Bx, by = g * By, bz = g * Bz;
+    const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+    T Fx = 0, Fy = 0, Fz = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      T tx, ty, tz;   // the column after the rotation, before the relaxation, of step t
+      if (K == 1) {
+        if (t > 0) {
+          const T* cp = ck + (size_t)(t - 1) * 12 * nM;
+          tx = cp[(size_t)(3 * q) * nM]; ty = cp[(size_t)(3 * q + 1) * nM]; tz = cp[(size_t)(3 * q + 2) * nM];
+        } else {
+          tx = q == 0; ty = q == 1; tz = q == 2;
+        }
+        apply_fwd<T, false>(r, bx, by, bz, (T)0, (T)0, tx, ty, tz);
+      } else {
+        tx = cx[q] * iE2; ty = cy[q] * iE2; tz = (q == 3 ? cz[q] + e1 : cz[q]) * iE1;
+      }
+      sE2 = fma_(hx[q], tx, fma_(hy[q], ty, sE2));
+      sE1 = fma_(hz[q], q == 3 ? tz - (T)1 : tz, sE1);
+      T gx = fma_(e2, hx[q], hx[q]), gy = fma_(e2, hy[q], hy[q]), gz = fma_(e1, hz[q], hz[q]);
+      T fx, fy, fz;
+      apply_bwd<T, false, 1>(kd, r, bx, by, bz, tx, ty, tz, gx, gy, gz, fx, fy, fz);
+      cx[q] = tx; cy[q] = ty; cz[q] = tz;
+      hx[q] = gx; hy[q] = gy; hz[q] = gz;
+      Fx += fx; Fy += fy; Fz += fz;
+    }
+    G[3 * t] = -g * Fx; G[3 * t + 1] = -g * Fy; G[3 * t + 2] = -g * Fz;   // dL/dBeff = -g F, dL/dg = -F.Beff
+    sg -= fma_(Fx, Bx, fma_(Fy, By, Fz * Bz));
+    if (K > 1 && t % K == 0 && t > 0) {
+      const T* cp = ck + (size_t)(t / K - 1) * 12 * nM;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cx[q] = cp[(size_t)(3 * q) * nM]; cy[q] = cp[(size_t)(3 * q + 1) * nM]; cz[q] = cp[(size_t)(3 * q + 2) * nM];
+      }
+    }
+  }
+  T* gp = (T*)a.gP + ((size_t)n * nM + i) * 3;
+  gp[0] = sE1; gp[1] = sE2; gp[2] = sg;
+}
+
+// ---- beff2u-phi (beffective.py:14-37) --------------------------------------------------------------
+// U = b / max(|b|, 1e-12) (F.normalize), Phi = -|b| g; the adjoint is the autograd of exactly that.
+template <typename T>
+__global__ void __launch_bounds__(256) beff2uphi_kernel(const mrphy_beff2uphi_args a) {
+  const int n = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.nM) return;
+  const T* bp = (const T*)a.beff + (int64_t)n * a.b_sn + (int64_t)i * a.b_sm;
+  const T x = bp[0], y = bp[1], z = bp[2];
+  const T g = (T)ld_param(a.g, n, i);
+  const T nrm = sqrt(x * x + y * y + z * z);
+  const T inv = (T)1 / max(nrm, (T)1e-12);
+  const size_t o = (size_t)n * a.nM + i;
+  if (!a.adjoint) {
+    T* u = (T*)a.U + o * 3;
+    u[0] = x * inv; u[1] = y * inv; u[2] = z * inv;
+    ((T*)a.Phi)[o] = -nrm * g;
+    return;
+  }
+  T gx = 0, gy = 0, gz = 0, gn = 0;
+  if (a.gU) {
+    const T* gu = (const T*)a.gU + o * 3;
+    gx = gu[0] * inv; gy = gu[1] * inv; gz = gu[2] * inv;
+    if (nrm > (T)1e-12) gn = -(gx * x + gy * y + gz * z) * inv;   // d(1/|b|): -(gU.b)/|b|^2
+  }
+  if (a.gPhi) {
+    const T gp = ((const T*)a.gPhi)[o];
+    gn -= gp * g;
+    if (a.gg) ((T*)a.gg)[o] = -gp * nrm;
+  } else if (a.gg) {
+    ((T*)a.gg)[o] = 0;
+  }
+  const T w = nrm > (T)0 ? gn / nrm : (T)0;   // d|b|/db = b/|b|, 0 at the origin (torch.norm)
+  T* out = (T*)a.gbeff + o * 3;
+  out[0] = fma_(w, x, gx); out[1] = fma_(w, y, gy); out[2] = fma_(w, z, gz);
 }
 
 // ---- freeprec (sims.py:325-421) --------------------------------------------------------------------
@@ -178,18 +299,62 @@ extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream)
   return MRPHY_OK;
 }
 
-extern "C" int mrphy_beff2ab(const mrphy_beff2ab_args* a, void* cuda_stream) {
-  BEGIN_CALL();
+static int check_beff2ab(const mrphy_beff2ab_args* a, bool bwd) {
   if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1 || a->nT < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
   if (!a->Beff || !a->A || !a->B || !a->E1.ptr || !a->E2.ptr || !a->gamma.ptr || !a->dt.ptr) return fail(MRPHY_ERR_ARG, "Beff, A, B, E1, E2, gamma, dt are required%s");
-  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if ((a->ckpt || bwd) && a->K < 1) return fail(MRPHY_ERR_ARG, "K must be >= 1%s");
+  if (bwd && (!a->ckpt || !a->gA || !a->gB || !a->gBeff || !a->gP)) return fail(MRPHY_ERR_ARG, "ckpt, gA, gB, gBeff, gP are required%s");
+  return MRPHY_OK;
+}
+
+extern "C" size_t mrphy_beff2ab_ckpt_elems(const mrphy_beff2ab_args* a) {
+  if (!a || a->K < 1 || a->nT < 1) return 0;
+  const size_t n = (size_t)a->N * (size_t)((a->nT - 1) / a->K) * 12 * (size_t)a->nM;
+  return n ? n : 1;
+}
+
+template <bool BWD>
+static int launch_beff2ab(const mrphy_beff2ab_args* a, cudaStream_t st) {
   dim3 grid((a->nM + 127) / 128, a->N);
   const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0;
   timing_begin(st);
-  if (a->dtype == MRPHY_F64) beff2ab_kernel<double, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
-  else if (precise) beff2ab_kernel<float, TRIG_PRECISE><<<grid, 128, 0, st>>>(*a);
-  else beff2ab_kernel<float, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+  if (BWD) {
+    if (a->dtype == MRPHY_F64) beff2ab_bwd_kernel<double, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+    else if (precise) beff2ab_bwd_kernel<float, TRIG_PRECISE><<<grid, 128, 0, st>>>(*a);
+    else beff2ab_bwd_kernel<float, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+  } else {
+    if (a->dtype == MRPHY_F64) beff2ab_kernel<double, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+    else if (precise) beff2ab_kernel<float, TRIG_PRECISE><<<grid, 128, 0, st>>>(*a);
+    else beff2ab_kernel<float, TRIG_FAST><<<grid, 128, 0, st>>>(*a);
+  }
   timing_end(st);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+extern "C" int mrphy_beff2ab(const mrphy_beff2ab_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  const int rc = check_beff2ab(a, false);
+  return rc ? rc : launch_beff2ab<false>(a, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int mrphy_beff2ab_bwd(const mrphy_beff2ab_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  const int rc = check_beff2ab(a, true);
+  return rc ? rc : launch_beff2ab<true>(a, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int mrphy_beff2uphi(const mrphy_beff2uphi_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (!a->beff || !a->g.ptr) return fail(MRPHY_ERR_ARG, "beff and g are required%s");
+  if (!a->adjoint && (!a->U || !a->Phi)) return fail(MRPHY_ERR_ARG, "U and Phi are required%s");
+  if (a->adjoint && !a->gbeff) return fail(MRPHY_ERR_ARG, "gbeff is required%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  dim3 grid((a->nM + 255) / 256, a->N);
+  if (a->dtype == MRPHY_F64) beff2uphi_kernel<double><<<grid, 256, 0, st>>>(*a);
+  else beff2uphi_kernel<float><<<grid, 256, 0, st>>>(*a);
   ++launch_count();
   CK(cudaGetLastError());
   return MRPHY_OK;

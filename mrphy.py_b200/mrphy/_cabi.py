@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('MRPHY_B200_LIB') or os.path.join(os.path.dirname(_HER
 
 MRPHY_F32, MRPHY_F64 = 0, 1
 FLAG_TRIG_PRECISE, FLAG_NEED_GMI, FLAG_RF_COIL_DIM, FLAG_NEED_GBEFF = 1, 2, 4, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 
@@ -64,10 +64,19 @@ class RfGr2BeffArgs(ctypes.Structure):
 
 class Beff2abArgs(ctypes.Structure):
     _fields_ = [
-        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('_pad', c_i32),
+        ('dtype', c_i32), ('flags', c_i32), ('N', c_i32), ('nM', c_i32), ('nT', c_i32), ('K', c_i32),
         ('Beff', c_vp), ('B_sn', c_i64), ('B_sm', c_i64),
         ('E1', Param), ('E2', Param), ('gamma', Param), ('dt', Param),
-        ('A', c_vp), ('B', c_vp),
+        ('A', c_vp), ('B', c_vp), ('ckpt', c_vp), ('gA', c_vp), ('gB', c_vp), ('gBeff', c_vp), ('gP', c_vp),
+    ]
+
+
+class Beff2uphiArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('adjoint', c_i32), ('N', c_i32), ('nM', c_i32),
+        ('beff', c_vp), ('b_sn', c_i64), ('b_sm', c_i64),
+        ('g', Param),
+        ('U', c_vp), ('Phi', c_vp), ('gU', c_vp), ('gPhi', c_vp), ('gbeff', c_vp), ('gg', c_vp),
     ]
 
 
@@ -96,7 +105,10 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_blochsim_beff_fwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
     'mrphy_blochsim_beff_bwd': (ctypes.c_int, [ctypes.POINTER(BeffArgs), c_vp]),
     'mrphy_rfgr2beff': (ctypes.c_int, [ctypes.POINTER(RfGr2BeffArgs), c_vp]),
+    'mrphy_beff2ab_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(Beff2abArgs)]),
     'mrphy_beff2ab': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),
+    'mrphy_beff2ab_bwd': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),
+    'mrphy_beff2uphi': (ctypes.c_int, [ctypes.POINTER(Beff2uphiArgs), c_vp]),
     'mrphy_freeprec': (ctypes.c_int, [ctypes.POINTER(FreePrecArgs), c_vp]),
 }
 

@@ -254,7 +254,7 @@ def beff_ckpt_interval(K: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
-# stand-alone operators: rfgr2beff, beff2ab (forward), freeprec
+# stand-alone operators: rfgr2beff, beff2ab (+ adjoint), beff2uphi (+ adjoint), freeprec
 def _impl_rfgr2beff(rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b1: Optional[Tensor],
                    gamma: Tensor) -> Tensor:
     """rf (N,2,nT[,nC]), gr (N,3,nT), loc (N,nM,3), df (N|1,nM|1), b1 (N,nM,2,nC) -> Beff (N,nM,nT,3)."""
@@ -282,27 +282,104 @@ def _fake_rfgr2beff(rf, gr, loc, df, b1, gamma):
     return loc.new_empty((loc.shape[0], loc.shape[1], rf.shape[2], 3))
 
 
-def _impl_beff2ab(beff: Tensor, E1: Tensor, E2: Tensor, gamma: Tensor, dt: Tensor, flags: int) -> Tuple[Tensor, Tensor]:
-    """beff (N,nM,nT,3) -> A (N,nM,3,3), B (N,nM,3); E1/E2/gamma broadcastable to (N,nM), dt () or (N|1,)."""
-    L = _cabi.lib()
+def _beff2ab_args(beff, E1, E2, gamma, dt, K, flags):
     a = _cabi.Beff2abArgs()
     N, nM, nT = beff.shape[0], beff.shape[1], beff.shape[2]
     a.dtype = _cabi.MRPHY_F64 if beff.dtype == torch.float64 else _cabi.MRPHY_F32
-    a.flags, a.N, a.nM, a.nT = flags, N, nM, nT
+    a.flags, a.N, a.nM, a.nT, a.K = flags, N, nM, nT, K
     a.Beff, a.B_sn, a.B_sm = beff.data_ptr(), _bstride(beff, 0), _bstride(beff, 1)
     a.E1, a.E2, a.gamma = _param(E1, N, nM), _param(E2, N, nM), _param(gamma, N, nM)
     a.dt = _param(dt, N, nM, per_batch_only=True)
-    A = torch.empty((N, nM, 3, 3), dtype=beff.dtype, device=beff.device)
-    B = torch.empty((N, nM, 3), dtype=beff.dtype, device=beff.device)
+    return a
+
+
+def _impl_beff2ab(beff: Tensor, E1: Tensor, E2: Tensor, gamma: Tensor, dt: Tensor, K: int,
+                  flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """beff (N,nM,nT,3) -> A (N,nM,3,3), B (N,nM,3), ckpt; E1/E2/gamma broadcastable to (N,nM), dt () or (N|1,).
+    K > 0 also stores [A|B] every K steps for the adjoint; K = 0: forward only (ckpt is empty)."""
+    L = _cabi.lib()
+    a = _beff2ab_args(beff, E1, E2, gamma, dt, K, flags)
+    kw = {'dtype': beff.dtype, 'device': beff.device}
+    A, B = torch.empty((a.N, a.nM, 3, 3), **kw), torch.empty((a.N, a.nM, 3), **kw)
+    ckpt = torch.empty(L.mrphy_beff2ab_ckpt_elems(a) if K > 0 else 0, **kw)
     a.A, a.B = A.data_ptr(), B.data_ptr()
+    if K > 0:
+        a.ckpt = ckpt.data_ptr()
     with torch.cuda.device(beff.device):
         _cabi.check(L.mrphy_beff2ab(a, _stream()), 'beff2ab')
     _cabi.count_launches()
-    return A, B
+    return A, B, ckpt
 
 
-def _fake_beff2ab(beff, E1, E2, gamma, dt, flags):
-    return beff.new_empty(beff.shape[:2] + (3, 3)), beff.new_empty(beff.shape[:2] + (3,))
+def _fake_beff2ab(beff, E1, E2, gamma, dt, K, flags):
+    N, nM, nT = beff.shape[:3]
+    return (beff.new_empty((N, nM, 3, 3)), beff.new_empty((N, nM, 3)),
+            beff.new_empty((max(N * ((nT - 1) // K) * 12 * nM, 1) if K > 0 else 0,)))
+
+
+def _impl_beff2ab_bwd(gA: Tensor, gB: Tensor, A: Tensor, B: Tensor, ckpt: Tensor, beff: Tensor, E1: Tensor, E2: Tensor,
+                      gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
+    """-> gbeff (N,nM,nT,3), gP (N,nM,3) = per-spin [dL/dE1, dL/dE2, dL/d(2*pi*gamma*dt)]."""
+    L = _cabi.lib()
+    a = _beff2ab_args(beff, E1, E2, gamma, dt, K, flags)
+    kw = {'dtype': beff.dtype, 'device': beff.device}
+    gbeff, gP = torch.empty((a.N, a.nM, a.nT, 3), **kw), torch.empty((a.N, a.nM, 3), **kw)
+    a.A, a.B, a.ckpt = A.data_ptr(), B.data_ptr(), ckpt.data_ptr()
+    a.gA, a.gB, a.gBeff, a.gP = gA.data_ptr(), gB.data_ptr(), gbeff.data_ptr(), gP.data_ptr()
+    with torch.cuda.device(beff.device):
+        _cabi.check(L.mrphy_beff2ab_bwd(a, _stream()), 'beff2ab_bwd')
+    _cabi.count_launches()
+    return gbeff, gP
+
+
+def _fake_beff2ab_bwd(gA, gB, A, B, ckpt, beff, E1, E2, gamma, dt, K, flags):
+    return beff.new_empty(beff.shape), beff.new_empty(beff.shape[:2] + (3,))
+
+
+def _impl_beff2uphi(beff: Tensor, g: Tensor) -> Tuple[Tensor, Tensor]:
+    """beff (N,nM,3), g broadcastable to (N,nM) -> U (N,nM,3), Phi (N,nM)."""
+    L = _cabi.lib()
+    a = _cabi.Beff2uphiArgs()
+    N, nM = beff.shape[0], beff.shape[1]
+    a.dtype = _cabi.MRPHY_F64 if beff.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.N, a.nM = N, nM
+    a.beff, a.b_sn, a.b_sm = beff.data_ptr(), _bstride(beff, 0), _bstride(beff, 1)
+    a.g = _param(g, N, nM)
+    U, Phi = torch.empty((N, nM, 3), dtype=beff.dtype, device=beff.device), torch.empty((N, nM), dtype=beff.dtype, device=beff.device)
+    a.U, a.Phi = U.data_ptr(), Phi.data_ptr()
+    with torch.cuda.device(beff.device):
+        _cabi.check(L.mrphy_beff2uphi(a, _stream()), 'beff2uphi')
+    _cabi.count_launches()
+    return U, Phi
+
+
+def _fake_beff2uphi(beff, g):
+    return beff.new_empty(beff.shape), beff.new_empty(beff.shape[:2])
+
+
+def _impl_beff2uphi_bwd(gU: Optional[Tensor], gPhi: Optional[Tensor], beff: Tensor, g: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> gbeff (N,nM,3), gg (N,nM) = per-spin dL/dg."""
+    L = _cabi.lib()
+    a = _cabi.Beff2uphiArgs()
+    N, nM = beff.shape[0], beff.shape[1]
+    a.dtype = _cabi.MRPHY_F64 if beff.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.adjoint, a.N, a.nM = 1, N, nM
+    a.beff, a.b_sn, a.b_sm = beff.data_ptr(), _bstride(beff, 0), _bstride(beff, 1)
+    a.g = _param(g, N, nM)
+    gbeff, gg = torch.empty((N, nM, 3), dtype=beff.dtype, device=beff.device), torch.empty((N, nM), dtype=beff.dtype, device=beff.device)
+    if gU is not None:
+        a.gU = gU.data_ptr()
+    if gPhi is not None:
+        a.gPhi = gPhi.data_ptr()
+    a.gbeff, a.gg = gbeff.data_ptr(), gg.data_ptr()
+    with torch.cuda.device(beff.device):
+        _cabi.check(L.mrphy_beff2uphi(a, _stream()), 'beff2uphi_bwd')
+    _cabi.count_launches()
+    return gbeff, gg
+
+
+def _fake_beff2uphi_bwd(gU, gPhi, beff, g):
+    return beff.new_empty(beff.shape), beff.new_empty(beff.shape[:2])
 
 
 def _impl_freeprec(Mi: Tensor, dur: Tensor, T1: Optional[Tensor], T2: Optional[Tensor], df: Optional[Tensor],
@@ -332,7 +409,7 @@ def _fake_freeprec(Mi, dur, T1, T2, df, adjoint):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int flags) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -348,6 +425,9 @@ blochsim_beff_fwd = _register('blochsim_beff_fwd', _impl_blochsim_beff_fwd, _fak
 blochsim_beff_bwd = _register('blochsim_beff_bwd', _impl_blochsim_beff_bwd, _fake_blochsim_beff_bwd)
 rfgr2beff_cuda = _register('rfgr2beff', _impl_rfgr2beff, _fake_rfgr2beff)
 beff2ab_cuda = _register('beff2ab', _impl_beff2ab, _fake_beff2ab)
+beff2ab_bwd_cuda = _register('beff2ab_bwd', _impl_beff2ab_bwd, _fake_beff2ab_bwd)
+beff2uphi_cuda = _register('beff2uphi', _impl_beff2uphi, _fake_beff2uphi)
+beff2uphi_bwd_cuda = _register('beff2uphi_bwd', _impl_beff2uphi_bwd, _fake_beff2uphi_bwd)
 freeprec_cuda = _register('freeprec', _impl_freeprec, _fake_freeprec)
 torch.library.register_autograd('mrphy_b200::blochsim_fused_fwd', _fused_backward, setup_context=_fused_setup, lib=_LIB)
 

@@ -1,31 +1,132 @@
-r"""B-effective related functions (``/root/reference/mrphy/beffective.py`` surface).
+r"""B-effective related functions (``/root/reference/mrphy/beffective.py`` surface), CUDA only.
 
-``rfgr2beff`` materialises the dense field `(N,*Nd,nT,xyz)`; the fused simulation path
-(``mobjs.SpinArray.applypulse`` -> ``_ops.fused_applypulse``) never calls it -- the field is formed in
-registers inside the CUDA kernel.  It is kept for the explicit-``Beff`` API (``Pulse.beff``,
-``pulse2beff``, ``sims.blochsim(Mi, Beff)``) and stays differentiable w.r.t. every input by plain
-autograd, like upstream.
+Every function here runs a hand-written kernel of ``libmrphy_b200.so`` and carries its own explicit adjoint
+(``torch.autograd.Function``); CPU tensors raise -- there is no second implementation.  ``rfgr2beff``
+materialises the dense field `(N,*Nd,nT,xyz)`; the fused simulation path (``mobjs.SpinArray.applypulse`` ->
+``_ops.fused_applypulse``) never calls it -- there the field is formed in registers inside the kernel.  It serves
+the explicit-``Beff`` API (``Pulse.beff``, ``pulse2beff``, ``sims.blochsim(Mi, Beff)``).
 """
+import math
 from typing import Optional, Tuple
 
 import torch
-import torch.nn.functional as F
 from torch import tensor, Tensor
 
 from mrphy import γH, dt0, π
-from mrphy import utils, _ops
+from mrphy import _ops
 
 __all__ = ['beff2ab', 'beff2uφ', 'rfgr2beff']
+
+
+def _reduce_to(g: Tensor, shape, tail: int = 0) -> Tensor:
+    """Sum a full `(N,*Nd,<tail dims>)` gradient down to a broadcastable input of `shape`."""
+    lead = g.ndim - tail
+    padded = tuple(shape[:len(shape) - tail]) + (1,) * (lead - (len(shape) - tail)) + tuple(shape[len(shape) - tail:])
+    return g.sum_to_size(padded).reshape(shape)
+
+
+def _working(x: Tensor, like: Tensor) -> Tensor:
+    """The arithmetic type of a kernel is that of its main operand; a mismatching tensor operand is cast."""
+    return x if x.dtype == like.dtype else x.to(like.dtype)
+
+
+class _Beff2UPhi(torch.autograd.Function):
+    r"""``U = beff/max(|beff|, 1e-12)``, ``Φ = -|beff|·γ2πdt`` in one pass (28 B/spin fp32) with the adjoint of
+    exactly those two expressions; upstream composes ``F.normalize`` and ``torch.norm`` (beffective.py:35-36)."""
+
+    @staticmethod
+    def forward(ctx, beff, g):
+        N, Nd = beff.shape[0], tuple(beff.shape[1:-1])
+        b = _ops._inner_contig(beff.reshape(N, -1, 3), 1)
+        gf = _ops.flat_param(g, N, Nd, beff.device)
+        U, Phi = _ops.beff2uphi_cuda(b, gf)
+        ctx.save_for_backward(b, gf)
+        ctx.shapes = (beff.shape, g.shape)
+        return U.reshape(beff.shape), Phi.reshape(beff.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, gU, gPhi):
+        b, gf = ctx.saved_tensors
+        N, nM = b.shape[0], b.shape[1]
+        gU = None if gU is None else gU.reshape(N, nM, 3).contiguous()
+        gPhi = None if gPhi is None else gPhi.reshape(N, nM).contiguous()
+        gb, gg = _ops.beff2uphi_bwd_cuda(gU, gPhi, b, gf)
+        bshape, gshape = ctx.shapes
+        out_g = _reduce_to(gg.reshape(bshape[:-1]), gshape) if ctx.needs_input_grad[1] else None
+        return gb.reshape(bshape), out_g
 
 
 def beff2uϕ(beff: Tensor, γ2πdt: Tensor, *, dim=-1) -> Tuple[Tensor, Tensor]:
     r"""Rotation axes/angles from B-effective (beffective.py:18-37).
 
     - ``beff``: `(N, *Nd, xyz)` Gauss;  ``γ2πdt``: `()` ⊻ `(N ⊻ 1, *Nd ⊻ 1,)` rad/Gauss
+    - ``dim``: position of the `xyz` axis when it is not the last one
     - returns ``U`` `(N, *Nd, xyz)` unit axes (0 where the field vanishes), ``Φ`` `(N, *Nd)` angles,
       negative because the Bloch equation is M×B.
     """
-    return F.normalize(beff, dim=dim), -torch.norm(beff, dim=dim) * γ2πdt
+    _ops._require_cuda(beff)
+    last = beff.ndim - 1
+    dim = dim % beff.ndim
+    b = beff if dim == last else beff.movedim(dim, last)
+    if b.ndim == 1:
+        b = b[None]
+    U, Φ = _Beff2UPhi.apply(b, _working(γ2πdt.to(beff.device), beff))
+    if beff.ndim == 1:
+        U, Φ = U[0], Φ[0]
+    return (U if dim == last else U.movedim(last, dim)), Φ
+
+
+class _Beff2AB(torch.autograd.Function):
+    r"""[A|B] propagated in registers by one kernel (four columns through the same rotation + relaxation step as
+    the simulation) and its adjoint kernel: time-reversed columns, resynchronised every K steps with checkpoints
+    of [A|B], gradients w.r.t. ``beff`` and -- reduced here onto their broadcast shapes -- E1, E2, γ, dt.
+    Upstream differentiates its Python time loop by autograd (beffective.py:88-103)."""
+
+    @staticmethod
+    def forward(ctx, beff, E1, E2, γ, dt):
+        N, Nd, dev = beff.shape[0], tuple(beff.shape[1:-2]), beff.device
+        b = _ops._inner_contig(beff.reshape(N, -1, beff.shape[-2], 3), 2)
+        E1f, E2f, γf = (_ops.flat_param(x, N, Nd, dev) for x in (E1, E2, γ))
+        dtf = dt.to(dev).reshape(-1)
+        flags = _ops.default_flags()
+        K = 0
+        if any(ctx.needs_input_grad):
+            # un-relaxing K steps amplifies rounding by E^-K: keep that below e^0.4 (one host read of min E);
+            # K = 1 is the division-free mode of the kernel, also right for E = 0
+            Emin = float(torch.minimum(E1f.min(), E2f.min()))
+            K = 1 if not (Emin > 0) else (_ops.K_MAX if Emin >= 1 else
+                                          int(max(1, min(_ops.K_MAX, _ops._AMPLIFY_BUDGET / -math.log(Emin)))))
+        A, B, ckpt = _ops.beff2ab_cuda(b, E1f, E2f, γf, dtf, K, flags)
+        ctx.save_for_backward(A, B, ckpt, b, E1f, E2f, γf, dtf)
+        ctx.K, ctx.flags = K, flags
+        ctx.shapes = (beff.shape, E1.shape, E2.shape, γ.shape, dt.shape)
+        lead = beff.shape[:-2]
+        return A.reshape(lead + (3, 3)), B.reshape(lead + (3,))
+
+    @staticmethod
+    def backward(ctx, gA, gB):
+        A, B, ckpt, b, E1f, E2f, γf, dtf = ctx.saved_tensors
+        N, nM = b.shape[0], b.shape[1]
+        zero = lambda ref: torch.zeros_like(ref)
+        gA = zero(A) if gA is None else gA.reshape(N, nM, 3, 3).contiguous()
+        gB = zero(B) if gB is None else gB.reshape(N, nM, 3).contiguous()
+        gb, gP = _ops.beff2ab_bwd_cuda(gA, gB, A, B, ckpt, b, E1f, E2f, γf, dtf, ctx.K, ctx.flags)
+        bshape, s1, s2, sγ, sdt = ctx.shapes
+        lead, need = bshape[:-2], ctx.needs_input_grad
+        full = lambda x: x.reshape(lead)
+        out = [gb.reshape(bshape) if need[0] else None, None, None, None, None]
+        if need[1]:
+            out[1] = _reduce_to(full(gP[..., 0]), s1)
+        if need[2]:
+            out[2] = _reduce_to(full(gP[..., 1]), s2)
+        if need[3] or need[4]:       # g = 2π·γ·dt per spin
+            gg = gP[..., 2]
+            dtb = dtf.reshape(-1, 1).to(gg.dtype)
+            if need[3]:
+                out[3] = _reduce_to(full(gg * (2 * π) * dtb), sγ)
+            if need[4]:
+                out[4] = _reduce_to(full(gg * (2 * π) * γf.to(gg.dtype)), sdt)
+        return tuple(out)
 
 
 def beff2ab(
@@ -39,35 +140,9 @@ def beff2ab(
       `(N ⊻ 1, *Nd ⊻ 1,)` (NB: factors, not times -- same as upstream despite its docstring)
     - returns ``A`` `(N,*Nd,xyz,3)`, ``B`` `(N,*Nd,xyz)` with ``M_end = A @ M_start + B``.
     """
-    dev, nd = beff.device, beff.ndim - 2
-    if beff.is_cuda and beff.dtype in _ops._F and not (torch.is_grad_enabled() and beff.requires_grad):
-        # forward-only CUDA kernel (one spin per thread, [A|B] in registers); gradients use the loop below
-        N, Nd = beff.shape[0], tuple(beff.shape[1:-2])
-        flat = lambda x: _ops.flat_param(x, N, Nd, dev)
-        b = _ops._inner_contig(beff.reshape(N, -1, beff.shape[-2], 3), 2)
-        A, B = _ops.beff2ab_cuda(b, flat(E1), flat(E2), flat(γ), dt.to(dev).reshape(-1), _ops.default_flags())
-        return A.reshape(beff.shape[:-2] + (3, 3)), B.reshape(beff.shape[:-2] + (3,))
-    E1, E2, γ, dt = (utils._tail(x.to(dev), nd) for x in (E1, E2, γ, dt))
-    g = 2 * π * γ * dt
-    NNd, nT = beff.shape[:-2], beff.shape[-2]
-    AB = torch.eye(3, 4, device=dev, dtype=beff.dtype).expand(NNd + (3, 4)).clone()   # [A | B]
-    scale = torch.stack((E2, E2, E1), dim=-1)[..., None].to(beff.dtype)               # (N,*Nd,3,1) rows
-    recover = (1 - E1).to(beff.dtype)
-    for t in range(nT):
-        u, ϕ = beff2uϕ(beff[..., t, :], g)
-        AB = utils.uϕrot(u, ϕ, AB) if torch.any(ϕ != 0) else AB
-        AB = AB * scale
-        AB = torch.cat((AB[..., :3], AB[..., 3:] + torch.stack(
-            (torch.zeros_like(recover), torch.zeros_like(recover), recover), dim=-1)[..., None].expand(NNd + (3, 1))),
-            dim=-1)
-    return AB[..., 0:3], AB[..., 3]
-
-
-def _reduce_to(g: Tensor, shape, tail: int = 0) -> Tensor:
-    """Sum a full `(N,*Nd,<tail dims>)` gradient down to a broadcastable input of `shape`."""
-    lead = g.ndim - tail
-    padded = tuple(shape[:len(shape) - tail]) + (1,) * (lead - (len(shape) - tail)) + tuple(shape[len(shape) - tail:])
-    return g.sum_to_size(padded).reshape(shape)
+    _ops._require_cuda(beff)
+    dev = beff.device
+    return _Beff2AB.apply(beff, E1.to(dev), E2.to(dev), γ.to(dev), dt.to(dev))
 
 
 class _RfGr2Beff(torch.autograd.Function):
@@ -148,28 +223,7 @@ def rfgr2beff(
     - returns ``beff``: `(N,*Nd,nT,xyz)` Gauss
     """
     assert (rf.device == gr.device == loc.device)
+    _ops._require_cuda(rf)
     dev = rf.device
-    N, Nd = loc.shape[0], tuple(loc.shape[1:-1])
-    nd = len(Nd)
-    same = all(x is None or (x.dtype == rf.dtype) for x in (gr, loc, Δf, b1Map))
-    if rf.is_cuda and rf.dtype in _ops._F and same and γ.dtype in _ops._F:
-        return _RfGr2Beff.apply(rf, gr, loc, Δf, None if b1Map is None else b1Map.to(dev), γ.to(dev))
-    Bz = torch.matmul(loc.reshape(N, -1, 3), gr).reshape((N,) + Nd + (-1,))        # loc·gr
-    if Δf is not None:
-        Bz = Bz + utils._tail(Δf, nd + 2) / utils._tail(γ.to(device=dev), nd + 2)   # off-resonance as a z-field
-    rfx = rf.reshape((N,) + nd * (1,) + tuple(rf.shape[1:]))                         # (N,1..,xy,nT,(nCoils))
-    if b1Map is None:
-        if rfx.ndim == Bz.ndim + 2:
-            rfx = rfx.sum(dim=-1)                                                     # coils add up
-        Bx, By = rfx[..., 0, :].expand_as(Bz), rfx[..., 1, :].expand_as(Bz)
-    else:
-        b1 = b1Map.to(dev)
-        if b1.ndim == nd + 2:
-            b1 = b1[..., None]
-        if rfx.ndim == b1.ndim:
-            rfx = rfx[..., None]
-        br, bi = b1[..., 0, None, :], b1[..., 1, None, :]                            # (N,*Nd,1,nCoils)
-        rx, ry = rfx[..., 0, :, :], rfx[..., 1, :, :]                                # (N,1..,nT,nCoils)
-        Bx = (br * rx - bi * ry).sum(dim=-1).expand_as(Bz)                           # Re(b1·rf)
-        By = (br * ry + bi * rx).sum(dim=-1).expand_as(Bz)                           # Im(b1·rf)
-    return torch.stack((Bx, By, Bz), dim=-1)
+    cast = lambda x: None if x is None else _working(x.to(dev), rf)
+    return _RfGr2Beff.apply(rf, cast(gr), cast(loc), cast(Δf), cast(b1Map), γ.to(dev))

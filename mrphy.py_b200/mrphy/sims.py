@@ -107,48 +107,27 @@ def blochsim(
 class FreePrec(Function):
     r"""Free precession with explicit Jacobian (differentiable w.r.t. ``Mi`` only; sims.py:318-421).
 
-    O(nM) elementwise work done once per call (not per time step): kept as device-agnostic torch ops.
+    One elementwise CUDA kernel (``mrphy_freeprec``); the backward applies the transposed map with the same kernel.
     """
 
     @staticmethod
     def forward(ctx, Mi: Tensor, dur: Tensor, T1: Optional[Tensor], T2: Optional[Tensor],
                 Δf: Optional[Tensor]) -> Tensor:
         assert (T1 is None) == (T2 is None)
-        ctx.cuda = Mi.is_cuda and Mi.dtype in _ops._F
-        if ctx.cuda:   # one elementwise CUDA kernel (mrphy_freeprec); backward applies the transposed map
-            N, Nd, dev = Mi.shape[0], tuple(Mi.shape[1:-1]), Mi.device
-            args = (dur.to(dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
-                    _flat_param(Δf, N, Nd, dev))
-            ctx.args, ctx.shape = args, Mi.shape
-            M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)
-            return _ops.freeprec_cuda(M, *args, False).reshape(Mi.shape)
-        c = s = E1 = E2 = None
-        x, y, z = Mi.unbind(-1)
-        if Δf is not None:                           # positive Δf rotates clockwise
-            ang = -(2 * π) * Δf * dur[..., 0]
-            c, s = torch.cos(ang), torch.sin(ang)
-            x, y = c * x - s * y, s * x + c * y
-        if T1 is not None:
-            a1, a2 = (-dur / T1)[..., 0], (-dur / T2)[..., 0]
-            E1, E2 = torch.exp(a1), torch.exp(a2)
-            x, y, z = E2 * x, E2 * y, E1 * z - torch.expm1(a1)
-        ctx.save_for_backward(c, s, E1, E2)
-        return torch.stack((x, y, z), dim=-1)
+        _ops._require_cuda(Mi)
+        N, Nd, dev = Mi.shape[0], tuple(Mi.shape[1:-1]), Mi.device
+        args = (dur.to(dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
+                _flat_param(Δf, N, Nd, dev))
+        ctx.args, ctx.shape = args, Mi.shape
+        M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)
+        return _ops.freeprec_cuda(M, *args, False).reshape(Mi.shape)
 
     @staticmethod
     def backward(ctx, grad_Mo: Tensor):
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
-        if ctx.cuda:
-            g = _ops._inner_contig(grad_Mo.reshape(ctx.shape[0], -1, 3), 1)
-            return _ops.freeprec_cuda(g, *ctx.args, True).reshape(ctx.shape), None, None, None, None
-        c, s, E1, E2 = ctx.saved_tensors
-        gx, gy, gz = grad_Mo.unbind(-1)
-        if E1 is not None:
-            gx, gy, gz = E2 * gx, E2 * gy, E1 * gz
-        if c is not None:
-            gx, gy = c * gx + s * gy, c * gy - s * gx
-        return torch.stack((gx, gy, gz), dim=-1), None, None, None, None
+        g = _ops._inner_contig(grad_Mo.reshape(ctx.shape[0], -1, 3), 1)
+        return _ops.freeprec_cuda(g, *ctx.args, True).reshape(ctx.shape), None, None, None, None
 
 
 def freeprec(

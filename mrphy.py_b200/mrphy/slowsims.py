@@ -1,16 +1,18 @@
 r"""Autograd-differentiated simulators (``blochsim_1step``, ``blochsim``, ``blochsim_ab``, ``freeprec``).
 
 The reference ships these (``/root/reference/mrphy/slowsims.py``) as its own cross-check of the hand-written
-Jacobians in ``sims``; they are kept here for API completeness only.  They are a few device-agnostic torch
-expressions inside a Python loop over time, differentiable w.r.t. every argument by plain autograd -- and are
-NOT the product path: ``sims.blochsim`` and ``SpinArray.applypulse`` never come through this module.
+Jacobians in ``sims``; they are kept here for API completeness only.  They are a few self-contained,
+device-agnostic torch expressions inside a Python loop over time, differentiable w.r.t. every argument by plain
+autograd -- and are NOT the product path: nothing in ``sims``, ``beffective`` or ``mobjs`` comes through this
+module, and this module calls none of the CUDA operators.
 """
 from typing import Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 from torch import Tensor
 
-from mrphy import beffective, dt0, utils, γH, π
+from mrphy import dt0, utils, γH, π
 
 __all__ = ['blochsim_1step', 'blochsim', 'blochsim_ab', 'freeprec']
 
@@ -20,7 +22,7 @@ _Opt = Optional[Tensor]
 def _advance(M: Tensor, b: Tensor, rad_per_gauss: Tensor, E1: Tensor, E2: Tensor) -> Tensor:
     """One dwell time: precess about ``b`` (skipped where the whole field is zero), then T2 decay / T1 recovery.
     ``E1`` is `(N,*Nd)`-broadcastable, ``E2`` already carries a trailing singleton for the xy pair."""
-    axis, angle = beffective.beff2uϕ(b, rad_per_gauss)
+    axis, angle = F.normalize(b, dim=-1), -torch.norm(b, dim=-1) * rad_per_gauss   # M×B: negative angle
     if torch.any(angle != 0):
         M = utils.uϕrot(axis, angle, M)
     xy = M[..., 0:2] * E2

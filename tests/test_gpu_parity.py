@@ -10,6 +10,7 @@ import os
 
 import numpy as np
 import pytest
+import torch_ref
 import torch
 from torch import tensor
 
@@ -344,7 +345,8 @@ def test_rfgr2beff_kernel_and_its_chain_rule(dev):
         res = {}
         for where in ('cpu', 'cuda'):
             t = {k: (None if v is None else v.detach().clone().to(where).requires_grad_(True)) for k, v in ins.items()}
-            beff = beffective.rfgr2beff(t['rf'], t['gr'], t['loc'], Δf=t['df'], b1Map=t['b1'], γ=t['gam'])
+            fn = beffective.rfgr2beff if where == 'cuda' else torch_ref.rfgr2beff
+            beff = fn(t['rf'], t['gr'], t['loc'], Δf=t['df'], b1Map=t['b1'], γ=t['gam'])
             (beff * w.to(where)).sum().backward()
             res[where] = [beff.detach().cpu()] + [None if v is None else v.grad.cpu() for v in t.values()]
         for a, b in zip(res['cpu'], res['cuda']):
@@ -373,12 +375,91 @@ def test_beff2ab_kernel(dev, golden):
                                   E2=torch.exp(-dtb / T(g2['in_T2'], dev, f64)).float(), γ=T(g2['in_gam'], dev, f32),
                                   dt=T(g2['in_dt'], dev, f32))
     assert A32.dtype == f32 and mx(A32, g2['A_f64']) < 5e-5 and mx(B32, g2['B_f64']) < 5e-5
-    # with grad enabled on beff the differentiable (autograd) implementation is used and agrees
-    bg = T(g2['beff_f64'], dev, f64).requires_grad_(True)
-    A2, B2 = beffective.beff2ab(bg, E1=torch.exp(-dtb / T(g2['in_T1'], dev, f64)),
-                                E2=torch.exp(-dtb / T(g2['in_T2'], dev, f64)), γ=T(g2['in_gam'], dev, f64),
-                                dt=T(g2['in_dt'], dev, f64))
-    assert A2.requires_grad and mx(A2, A) < 1e-12 and mx(B2, B) < 1e-12
+
+
+def test_gradients_through_beff2ab_equal_blochsim_goldens(dev, golden):
+    """tests/test_slowsims.py:86-96: d/d(rf, gr, M0) of sum(w * blochsim_ab(M0, *beff2ab(beff))) equals the gradients
+    through blochsim -- here against the reference's own gradients stored in the golden fixture."""
+    from mrphy import beffective, slowsims
+    g = golden('rand_mc')
+    t = {k[3:]: T(v, dev, f64) for k, v in g.items() if k.startswith('in_')}
+    rf, gr, M0 = (t[k].requires_grad_(True) for k in ('rf', 'gr', 'M0'))
+    beff = beffective.rfgr2beff(rf, gr, t['loc'], Δf=t['df'], b1Map=t['b1'], γ=t['gam'])
+    dtb = t['dt'].reshape(-1, 1)
+    A, B = beffective.beff2ab(beff, E1=torch.exp(-dtb / t['T1']), E2=torch.exp(-dtb / t['T2']), γ=t['gam'], dt=t['dt'])
+    Mo = slowsims.blochsim_ab(M0, A, B)
+    (Mo * t['w']).sum().backward()
+    assert mx(Mo, g['Mo_f64']) < 1e-12
+    assert rel(rf.grad, g['grf_f64']) < 1e-10 and rel(gr.grad, g['ggr_f64']) < 1e-10
+    assert rel(M0.grad, g['gM0_slow_f64']) < 1e-10
+
+
+@pytest.mark.parametrize('case', ['typical', 'strong', 'E0', 'norelax'])
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_beff2ab_adjoint_kernel(dev, case, dtype):
+    """dL/d(beff, E1, E2, γ, dt) of the CUDA beff2ab adjoint == autograd through the reference's time loop
+    (beffective.py:88-103, restated in tests/torch_ref.py).  'strong' relaxation shortens the checkpoint interval,
+    'E0' (the upstream default E1=E2=0) takes the division-free K=1 mode, 'norelax' is E=1."""
+    from mrphy import beffective
+    gen = torch.Generator().manual_seed(11)
+    U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
+    N, Nd, nT = 2, (3, 5), 150
+    beff = U(N, *Nd, nT, 3) * torch.tensor([0.1, 0.1, 2.0], dtype=f64)
+    γ = 4257.6 * (1 + 0.1 * U(N, *Nd))
+    dt = 4e-6 * (1 + 0.2 * U(N))
+    if case == 'typical':
+        E1, E2 = torch.exp(-4e-6 / (1.0 + 0.3 * U(N, *Nd))), torch.exp(-4e-6 / (0.07 + 0.02 * U(N, *Nd)))
+    elif case == 'strong':
+        E1, E2 = 0.9 + 0.05 * U(N, 1, 1), 0.8 + 0.1 * U(1, *Nd)
+    elif case == 'E0':
+        E1, E2 = torch.tensor(0., dtype=f64), torch.tensor(0.5, dtype=f64)
+    else:
+        E1, E2 = torch.tensor(1., dtype=f64), torch.ones(N, 1, 1, dtype=f64)
+    wA, wB = U(N, *Nd, 3, 3), U(N, *Nd, 3)
+    res = {}
+    for where in ('ref', 'cuda'):
+        d, ty = ('cpu', f64) if where == 'ref' else (dev, dtype)
+        # both sides start from the inputs as rounded to the working type (1 - E1 ~ 4e-6 has few bits left in fp32)
+        t = [x.detach().clone().to(dtype).to(device=d, dtype=ty).requires_grad_(True) for x in (beff, E1, E2, γ, dt)]
+        if where == 'ref':
+            A, B = torch_ref.beff2ab(*t)
+        else:
+            A, B = beffective.beff2ab(t[0], E1=t[1], E2=t[2], γ=t[3], dt=t[4])
+        ((A * wA.to(device=d, dtype=ty)).sum() + (B * wB.to(device=d, dtype=ty)).sum()).backward()
+        res[where] = [A.detach().cpu().double(), B.detach().cpu().double()] + [x.grad.cpu().double() for x in t]
+    tol = 1e-10 if dtype == f64 else 2e-3      # fp32: nT=150 steps of rounding in both state and adjoint
+    for a, b in zip(res['ref'], res['cuda']):   # (+1e-30: with E2 = 0.5, A ~ 0.5^150 underflows in fp32)
+        assert a.shape == b.shape and float((b - a).abs().max()) <= tol * float(a.abs().max()) + 1e-30
+
+
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_beff2uphi_kernel_and_adjoint(dev, dtype):
+    """CUDA beff2uϕ == F.normalize / -norm·γ2πdt (beffective.py:35-36), values and both gradients, including a
+    vanishing field, a broadcast γ2πdt and an xyz axis that is not the last one."""
+    from mrphy import beffective
+    gen = torch.Generator().manual_seed(12)
+    U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
+    for shape, gshape, dim in (((2, 4, 5, 3), (2, 1, 5), -1), ((3, 7, 3), (), -1), ((2, 3, 6), (2, 1), 1), ((1, 3), (1,), -1)):
+        b = U(*shape)
+        if dim == -1 and b.ndim > 2:
+            b[0, 0] = 0                      # zero field: U = 0, Φ = 0, finite gradients
+        g = U(*gshape) + 2
+        wU, wP = U(*shape), U(*(shape[:dim % len(shape)] + shape[dim % len(shape) + 1:]))
+        res = {}
+        for where in ('ref', 'cuda'):
+            d, ty = ('cpu', f64) if where == 'ref' else (dev, dtype)
+            bt, gt = (x.detach().clone().to(device=d, dtype=ty).requires_grad_(True) for x in (b, g))
+            fn = torch_ref.beff2uphi if where == 'ref' else beffective.beff2uϕ
+            Uo, P = fn(bt, gt, dim=dim)
+            ((Uo * wU.to(device=d, dtype=ty)).sum() + (P * wP.to(device=d, dtype=ty)).sum()).backward()
+            res[where] = [x.detach().cpu().double() for x in (Uo, P, bt.grad, gt.grad)]
+        for a, c in zip(res['ref'], res['cuda']):
+            assert a.shape == c.shape and mx(c, a) < (1e-12 if dtype == f64 else 2e-5) * max(1.0, float(a.abs().max()))
+    with torch.no_grad():                    # Φ only / U only consumers
+        bt = U(2, 5, 3).to(dev).requires_grad_(True)
+    Uo, P = beffective.beff2uϕ(bt, torch.tensor(2., dtype=f64, device=dev))
+    P.sum().backward()
+    assert mx(bt.grad, -2 * torch.nn.functional.normalize(bt.detach(), dim=-1)) < 1e-12
 
 
 def test_freeprec_kernel(dev, golden):

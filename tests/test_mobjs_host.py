@@ -134,42 +134,37 @@ def test_interpT_goldens(golden):
     assert q3f.gmax.shape == (1, 3)
 
 
-def test_rfgr2beff_and_beff2ab_match_reference(golden):
+def test_slowsims_match_reference_and_cuda_operators_refuse_cpu(golden):
+    """slowsims (plain torch, the reference's own cross-check) reproduces the reference on CPU; the operators of
+    beffective / sims are CUDA kernels only and say so instead of computing anything on the host."""
     g = golden('rand_mc')
     T = lambda k: tensor(g[k], dtype=f64)
-    beff = beffective.rfgr2beff(T('in_rf'), T('in_gr'), T('in_loc'), Δf=T('in_df'), b1Map=T('in_b1'), γ=T('in_gam'))
-    assert np.abs(beff.numpy() - g['beff_f64']).max() < 1e-11
-    dt = T('in_dt')
-    E1, E2 = torch.exp(-dt / T('in_T1')), torch.exp(-dt / T('in_T2'))
-    A, B = beffective.beff2ab(beff, E1=E1, E2=E2, γ=T('in_gam'), dt=dt)
-    assert np.abs(A.numpy() - g['A_f64']).max() < 1e-12 and np.abs(B.numpy() - g['B_f64']).max() < 1e-12
-    Mo = slowsims.blochsim_ab(T('in_M0'), A, B)
+    beff, dt = T('beff_f64'), T('in_dt')
+    Mo = slowsims.blochsim_ab(T('in_M0'), T('A_f64'), T('B_f64'))
     assert np.abs(Mo.numpy() - g['Mo_f64']).max() < 1e-12
     Ms = slowsims.blochsim(T('in_M0'), beff, T1=T('in_T1'), T2=T('in_T2'), γ=T('in_gam'), dt=dt)
     assert np.abs(Ms.numpy() - g['Mo_slow_f64']).max() < 1e-12
-    g2 = golden('rand_nob1')
-    beff2 = beffective.rfgr2beff(tensor(g2['in_rf'], dtype=f64), tensor(g2['in_gr'], dtype=f64),
-                                 tensor(g2['in_loc'], dtype=f64), γ=tensor(g2['in_gam'], dtype=f64))
-    assert np.abs(beff2.numpy() - g2['beff_f64']).max() < 1e-11
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        beffective.rfgr2beff(T('in_rf'), T('in_gr'), T('in_loc'), Δf=T('in_df'), b1Map=T('in_b1'), γ=T('in_gam'))
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        beffective.beff2ab(beff, E1=torch.exp(-dt / T('in_T1')), E2=torch.exp(-dt / T('in_T2')), γ=T('in_gam'), dt=dt)
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        beffective.beff2uϕ(beff[..., 0, :], tensor(1., dtype=f64))
 
 
 def test_freeprec_goldens(golden):
-    """tests/test_slowsims.py:100-122 and tests/test_sims.py:145-198 (sims.freeprec == slowsims.freeprec)."""
+    """tests/test_slowsims.py:100-122 (slowsims.freeprec on CPU; sims.freeprec is a CUDA kernel -> tests/test_gpu_parity)."""
     g = golden('freeprec')
     T = lambda k: tensor(g[k], dtype=f64)
-    for mod in (mrphy.sims, slowsims):
-        Mo = mod.freeprec(T('a_Mi'), T('a_dur'), T1=T('a_T1'), T2=T('a_T2'), Δf=T('a_df'))
-        assert np.abs(Mo.numpy() - np.array([[[0., -0.5, 0.5], [-0.5, 0, 0.5], [0., 0., 1.]]])).max() < 1e-12
-        Mi = T('b_Mi').requires_grad_(True)
-        Mo = mod.freeprec(Mi, T('b_dur'), T1=T('b_T1'), T2=T('b_T2'), Δf=T('b_df'))
-        (Mo * T('b_w')).sum().backward()
-        assert np.abs(Mo.detach().numpy() - g['b_Mo']).max() < 1e-13
-        assert np.abs(Mi.grad.numpy() - g['b_gMi']).max() < 1e-13
-    Th = -tensor(0.5, dtype=f64) / torch.log(tensor([[0.5]], dtype=f64))
-    cube, _ = _setup(Th, Th, γH.to(f64), torch.device('cpu'), f64)
-    cube.Δf = tensor([[[1 / 4 / 0.5], [-1 / 4 / 0.5], [1]]], dtype=f64).repeat(1, 3, 1, 3)
-    M = cube.freeprec(tensor(0.5, dtype=f64), doEmbed=True)
-    assert M[0:1, 1, :, 1, :].numpy() == pytest.approx(np.array([[[0., -0.5, 0.5], [-0.5, 0, 0.5], [0., 0., 1.]]]), abs=1e-9)
+    Mo = slowsims.freeprec(T('a_Mi'), T('a_dur'), T1=T('a_T1'), T2=T('a_T2'), Δf=T('a_df'))
+    assert np.abs(Mo.numpy() - np.array([[[0., -0.5, 0.5], [-0.5, 0, 0.5], [0., 0., 1.]]])).max() < 1e-12
+    Mi = T('b_Mi').requires_grad_(True)
+    Mo = slowsims.freeprec(Mi, T('b_dur'), T1=T('b_T1'), T2=T('b_T2'), Δf=T('b_df'))
+    (Mo * T('b_w')).sum().backward()
+    assert np.abs(Mo.detach().numpy() - g['b_Mo']).max() < 1e-13
+    assert np.abs(Mi.grad.numpy() - g['b_gMi']).max() < 1e-13
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        mrphy.sims.freeprec(T('a_Mi'), T('a_dur'), T1=T('a_T1'), T2=T('a_T2'), Δf=T('a_df'))
 
 
 class TestUtils:
