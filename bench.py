@@ -108,6 +108,13 @@ def synth(N, n_x, n, nT, dtype, seed=0, x_off=0, n_x_total=None):
     return {k: v.to(dtype) for k, v in dict(rf=rf, gr=gr, loc=loc, df=df, b1=b1, M0=M0).items()}
 
 
+def workload_desc(args, world):
+    N, n, nT = WORKLOADS[args.workload]
+    return (f'{args.workload.upper()}: SpinCube {n}^3 x N={N} ' +
+            ('per GPU' if args.scaling == 'weak' else f'split over {world} GPUs') +
+            f', nT={nT}, dt=4us, b1Map+df+relaxation, fwd+adjoint bwd')
+
+
 def run_ours(args):
     from mrphy import mobjs, parallel, _cabi
     import torch.distributed as dist
@@ -265,9 +272,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': f'{args.workload.upper()}: SpinCube {n}^3 x N={N} ' +
-                                   ('per GPU' if args.scaling == 'weak' else f'split over {world} GPUs') + f', nT={nT}, dt=4us, '
-                                   'b1Map+df+relaxation, fwd+adjoint bwd', 'spins_per_gpu': N * nM, 'nT': nT,
+            'config': {'workload': workload_desc(args, world), 'spins_per_gpu': N * nM, 'nT': nT,
                        'l2': 'flushed between steps (256 MB write)', 'sharding': f'spin slabs x{world}, waveform '
                        'replicated, 1 allreduce of grads' if world > 1 else 'single GPU'},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
@@ -360,7 +365,7 @@ def run_reference(args):
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
     cores = len(os.sched_getaffinity(0))
     budget = min(8.0, 150.0 / max(args.steps + args.warmup, 1))       # seconds per step
-    n_cpu = int(max(8, min(32, round((budget * 7e5 / nT) ** (1 / 3)))))
+    n_cpu = min(n, int(max(8, min(32, round((budget * 7e5 / nT) ** (1 / 3))))))
     for _ in range(args.warmup):
         cpu_port_step(n_cpu, nT, dtype, cores)
     tot, units = 0.0, 0
@@ -373,8 +378,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')),
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': tot / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': f'{args.workload.upper()} proxy: SpinCube {n_cpu}^3, nT={nT}, dt=4us (CPU sample of '
-                               f'the {n}^3 workload; spin·steps/s is size-insensitive at fixed nT, BASELINE.md sec. 2)'},
+        'config': {'workload': workload_desc(args, int(os.environ.get('WORLD_SIZE', '1'))), 'nT': nT,
+                   'sample': f'each step = one fwd+bwd over a {n_cpu}^3 sub-cube of the workload (same distributions, same '
+                             f'nT); spin·steps/s is size-insensitive at fixed nT (BASELINE.md sec. 2) and the full cube '
+                             'needs 52 B/spin-step in the reference'},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{n_cpu}^3 spins x {nT} steps per step, torch CPU {cores} threads'},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

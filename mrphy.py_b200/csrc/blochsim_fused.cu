@@ -297,30 +297,38 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
   }
 }
 
-// Column sums of one warp's transposition tile red[W][TR][32]: lane l owns row r = l % TR and adds up the TR source
-// lanes of its group, then the 32/TR groups meet through shuffles; lanes < TR publish out[w][r].
-// fp32, TR == 16: four 128-bit loads per row (chunk order rotated by the row: at most 2-way bank conflicts) instead
-// of sixteen scalar ones.  Otherwise scalar loads with a rotated start (conflict-free).
+// Column sums of one warp's transposition tile red[W][TR][32]: every lane owns one row r and adds up the TR source
+// lanes of its group, then the 32/TR groups meet through shuffles; one lane per row publishes out[w][r].
+// fp32, TR == 16: lane l takes row l/2 and the half (l&1) of its 32 source lanes with four 128-bit loads whose
+// chunk order is rotated by the row -- the 8 lanes of a quarter-warp then touch 8 distinct 16-byte bank groups
+// (conflict-free).  Otherwise scalar loads with a rotated start (conflict-free).
 template <typename T, int W, int TR>
 __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int lane, T (*out)[TR]) {
-  const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
+  if constexpr (sizeof(T) == 4 && TR == 16) {
+    const int r = lane >> 1, half = (lane & 1) << 4;
 #pragma unroll
-  for (int w = 0; w < W; ++w) {
-    T sum = (T)0;
-    if constexpr (sizeof(T) == 4 && TR == 16) {
-      const float4* row = reinterpret_cast<const float4*>(&tile[w][r][grp]);
+    for (int w = 0; w < W; ++w) {
+      const float4* row = reinterpret_cast<const float4*>(&tile[w][r][half]);
+      T sum = (T)0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 v = row[(q + r) & 3];
         sum += (v.x + v.y) + (v.z + v.w);
       }
-    } else {
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (!(lane & 1)) out[w][r] = sum;
+    }
+  } else {
+    const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      T sum = (T)0;
 #pragma unroll
       for (int q = 0; q < TR; ++q) sum += tile[w][r][grp + ((q + lane) & (TR - 1))];
-    }
 #pragma unroll
-    for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane < TR) out[w][r] = sum;
+      for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane < TR) out[w][r] = sum;
+    }
   }
 }
 
