@@ -34,7 +34,9 @@ constexpr int TCMAX = 64;   // max steps per staged waveform chunk (== max check
 template <typename T, int PK> struct Pack { typedef T type; };
 template <> struct Pack<float, 2> { typedef f2 type; };
 
-// steps per gradient-reduction tile: the per-warp transposition tile [W][TR][32] is kept <= 10 KB
+// steps per gradient-reduction tile (a CTA barrier every TR steps): the per-warp transposition tile [W][TR][32] is
+// kept <= 10 KB; 11 KB with 4 coils (TR 8 instead of 4, still 4 CTAs per SM) and 20 KB with 8 and 16 coils
+// (fp32 TR 8 / 4; 2 CTAs per SM -- measured 1.3x / 1.5x faster than TR 4 / 2 at twice the occupancy)
 #ifndef MRPHY_RED_BUDGET
 #define MRPHY_RED_BUDGET 10240
 #endif
@@ -43,7 +45,8 @@ template <> struct Pack<float, 2> { typedef f2 type; };
 #endif
 constexpr int pick_tr(int W, int elem) {
   int tr = 16;
-  while (tr > 1 && W * tr * 32 * elem > MRPHY_RED_BUDGET) tr >>= 1;
+  const int budget = W >= 19 ? 2 * MRPHY_RED_BUDGET : (W == 11 ? MRPHY_RED_BUDGET + 1024 : MRPHY_RED_BUDGET);
+  while (tr > 1 && W * tr * 32 * elem > budget) tr >>= 1;
   return tr;
 }
 
