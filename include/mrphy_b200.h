@@ -139,8 +139,15 @@ typedef struct mrphy_rfgr2beff_args {
   const void* b1; int64_t b1_sn, b1_sm;               /* (N,nM,2,nC) inner contiguous, or NULL */
   mrphy_param df, gamma;                              /* df.ptr NULL = no off-resonance */
   void* Beff;
+  const void* gBeff;                                  /* adjoint in: dL/dBeff (N,nM,nT,3) contiguous */
+  void* grf; void* ggr;                               /* adjoint out: dL/drf like rf (contiguous), dL/dgr (N,3,nT) */
+  void* partials;                                     /* adjoint workspace, mrphy_rfgr2beff_partial_elems() */
 } mrphy_rfgr2beff_args;
 int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream);
+/* The spin sums of the autograd of rfgr2beff (upstream: bmm / expand / sum backward): dL/drf_c = sum_i conj(b1_c)*gBxy,
+ * dL/dgr = sum_i loc*gBz -- one pass over dL/dBeff (12 B/spin.step read, fp32), two-stage and bitwise reproducible. */
+size_t mrphy_rfgr2beff_partial_elems(const mrphy_rfgr2beff_args* a);
+int mrphy_rfgr2beff_bwd(const mrphy_rfgr2beff_args* a, void* cuda_stream);
 
 /* Hargreaves A/B propagation, replacing beffective.beff2ab (beffective.py:40-104) and its autograd:
  * A (N,nM,3,3), B (N,nM,3) contiguous out; E1, E2 are the per-step relaxation FACTORS as upstream.

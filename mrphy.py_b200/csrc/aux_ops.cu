@@ -8,60 +8,73 @@
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
 #include "bloch_math.cuh"
+#include "grad_finalize.cuh"
 
 namespace mrphy {
 
 // ---- rfgr2beff (beffective.py:107-168) -------------------------------------------------------------
-// Threads run along time for one spin: the three components of 32 consecutive steps are 384 contiguous
-// bytes, so stores are fully coalesced; the spin's constants are warp-uniform (broadcast loads).
-// A block owns RB consecutive steps of ONE spin (SPT steps per thread, so the spin's constants and the division
-// df/gamma are amortised); results are staged in shared memory and leave as 128-bit stores of a contiguous
-// 12*RB-byte run when rows are 16-byte aligned (ALIGNED), as scalar stores otherwise.
-template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
-  constexpr int SPT = 4, RB = 256 * SPT, SPB = 8;   // steps per thread, steps per block, spins per block
-  __shared__ __align__(16) T stage[2][3 * RB];       // double-buffered: stores of spin s overlap the math of spin s+1
-  const int n = blockIdx.y;
-  const int64_t bid = blockIdx.x;
-  const int sb = (int)(bid / tblocks);               // spin block
-  const int tb0 = (int)(bid % tblocks) * RB;
+// Threads run along time for one spin: the three components of consecutive steps are contiguous, so a block's
+// output for one spin is ONE contiguous run of 12*RB bytes.  A block owns RB = 1024 consecutive steps (4 per
+// thread, waveform samples in registers) of SPB consecutive spins; per spin the 4x3 results are staged in shared
+// memory (double-buffered, one barrier per spin) and leave as 128-bit stores when rows are 16-byte aligned
+// (ALIGNED), as scalar stores otherwise.  The next spin's constants are fetched while the current one is stored.
+// MC: several coils with a b1Map (the coil sum runs inside, rf re-read from L1); otherwise the coils are
+// pre-summed (no b1Map, beffective.py:147-151) or there is one coil.
+template <typename T> struct SpinK { T lx, ly, lz, bz0, br, bi; };
+
+template <typename T>
+__device__ __forceinline__ SpinK<T> load_spin_k(const mrphy_rfgr2beff_args& a, int n, int i, bool mc) {
+  SpinK<T> k;
+  const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
+  k.lx = lp[0]; k.ly = lp[1]; k.lz = lp[2];
+  k.bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
+  k.br = (T)1; k.bi = (T)0;
+  if (a.b1 && !mc) {
+    const T* bp = (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;
+    k.br = bp[0]; k.bi = bp[a.nC];
+  }
+  return k;
+}
+
+template <typename T, bool ALIGNED, bool MC>
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 3 : 4) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
+  constexpr int SPT = 4, RB = 256 * SPT, SPB = 16;   // steps per thread, steps per block, spins per block
+  __shared__ __align__(16) T stage[2][3 * RB];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int sb = (int)(blockIdx.x / tblocks);
+  const int tb0 = (int)(blockIdx.x % tblocks) * RB;
   const int cnt = min(RB, a.nT - tb0);
-  // the block's waveform samples live in registers across its SPB spins
   T rx[SPT], ry[SPT], gx[SPT], gy[SPT], gz[SPT];
-  const bool one = a.nC == 1;
 #pragma unroll
   for (int u = 0; u < SPT; ++u) {
-    const int t = tb0 + u * 256 + threadIdx.x;
+    const int t = tb0 + u * 256 + tid;
     rx[u] = ry[u] = gx[u] = gy[u] = gz[u] = (T)0;
     if (t < a.nT) {
       const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn + (int64_t)t * a.gr_st;
       gx[u] = gr[0]; gy[u] = gr[a.gr_sx]; gz[u] = gr[2 * a.gr_sx];
-      if (one || !a.b1) {   // single coil, or coils summed because there is no b1Map (beffective.py:147-151)
+      if (!MC) {
         const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)t * a.rf_st;
         for (int c = 0; c < a.nC; ++c) { rx[u] += rf[c * a.rf_sc]; ry[u] += rf[a.rf_sx + c * a.rf_sc]; }
       }
     }
   }
-  for (int s = 0; s < SPB; ++s) {
-    const int i = sb * SPB + s;
-    if (i >= a.nM) break;
-    T* st = stage[s & 1];
-    const T* lp = (const T*)a.loc + (int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm;
-    const T lx = lp[0], ly = lp[1], lz = lp[2];
-    const T bz0 = a.df.ptr ? (T)ld_param(a.df, n, i) / (T)ld_param(a.gamma, n, i) : (T)0;   // beffective.py:142
-    const T* bp = a.b1 ? (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm : nullptr;
-    const T br0 = bp ? bp[0] : (T)1, bi0 = bp ? bp[a.nC] : (T)0;
+  const int i0 = sb * SPB, i1 = min(a.nM, i0 + SPB);
+  SpinK<T> k = load_spin_k<T>(a, n, i0, MC);
+  for (int i = i0; i < i1; ++i) {
+    const SpinK<T> kn = load_spin_k<T>(a, n, min(i + 1, i1 - 1), MC);   // in flight during this spin's math + stores
+    T* st = stage[(i - i0) & 1];
 #pragma unroll
     for (int u = 0; u < SPT; ++u) {
-      const int j = u * 256 + threadIdx.x;
+      const int j = u * 256 + tid;
       T bx, by;
-      if (one || !bp) {
-        bx = br0 * rx[u] - bi0 * ry[u];
-        by = br0 * ry[u] + bi0 * rx[u];
+      if (!MC) {
+        bx = fnma_(k.bi, ry[u], k.br * rx[u]);
+        by = fma_(k.bi, rx[u], k.br * ry[u]);
       } else {              // several coils with a b1Map (beffective.py:160-165)
         bx = by = (T)0;
         if (tb0 + j < a.nT) {
           const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn + (int64_t)(tb0 + j) * a.rf_st;
+          const T* bp = (const T*)a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;
           for (int c = 0; c < a.nC; ++c) {
             const T x = rf[c * a.rf_sc], y = rf[a.rf_sx + c * a.rf_sc], br = bp[c], bi = bp[a.nC + c];
             bx += br * x - bi * y;
@@ -69,19 +82,77 @@ __global__ void __launch_bounds__(256) rfgr2beff_kernel(const mrphy_rfgr2beff_ar
           }
         }
       }
-      st[3 * j] = bx; st[3 * j + 1] = by; st[3 * j + 2] = lx * gx[u] + ly * gy[u] + lz * gz[u] + bz0;
+      st[3 * j] = bx; st[3 * j + 1] = by;
+      st[3 * j + 2] = fma_(k.lx, gx[u], fma_(k.ly, gy[u], fma_(k.lz, gz[u], k.bz0)));
     }
-    __syncthreads();   // also orders buffer reuse: stage[s&1] was last read two iterations ago
+    __syncthreads();   // also orders buffer reuse: this buffer was last read two spins ago
     T* out = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + tb0) * 3;
     if (ALIGNED) {
       const int nvec = cnt * 3 * (int)sizeof(T) / 16;
       float4* dst = reinterpret_cast<float4*>(out);
       const float4* src = reinterpret_cast<const float4*>(st);
-      for (int q = threadIdx.x; q < nvec; q += 256) dst[q] = src[q];
+      for (int q = tid; q < nvec; q += 256) dst[q] = src[q];
     } else {
-      for (int q = threadIdx.x; q < 3 * cnt; q += 256) out[q] = st[q];
+      for (int q = tid; q < 3 * cnt; q += 256) out[q] = st[q];
+    }
+    k = kn;
+  }
+}
+
+// ---- adjoint of rfgr2beff: the sums over spins ------------------------------------------------------
+// Threads run along time (the xyz triplets of 256 consecutive steps of one spin are 3 KB contiguous, so a warp's
+// three strided loads cover whole lines); a block owns 256 steps x one range of spins and keeps its W = 2*NC+3
+// running sums in registers; the spins' constants (b1, loc) are staged through shared memory 32 spins at a time.
+// Block partials go to partials[N][S][W][nT]; grad_finalize_kernel sums the S slices in fixed order.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) rfgr2beff_bwd_kernel(const mrphy_rfgr2beff_args a, const int per_split) {
+  constexpr int W = 2 * NC + 3, CH = 32;
+  __shared__ T cst[CH][W];
+  const int n = blockIdx.z, split = blockIdx.y, S = gridDim.y, tid = threadIdx.x;
+  const int t = blockIdx.x * 256 + tid;
+  const bool valid = t < a.nT;
+  const int i0 = split * per_split, i1 = min(a.nM, i0 + per_split);
+  T arx[NC], ary[NC], ag[3] = {0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) arx[c] = ary[c] = (T)0;
+  const T* G = (const T*)a.gBeff + ((size_t)n * a.nM * a.nT + (valid ? t : 0)) * 3;
+  for (int c0 = i0; c0 < i1; c0 += CH) {
+    const int cnt = min(CH, i1 - c0);
+    __syncthreads();
+    for (int e = tid; e < cnt * W; e += 256) {
+      const int s = e / W, w = e - s * W, i = c0 + s;
+      T v;
+      if (w < 2 * NC) {     // Re / Im of b1 for coil w % NC; without a b1Map the (summed) coil sees b1 = 1
+        const int c = w % NC;
+        v = a.b1 ? (c < a.nC ? ((const T*)a.b1)[(int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm + (w / NC) * a.nC + c] : (T)0)
+                 : (w < NC ? (T)1 : (T)0);
+      } else {
+        v = ((const T*)a.loc)[(int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm + (w - 2 * NC)];
+      }
+      cst[s][w] = v;
+    }
+    __syncthreads();
+    if (!valid) continue;
+#pragma unroll 4
+    for (int s = 0; s < cnt; ++s) {
+      const T* g = G + (size_t)(c0 + s) * a.nT * 3;
+      const T gx = g[0], gy = g[1], gz = g[2];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const T br = cst[s][c], bi = cst[s][NC + c];
+        arx[c] = fma_(br, gx, fma_(bi, gy, arx[c]));     // adjoint of Bx = br rx - bi ry, By = br ry + bi rx
+        ary[c] = fma_(br, gy, fnma_(bi, gx, ary[c]));
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) ag[q] = fma_(cst[s][2 * NC + q], gz, ag[q]);
     }
   }
+  if (!valid) return;
+  T* P = (T*)a.partials + (((size_t)n * S + split) * W) * (size_t)a.nT + t;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { P[(size_t)c * a.nT] = arx[c]; P[(size_t)(NC + c) * a.nT] = ary[c]; }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) P[(size_t)(2 * NC + q) * a.nT] = ag[q];
 }
 
 // ---- beff2ab (beffective.py:40-104) ----------------------------------------------------------------
@@ -280,23 +351,90 @@ extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream)
   if (a->df.ptr && !a->gamma.ptr) return fail(MRPHY_ERR_ARG, "df needs gamma%s");
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int tblocks = (a->nT + 1023) / 1024;
-  const int64_t gx = (int64_t)((a->nM + 7) / 8) * tblocks;   // 8 spins per block (SPB)
+  const int64_t gx = (int64_t)((a->nM + 15) / 16) * tblocks;   // 16 spins per block (SPB)
   if (gx > 2147483647LL) return fail(MRPHY_ERR_ARG, "nM*nT too large for one launch%s");
   dim3 grid((unsigned)gx, a->N);
   timing_begin(st);
   const size_t es = a->dtype == MRPHY_F64 ? 8 : 4;
   const bool aligned = ((size_t)a->nT * 3 * es) % 16 == 0 && ((uintptr_t)a->Beff) % 16 == 0;
-  if (a->dtype == MRPHY_F64) {
-    if (aligned) rfgr2beff_kernel<double, true><<<grid, 256, 0, st>>>(*a, tblocks);
-    else rfgr2beff_kernel<double, false><<<grid, 256, 0, st>>>(*a, tblocks);
-  } else {
-    if (aligned) rfgr2beff_kernel<float, true><<<grid, 256, 0, st>>>(*a, tblocks);
-    else rfgr2beff_kernel<float, false><<<grid, 256, 0, st>>>(*a, tblocks);
-  }
+  const bool mc = a->b1 && a->nC > 1;
+#define RFGR_LAUNCH(T, AL, MCV) rfgr2beff_kernel<T, AL, MCV><<<grid, 256, 0, st>>>(*a, tblocks)
+#define RFGR_PICK(T)                                                  \
+  do {                                                                \
+    if (aligned) { if (mc) RFGR_LAUNCH(T, true, true); else RFGR_LAUNCH(T, true, false); }   \
+    else { if (mc) RFGR_LAUNCH(T, false, true); else RFGR_LAUNCH(T, false, false); }         \
+  } while (0)
+  if (a->dtype == MRPHY_F64) RFGR_PICK(double); else RFGR_PICK(float);
+#undef RFGR_PICK
+#undef RFGR_LAUNCH
   timing_end(st);
   ++launch_count();
   CK(cudaGetLastError());
   return MRPHY_OK;
+}
+
+namespace {
+struct RBPlan { int NC, W, S, per_split, tblocks; };
+// S spin ranges per (batch entry, 256-step block): about 4 blocks per SM in total, at least 64 spins per range
+int rb_plan(const mrphy_rfgr2beff_args* a, RBPlan* p) {
+  if (!a || !DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1 || a->nT < 1 || a->nC < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  const int nc = a->b1 ? a->nC : 1;
+  if (nc > 16) return fail(MRPHY_ERR_ARG, "more than 16 transmit coils with a b1Map are not supported%s");
+  p->NC = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : nc <= 8 ? 8 : 16;
+  p->W = 2 * p->NC + 3;
+  p->tblocks = (a->nT + 255) / 256;
+  int S = (4 * 148 + p->tblocks * a->N - 1) / (p->tblocks * a->N);
+  const int smax = (a->nM + 63) / 64;
+  S = S < 1 ? 1 : (S > smax ? smax : S);
+  if (S > 65535) S = 65535;
+  p->per_split = ((a->nM + S - 1) / S + 31) / 32 * 32;
+  p->S = (a->nM + p->per_split - 1) / p->per_split;
+  return MRPHY_OK;
+}
+
+template <typename T, int NC>
+int launch_rb(const mrphy_rfgr2beff_args* a, const RBPlan& p, cudaStream_t st) {
+  dim3 grid(p.tblocks, p.S, a->N);
+  timing_begin(st);
+  rfgr2beff_bwd_kernel<T, NC><<<grid, 256, 0, st>>>(*a, p.per_split);
+  timing_end(st);
+  ++launch_count();
+  CK(cudaGetLastError());
+  dim3 fgrid((a->nT + 31) / 32, p.W, a->N), fblock(32, 32);
+  grad_finalize_kernel<T><<<fgrid, fblock, 0, st>>>((const T*)a->partials, p.S, p.W, p.NC, a->nC, a->nT,
+                                                    (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, a->b1 ? 0 : 1, (T)1,
+                                                    (T*)a->grf, (T*)a->ggr);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+template <typename T>
+int dispatch_rb(const mrphy_rfgr2beff_args* a, const RBPlan& p, cudaStream_t st) {
+  switch (p.NC) {
+    case 1: return launch_rb<T, 1>(a, p, st);
+    case 2: return launch_rb<T, 2>(a, p, st);
+    case 4: return launch_rb<T, 4>(a, p, st);
+    case 8: return launch_rb<T, 8>(a, p, st);
+    default: return launch_rb<T, 16>(a, p, st);
+  }
+}
+}  // namespace
+
+extern "C" size_t mrphy_rfgr2beff_partial_elems(const mrphy_rfgr2beff_args* a) {
+  RBPlan p;
+  if (rb_plan(a, &p) != MRPHY_OK) return 0;
+  return (size_t)a->N * p.S * p.W * (size_t)a->nT;
+}
+
+extern "C" int mrphy_rfgr2beff_bwd(const mrphy_rfgr2beff_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  RBPlan p;
+  const int rc = rb_plan(a, &p);
+  if (rc) return rc;
+  if (!a->loc || !a->gBeff || !a->grf || !a->ggr || !a->partials) return fail(MRPHY_ERR_ARG, "loc, gBeff, grf, ggr, partials are required%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return a->dtype == MRPHY_F64 ? dispatch_rb<double>(a, p, st) : dispatch_rb<float>(a, p, st);
 }
 
 static int check_beff2ab(const mrphy_beff2ab_args* a, bool bwd) {

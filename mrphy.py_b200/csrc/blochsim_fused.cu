@@ -8,7 +8,7 @@
 //   fused_fwd_kernel<T,..>    one spin, or two spins packed in an f2 (FFMA2), per thread; checkpoint every K steps
 //   fused_*_tp_kernel         time-packed fp32 variant (one spin per thread, two steps' coefficients per f2)
 //   fused_bwd_kernel<T,..>    time-reversed state reconstruction + adjoint + spin reduction
-//   grad_finalize_kernel<T>   deterministic sum of the per-CTA partials, reference layout out
+//   grad_finalize_kernel<T>   deterministic sum of the per-CTA partials, reference layout out (grad_finalize.cuh)
 //
 // Data layout in HBM (T = float | double):
 //   wave      [N][nChunks][W][TCP]   one chunk = K steps (TCP = K rounded up to 4): a chunk is
@@ -25,6 +25,7 @@
 #include "abi_common.cuh"
 #include "bloch_math.cuh"
 #include "ptx_helpers.cuh"
+#include "grad_finalize.cuh"
 
 namespace mrphy {
 
@@ -709,40 +710,6 @@ __global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// finalize: out[n][w][t] = - sum_p partials[n][p][w][t]   (fixed order => bitwise reproducible)
-template <typename T>
-__global__ void grad_finalize_kernel(const T* __restrict__ partials, int P, int W, int NC, int nC, int nT,
-                                     int coil_dim, int bcast_coils, T* __restrict__ grf, T* __restrict__ ggr) {
-  constexpr int NY = 32;   // slices of the partial index summed in parallel, then combined in fixed order
-  __shared__ T sm[NY][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int t = blockIdx.x * 32 + tx, w = blockIdx.y, n = blockIdx.z;
-  T sum = (T)0;
-  if (t < nT) {
-    const T* p = partials + ((size_t)n * P * W + w) * (size_t)nT + t;
-    for (int q = ty; q < P; q += NY) sum += p[(size_t)q * W * nT];
-  }
-  sm[ty][tx] = sum;
-  __syncthreads();
-  if (ty == 0 && t < nT) {
-    T tot = sm[0][tx];
-#pragma unroll
-    for (int q = 1; q < NY; ++q) tot += sm[q][tx];
-    tot = -tot;
-    if (w >= 2 * NC) {
-      ggr[((size_t)n * 3 + (w - 2 * NC)) * nT + t] = tot;
-    } else {
-      const int x = w / NC, coil = w % NC;
-      const int nCo = coil_dim ? nC : 1;   // trailing dim of grf
-      if (bcast_coils) {                   // no b1Map: every coil sees the same gradient
-        for (int q = 0; q < nCo; ++q) grf[(((size_t)n * 2 + x) * nT + t) * nCo + q] = tot;
-      } else if (coil < nC) {
-        grf[(((size_t)n * 2 + x) * nT + t) * nCo + coil] = tot;
-      }
-    }
-  }
-}
 
 }  // namespace mrphy
 
@@ -1065,7 +1032,7 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, cudaStream_t st) {
   if ((rc = dispatch<T>(true, a, p, st))) return rc;
   dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 32);
   grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT,
-                                                  (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T*)a->grf,
+                                                  (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T)-1, (T*)a->grf,
                                                   (T*)a->ggr);
   ++g_launches;
   CK(cudaGetLastError());

@@ -255,13 +255,11 @@ def beff_ckpt_interval(K: int) -> int:
 
 # ------------------------------------------------------------------------------------------------
 # stand-alone operators: rfgr2beff, beff2ab (+ adjoint), beff2uphi (+ adjoint), freeprec
-def _impl_rfgr2beff(rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b1: Optional[Tensor],
-                   gamma: Tensor) -> Tensor:
-    """rf (N,2,nT[,nC]), gr (N,3,nT), loc (N,nM,3), df (N|1,nM|1), b1 (N,nM,2,nC) -> Beff (N,nM,nT,3)."""
-    L = _cabi.lib()
+def _rfgr2beff_args(rf, gr, loc, df, b1, gamma):
     a = _cabi.RfGr2BeffArgs()
     N, nM, nT = loc.shape[0], loc.shape[1], rf.shape[2]
     a.dtype = _cabi.MRPHY_F64 if loc.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.flags = _cabi.FLAG_RF_COIL_DIM if rf.ndim == 4 else 0
     a.N, a.nM, a.nT, a.nC = N, nM, nT, (rf.shape[3] if rf.ndim == 4 else 1)
     a.rf, a.rf_sn, a.rf_sx, a.rf_st = rf.data_ptr(), _bstride(rf, 0), rf.stride(1), rf.stride(2)
     a.rf_sc = rf.stride(3) if rf.ndim == 4 else 0
@@ -270,12 +268,38 @@ def _impl_rfgr2beff(rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b
     if b1 is not None:
         a.b1, a.b1_sn, a.b1_sm = b1.data_ptr(), _bstride(b1, 0), _bstride(b1, 1)
     a.df, a.gamma = _param(df, N, nM), _param(gamma, N, nM)
-    out = torch.empty((N, nM, nT, 3), dtype=loc.dtype, device=loc.device)
+    return a
+
+
+def _impl_rfgr2beff(rf: Tensor, gr: Tensor, loc: Tensor, df: Optional[Tensor], b1: Optional[Tensor],
+                   gamma: Tensor) -> Tensor:
+    """rf (N,2,nT[,nC]), gr (N,3,nT), loc (N,nM,3), df (N|1,nM|1), b1 (N,nM,2,nC) -> Beff (N,nM,nT,3)."""
+    L = _cabi.lib()
+    a = _rfgr2beff_args(rf, gr, loc, df, b1, gamma)
+    out = torch.empty((a.N, a.nM, a.nT, 3), dtype=loc.dtype, device=loc.device)
     a.Beff = out.data_ptr()
     with torch.cuda.device(loc.device):
         _cabi.check(L.mrphy_rfgr2beff(a, _stream()), 'rfgr2beff')
     _cabi.count_launches()
     return out
+
+
+def _impl_rfgr2beff_bwd(gB: Tensor, rf: Tensor, gr: Tensor, loc: Tensor, b1: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """gB (N,nM,nT,3) contiguous -> (grf like rf, ggr (N,3,nT)): the sums over spins of rfgr2beff's chain rule."""
+    L = _cabi.lib()
+    a = _rfgr2beff_args(rf, gr, loc, None, b1, None)
+    kw = {'dtype': loc.dtype, 'device': loc.device}
+    grf, ggr = torch.empty(rf.shape, **kw), torch.empty((a.N, 3, a.nT), **kw)
+    part = torch.empty(L.mrphy_rfgr2beff_partial_elems(a), **kw)
+    a.gBeff, a.grf, a.ggr, a.partials = gB.data_ptr(), grf.data_ptr(), ggr.data_ptr(), part.data_ptr()
+    with torch.cuda.device(loc.device):
+        _cabi.check(L.mrphy_rfgr2beff_bwd(a, _stream()), 'rfgr2beff_bwd')
+    _cabi.count_launches()
+    return grf, ggr
+
+
+def _fake_rfgr2beff_bwd(gB, rf, gr, loc, b1):
+    return rf.new_empty(rf.shape), gr.new_empty((loc.shape[0], 3, rf.shape[2]))
 
 
 def _fake_rfgr2beff(rf, gr, loc, df, b1, gamma):
@@ -409,7 +433,7 @@ def _fake_freeprec(Mi, dur, T1, T2, df, adjoint):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -424,6 +448,7 @@ blochsim_fused_bwd = _register('blochsim_fused_bwd', _impl_blochsim_fused_bwd, _
 blochsim_beff_fwd = _register('blochsim_beff_fwd', _impl_blochsim_beff_fwd, _fake_blochsim_beff_fwd)
 blochsim_beff_bwd = _register('blochsim_beff_bwd', _impl_blochsim_beff_bwd, _fake_blochsim_beff_bwd)
 rfgr2beff_cuda = _register('rfgr2beff', _impl_rfgr2beff, _fake_rfgr2beff)
+rfgr2beff_bwd_cuda = _register('rfgr2beff_bwd', _impl_rfgr2beff_bwd, _fake_rfgr2beff_bwd)
 beff2ab_cuda = _register('beff2ab', _impl_beff2ab, _fake_beff2ab)
 beff2ab_bwd_cuda = _register('beff2ab_bwd', _impl_beff2ab_bwd, _fake_beff2ab_bwd)
 beff2uphi_cuda = _register('beff2uphi', _impl_beff2uphi, _fake_beff2uphi)

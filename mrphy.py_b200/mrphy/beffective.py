@@ -178,18 +178,9 @@ class _RfGr2Beff(torch.autograd.Function):
         gx, gy, gz = gB.unbind(-1)
         out = [None] * 6
         rf4 = rf if rf.ndim == 4 else rf[..., None]
-        if need[0]:
-            if b1 is None:
-                g2 = torch.stack((gx.sum(1), gy.sum(1)), dim=1)                       # (N,2,nT)
-                out[0] = g2[..., None].expand(rf4.shape).contiguous() if rf.ndim == 4 else g2
-            else:
-                br, bi = b1[:, :, 0], b1[:, :, 1]                                      # (N,nM,nC)
-                grx = torch.einsum('nmc,nmt->ntc', br, gx) + torch.einsum('nmc,nmt->ntc', bi, gy)
-                gry = torch.einsum('nmc,nmt->ntc', br, gy) - torch.einsum('nmc,nmt->ntc', bi, gx)
-                g4 = torch.stack((grx, gry), dim=1)
-                out[0] = g4 if rf.ndim == 4 else g4[..., 0]
-        if need[1]:
-            out[1] = torch.einsum('nmc,nmt->nct', loc, gz)
+        if need[0] or need[1]:       # the two sums over spins: one native pass over dL/dBeff
+            grf, ggr = _ops.rfgr2beff_bwd_cuda(gB.contiguous(), rf, gr, loc, b1)
+            out[0], out[1] = (grf if need[0] else None), (ggr if need[1] else None)
         if need[2]:
             out[2] = torch.einsum('nct,nmt->nmc', gr, gz).reshape(ctx.shapes[0])
         gzs = gz.sum(-1).reshape((N,) + Nd) if (df is not None and (need[3] or need[5])) else None

@@ -46,11 +46,27 @@ for _ in range(a.reps):
     res['beff_bwd'].append(L.mrphy_last_kernel_ms())
     Mi.grad = None
     del beff, Mo
+# the whole API-faithful chain  rf,gr -> rfgr2beff -> sims.blochsim -> loss -> rf.grad, gr.grad  (4 kernels + finalize)
+rfg, grg = rf.clone().requires_grad_(True), gr.clone().requires_grad_(True)
+chain = []
+for _ in range(a.reps):
+    rfg.grad = grg.grad = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    beff = beffective.rfgr2beff(rfg, grg, loc, Δf=df, b1Map=b1)
+    Mo = sims.blochsim(Mi.detach(), beff, T1=torch.tensor(1.47, device=dev), T2=torch.tensor(0.07, device=dev))
+    Mo.sum().backward()
+    e1.record()
+    torch.cuda.synchronize()
+    res.setdefault('rfgr2beff_bwd', []).append(L.mrphy_last_kernel_ms())
+    chain.append(e0.elapsed_time(e1))
+    del beff, Mo
 units = a.nM * a.nT
-byt = {'rfgr2beff': 3 * esz, 'beff_fwd': 3 * esz, 'beff_bwd': 6 * esz}
+byt = {'rfgr2beff': 3 * esz, 'beff_fwd': 3 * esz, 'beff_bwd': 6 * esz, 'rfgr2beff_bwd': 3 * esz}
 out = {}
 for k, v in res.items():
     ms = min(v)
     out[k] = {'ms': ms, 'GB/s': units * byt[k] / (ms * 1e-3) / 1e9, 'frac_of_measured_hbm': units * byt[k] / (ms * 1e-3) / 1e9 / hbm,
               'spin_steps_per_s': units / (ms * 1e-3)}
+out['chain_fwd_bwd'] = {'ms': min(chain), 'spin_steps_per_s': units / (min(chain) * 1e-3)}
 print(json.dumps({'nM': a.nM, 'nT': a.nT, 'dtype': a.dtype, 'hbm_peak_gbs': hbm, **out}))
