@@ -164,6 +164,9 @@ template <> struct Fn<float, TRIG_FAST> {
 // 0 <= x < 2^22 * pi/2; two reduction terms are exact to < 1e-8 rad for x < ~1e4 rad), then the
 // minimax sin/cos polynomials on [-pi/4, pi/4].  ~21 FP32-pipe/ALU instructions, no XU, no branches.
 #define MRPHY_SC_MAGIC 12582912.0f   /* 1.5 * 2^23 */
+#ifndef MRPHY_PRECISE_NEWTON
+#define MRPHY_PRECISE_NEWTON 1
+#endif
 MRPHY_HD int f_as_i(float x) {
 #if defined(__CUDA_ARCH__)
   return __float_as_int(x);
@@ -204,9 +207,13 @@ template <> struct Fn<float, TRIG_PRECISE> {
 #else
     float r = (float)(1.0 / sqrt((double)x)) * (1.0f + 1.2e-7f);   // host: perturb so Newton does work
 #endif
+#if MRPHY_PRECISE_NEWTON
     // one Newton-Raphson step: r <- r + r*(0.5 - 0.5*x*r*r)
     float h = 0.5f * x * r;
     return fmaf(r, fmaf(-h, r, 0.5f), r);
+#else
+    return r;
+#endif
   }
   static MRPHY_HD void sc(float x, float& s, float& c) {
     const float t = fmaf(x, 0.63661977236758134f, MRPHY_SC_MAGIC);
@@ -233,8 +240,12 @@ template <> struct Fn<f2, TRIG_PRECISE> {
 #else
     f2 r((float)(1.0 / sqrt((double)x.v.x)) * (1.0f + 1.2e-7f), (float)(1.0 / sqrt((double)x.v.y)) * (1.0f + 1.2e-7f));
 #endif
+#if MRPHY_PRECISE_NEWTON
     const f2 nh = (f2(-0.5f) * x) * r;
     return fma_(r, fma_(nh, r, f2(0.5f)), r);
+#else
+    return r;
+#endif
   }
   static MRPHY_HD void sc(f2 x, f2& s, f2& c) {
     const f2 t = fma_(x, f2(0.63661977236758134f), f2(MRPHY_SC_MAGIC));
