@@ -194,6 +194,11 @@ typedef struct mrphy_freeprec_args {
 } mrphy_freeprec_args;
 int mrphy_freeprec(const mrphy_freeprec_args* a, void* cuda_stream);
 
+/* sizeof() of the argument structs as this library was compiled, for bindings to check their mirror of the layout:
+ * which = 0 mrphy_param, 1 mrphy_fused_args, 2 mrphy_beff_args, 3 mrphy_rfgr2beff_args, 4 mrphy_beff2ab_args,
+ * 5 mrphy_beff2uphi_args, 6 mrphy_freeprec_args; 0 for any other value. */
+size_t mrphy_sizeof_args(int which);
+
 /* Number of kernel launches the last forward / backward call on this thread issued. */
 int mrphy_last_launch_count(void);
 

@@ -344,6 +344,19 @@ using namespace mrphy;
   if (!a) return fail(MRPHY_ERR_ARG, "null args%s")
 #define DTYPE_OK(a) ((a)->dtype == MRPHY_F32 || (a)->dtype == MRPHY_F64)
 
+extern "C" size_t mrphy_sizeof_args(int which) {
+  switch (which) {
+    case 0: return sizeof(mrphy_param);
+    case 1: return sizeof(mrphy_fused_args);
+    case 2: return sizeof(mrphy_beff_args);
+    case 3: return sizeof(mrphy_rfgr2beff_args);
+    case 4: return sizeof(mrphy_beff2ab_args);
+    case 5: return sizeof(mrphy_beff2uphi_args);
+    case 6: return sizeof(mrphy_freeprec_args);
+  }
+  return 0;
+}
+
 extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream) {
   BEGIN_CALL();
   if (!DTYPE_OK(a) || a->N < 1 || a->N > 65535 || a->nM < 1 || a->nT < 1 || a->nC < 1) return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");

@@ -92,6 +92,7 @@ class FreePrecArgs(ctypes.Structure):
 EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mrphy_b200.h declares
     'mrphy_abi_version': (ctypes.c_int, []),
     'mrphy_last_error': (ctypes.c_char_p, []),
+    'mrphy_sizeof_args': (ctypes.c_size_t, [ctypes.c_int]),
     'mrphy_last_launch_count': (ctypes.c_int, []),
     'mrphy_device_sm_count': (ctypes.c_int, [ctypes.c_int]),
     'mrphy_kernel_timing': (ctypes.c_int, [ctypes.c_int]),
@@ -137,6 +138,11 @@ def lib():
                 if L.mrphy_abi_version() != ABI_VERSION:
                     raise RuntimeError(f'mrphy (B200): ABI version mismatch: library {L.mrphy_abi_version()} '
                                        f'!= binding {ABI_VERSION}; rebuild with mrphy.py_b200/build.py')
+                mirrors = (Param, FusedArgs, BeffArgs, RfGr2BeffArgs, Beff2abArgs, Beff2uphiArgs, FreePrecArgs)
+                for which, cls in enumerate(mirrors):
+                    if L.mrphy_sizeof_args(which) != ctypes.sizeof(cls):
+                        raise RuntimeError(f'mrphy (B200): layout of {cls.__name__} ({ctypes.sizeof(cls)} B) differs from '
+                                           f'the library ({L.mrphy_sizeof_args(which)} B); rebuild with mrphy.py_b200/build.py')
                 _lib = L
     return _lib
 
