@@ -3,12 +3,14 @@
 // the reference's path (a3, a5, f-1) has a native implementation behind the same C ABI.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
 #include "bloch_math.cuh"
 #include "grad_finalize.cuh"
+#include "ptx_helpers.cuh"
 
 namespace mrphy {
 
@@ -39,7 +41,9 @@ __device__ __forceinline__ SpinK<T> load_spin_k(const mrphy_rfgr2beff_args& a, i
 template <typename T, bool ALIGNED, bool MC>
 __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 3 : 4) rfgr2beff_kernel(const mrphy_rfgr2beff_args a, const int tblocks) {
   constexpr int SPT = 4, RB = 256 * SPT, SPB = 16;   // steps per thread, steps per block, spins per block
-  __shared__ __align__(16) T stage[2][3 * RB];
+  constexpr int NST = ALIGNED ? 3 : 2;               // stage buffers (3 with the asynchronous bulk stores)
+  extern __shared__ __align__(128) unsigned char rf_smem[];
+  T(*stage)[3 * RB] = reinterpret_cast<T(*)[3 * RB]>(rf_smem);
   const int n = blockIdx.y, tid = threadIdx.x;
   const int sb = (int)(blockIdx.x / tblocks);
   const int tb0 = (int)(blockIdx.x % tblocks) * RB;
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 3 : 4) rfgr2beff_kernel(
   SpinK<T> k = load_spin_k<T>(a, n, i0, MC);
   for (int i = i0; i < i1; ++i) {
     const SpinK<T> kn = load_spin_k<T>(a, n, min(i + 1, i1 - 1), MC);   // in flight during this spin's math + stores
-    T* st = stage[(i - i0) & 1];
+    T* st = stage[(i - i0) % NST];
 #pragma unroll
     for (int u = 0; u < SPT; ++u) {
       const int j = u * 256 + tid;
@@ -85,18 +89,25 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 3 : 4) rfgr2beff_kernel(
       st[3 * j] = bx; st[3 * j + 1] = by;
       st[3 * j + 2] = fma_(k.lx, gx[u], fma_(k.ly, gy[u], fma_(k.lz, gz[u], k.bz0)));
     }
-    __syncthreads();   // also orders buffer reuse: this buffer was last read two spins ago
     T* out = (T*)a.Beff + (((int64_t)n * a.nM + i) * a.nT + tb0) * 3;
     if (ALIGNED) {
-      const int nvec = cnt * 3 * (int)sizeof(T) / 16;
-      float4* dst = reinterpret_cast<float4*>(out);
-      const float4* src = reinterpret_cast<const float4*>(st);
-      for (int q = tid; q < nvec; q += 256) dst[q] = src[q];
+      // the row leaves as ONE TMA bulk store (cp.async.bulk shared -> global, 12*cnt bytes).  Three buffers: before this
+      // barrier thread 0 waits until all but the latest store have finished reading shared memory, so the buffer
+      // written at the next spin (last used three spins ago) is known to be free by everyone after the barrier.
+      fence_proxy_async_smem();
+      if (tid == 0) bulk_wait_read<1>();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_s2g(out, st, (uint32_t)(cnt * 3 * sizeof(T)));
+        bulk_commit();
+      }
     } else {
+      __syncthreads();   // also orders buffer reuse: this buffer was last read two spins ago
       for (int q = tid; q < 3 * cnt; q += 256) out[q] = st[q];
     }
     k = kn;
   }
+  if (ALIGNED && tid == 0) bulk_wait_read<0>();   // shared memory must outlive the last stores
 }
 
 // ---- adjoint of rfgr2beff: the sums over spins ------------------------------------------------------
@@ -153,6 +164,87 @@ __global__ void __launch_bounds__(256) rfgr2beff_bwd_kernel(const mrphy_rfgr2bef
   for (int c = 0; c < NC; ++c) { P[(size_t)c * a.nT] = arx[c]; P[(size_t)(NC + c) * a.nT] = ary[c]; }
 #pragma unroll
   for (int q = 0; q < 3; ++q) P[(size_t)(2 * NC + q) * a.nT] = ag[q];
+}
+
+// Same reduction with the rows staged by the TMA engine: one 1-D bulk copy (cp.async.bulk, 3 KB = 256 steps x xyz)
+// per spin, G spins per stage, two stages on mbarriers -- 24 KB in flight per block, no registers or L1 sectors spent
+// on the strided xyz pattern; threads then read their own triplet from shared memory (stride 3: conflict-free).
+// Needs 16-byte aligned rows: nT % 4 == 0 (the launcher falls back to the kernel above otherwise).
+template <typename T> struct RBTma {
+  static constexpr int G = 32 / (int)sizeof(T);                       // spins per stage: 8 (fp32), 4 (fp64)
+  static constexpr int TBK = 256;
+  static constexpr size_t buf_bytes = (size_t)2 * G * 3 * TBK * sizeof(T);   // 48 KB
+};
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) rfgr2beff_bwd_tma_kernel(const mrphy_rfgr2beff_args a, const int per_split) {
+  constexpr int W = 2 * NC + 3, G = RBTma<T>::G, TBK = RBTma<T>::TBK;
+  extern __shared__ __align__(128) unsigned char rb_smem[];
+  T(*buf)[G][3 * TBK] = reinterpret_cast<T(*)[G][3 * TBK]>(rb_smem);
+  T(*cst)[G][W] = reinterpret_cast<T(*)[G][W]>(rb_smem + RBTma<T>::buf_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(rb_smem + RBTma<T>::buf_bytes + ((sizeof(T) * 2 * G * W + 15) / 16) * 16);
+  const int n = blockIdx.z, split = blockIdx.y, S = gridDim.y, tid = threadIdx.x;
+  const int t0 = blockIdx.x * TBK, len = min(TBK, a.nT - t0);
+  const uint32_t row_bytes = (uint32_t)(len * 3 * sizeof(T));
+  const bool valid = tid < len;
+  const int i0 = split * per_split, i1 = min(a.nM, i0 + per_split);
+  const int ngroups = (i1 - i0 + G - 1) / G;
+  const T* Gb = (const T*)a.gBeff + ((size_t)n * a.nM * a.nT + t0) * 3;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int g, int s) {
+    const int c0 = i0 + g * G, cnt = min(G, i1 - c0);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&full[s], row_bytes * cnt);
+      for (int q = 0; q < cnt; ++q) bulk_g2s(buf[s][q], Gb + (size_t)(c0 + q) * a.nT * 3, row_bytes, &full[s]);
+    }
+    for (int e = tid; e < cnt * W; e += 256) {   // the group's b1 / loc (visible after the barrier closing this iteration)
+      const int q = e / W, w = e - q * W, i = c0 + q;
+      T v;
+      if (w < 2 * NC) {
+        const int c = w % NC;
+        v = a.b1 ? (c < a.nC ? ((const T*)a.b1)[(int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm + (w / NC) * a.nC + c] : (T)0)
+                 : (w < NC ? (T)1 : (T)0);
+      } else {
+        v = ((const T*)a.loc)[(int64_t)n * a.loc_sn + (int64_t)i * a.loc_sm + (w - 2 * NC)];
+      }
+      cst[s][q][w] = v;
+    }
+  };
+  T arx[NC], ary[NC], ag[3] = {0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) arx[c] = ary[c] = (T)0;
+  if (ngroups > 0) issue(0, 0);
+  __syncthreads();
+  for (int g = 0; g < ngroups; ++g) {
+    const int s = g & 1, cnt = min(G, i1 - (i0 + g * G));
+    if (g + 1 < ngroups) issue(g + 1, s ^ 1);   // that stage was drained in iteration g-1 (barrier below)
+    mbar_wait(&full[s], (g >> 1) & 1);
+    if (valid) {
+#pragma unroll 4
+      for (int q = 0; q < cnt; ++q) {
+        const T gx = buf[s][q][3 * tid], gy = buf[s][q][3 * tid + 1], gz = buf[s][q][3 * tid + 2];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const T br = cst[s][q][c], bi = cst[s][q][NC + c];
+          arx[c] = fma_(br, gx, fma_(bi, gy, arx[c]));
+          ary[c] = fma_(br, gy, fnma_(bi, gx, ary[c]));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ag[k] = fma_(cst[s][q][2 * NC + k], gz, ag[k]);
+      }
+    }
+    __syncthreads();
+  }
+  if (!valid) return;
+  T* P = (T*)a.partials + (((size_t)n * S + split) * W) * (size_t)a.nT + t0 + tid;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { P[(size_t)c * a.nT] = arx[c]; P[(size_t)(NC + c) * a.nT] = ary[c]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) P[(size_t)(2 * NC + k) * a.nT] = ag[k];
 }
 
 // ---- beff2ab (beffective.py:40-104) ----------------------------------------------------------------
@@ -371,7 +463,12 @@ extern "C" int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream)
   const size_t es = a->dtype == MRPHY_F64 ? 8 : 4;
   const bool aligned = ((size_t)a->nT * 3 * es) % 16 == 0 && ((uintptr_t)a->Beff) % 16 == 0;
   const bool mc = a->b1 && a->nC > 1;
-#define RFGR_LAUNCH(T, AL, MCV) rfgr2beff_kernel<T, AL, MCV><<<grid, 256, 0, st>>>(*a, tblocks)
+#define RFGR_LAUNCH(T, AL, MCV)                                                                       \
+  do {                                                                                                \
+    constexpr size_t smem_ = (size_t)((AL) ? 3 : 2) * 3 * 1024 * sizeof(T);                           \
+    CK(cudaFuncSetAttribute(rfgr2beff_kernel<T, AL, MCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+    rfgr2beff_kernel<T, AL, MCV><<<grid, 256, smem_, st>>>(*a, tblocks);                              \
+  } while (0)
 #define RFGR_PICK(T)                                                  \
   do {                                                                \
     if (aligned) { if (mc) RFGR_LAUNCH(T, true, true); else RFGR_LAUNCH(T, true, false); }   \
@@ -408,9 +505,19 @@ int rb_plan(const mrphy_rfgr2beff_args* a, RBPlan* p) {
 template <typename T, int NC>
 int launch_rb(const mrphy_rfgr2beff_args* a, const RBPlan& p, cudaStream_t st) {
   dim3 grid(p.tblocks, p.S, a->N);
-  timing_begin(st);
-  rfgr2beff_bwd_kernel<T, NC><<<grid, 256, 0, st>>>(*a, p.per_split);
-  timing_end(st);
+  const bool tma = a->nT % 4 == 0 && ((uintptr_t)a->gBeff & 15) == 0 && !getenv("MRPHY_B200_RB_NOTMA");
+  if (tma) {
+    constexpr size_t smem = RBTma<T>::buf_bytes + ((sizeof(T) * 2 * RBTma<T>::G * (2 * NC + 3) + 15) / 16) * 16 + 16;
+    auto kern = rfgr2beff_bwd_tma_kernel<T, NC>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    timing_begin(st);
+    kern<<<grid, 256, smem, st>>>(*a, p.per_split);
+    timing_end(st);
+  } else {
+    timing_begin(st);
+    rfgr2beff_bwd_kernel<T, NC><<<grid, 256, 0, st>>>(*a, p.per_split);
+    timing_end(st);
+  }
   ++launch_count();
   CK(cudaGetLastError());
   dim3 fgrid((a->nT + 31) / 32, p.W, a->N), fblock(32, 32);

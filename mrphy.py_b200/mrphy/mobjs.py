@@ -203,9 +203,9 @@ class SpinArray(_Obj):
     reach the compact data -- index the compact arrays through :meth:`crds_` instead.
     """
 
-    _readonly = ('shape', 'mask', 'device', 'dtype', 'is_cuda', 'ndim', 'nM')
+    _readonly = ('shape', 'mask', 'device', 'dtype', 'is_cuda', 'ndim', 'nM', 'midx')
     _compact = ('T1_', 'T2_', 'γ_', 'M_')
-    __slots__ = {'T1_', 'T2_', 'γ_', 'M_', 'shape', 'mask', 'ndim', 'nM', 'device', 'dtype', 'is_cuda'}
+    __slots__ = {'T1_', 'T2_', 'γ_', 'M_', 'shape', 'mask', 'ndim', 'nM', 'device', 'dtype', 'is_cuda', 'midx'}
 
     def __init__(
         self,
@@ -229,8 +229,11 @@ class SpinArray(_Obj):
         mask = mask.to(device=device)
         assert isinstance(device, torch.device) and isinstance(dtype, torch.dtype)
         assert mask.dtype == torch.bool and mask.shape == (1,) + shape[1:]
-        self._put(shape=shape, mask=mask, ndim=len(shape), nM=int(torch.count_nonzero(mask).item()), device=device,
-                  dtype=dtype, is_cuda=(device.type == 'cuda'))
+        # flat positions of the stored spins, found once: embed/extract are then an index_copy_/index_select on the
+        # device with no host synchronisation (boolean-mask indexing would run nonzero() + a sync on every call)
+        midx = mask.reshape(-1).nonzero().reshape(-1)
+        self._put(shape=shape, mask=mask, ndim=len(shape), nM=int(midx.numel()), device=device,
+                  dtype=dtype, is_cuda=(device.type == 'cuda'), midx=midx)
         fallback = {'T1': T1G, 'T2': T2G, 'γ': γH, 'M': tensor([0., 0., 1.])}
         for name, full, compact in (('T1', T1, T1_), ('T2', T2, T2_), ('γ', γ, γ_), ('M', M, M_)):
             assert (full is None) or (compact is None)
@@ -268,16 +271,19 @@ class SpinArray(_Obj):
         r"""Compact `(N,nM,...)` -> `(N,*Nd,...)`; positions outside the mask are NaN (or keep ``out``'s content)."""
         if out is None:
             out = v_.new_full(self.shape + v_.shape[2:], float('nan'))
-        out[self.mask.expand(self.shape)] = v_.reshape((-1,) + v_.shape[2:])
+        if out.is_contiguous():
+            out.view((self.shape[0], -1) + v_.shape[2:]).index_copy_(1, self.midx, v_.to(out.dtype))
+        else:
+            out[self.mask.expand(self.shape)] = v_.reshape((-1,) + v_.shape[2:])
         return out
 
     def extract(self, v: Tensor, *, out_: OptT = None) -> Tensor:
         r"""`(N,*Nd,...)` -> compact `(N,nM,...)`, row-major over `*Nd`."""
-        chosen = v[self.mask.expand(self.shape)]
         tail = v.shape[self.ndim:]
+        chosen = v.reshape((v.shape[0], -1) + tail).index_select(1, self.midx)
         if out_ is None:
-            return chosen.reshape((self.shape[0], self.nM) + tail)
-        out_.view((-1,) + tail).copy_(chosen)
+            return chosen
+        out_.copy_(chosen)
         return out_
 
     def crds_(self, crds: list) -> list:
@@ -292,7 +298,7 @@ class SpinArray(_Obj):
     def mask_(self, *, mask: Tensor) -> Tensor:
         r"""Restrict an external ``mask`` `(1,*Nd)` to the stored spins -> `(1,nM)`.  (Upstream's version calls a
         tensor and always raises, mobjs.py:605.)"""
-        return mask.to(self.device)[self.mask].reshape((1, -1))
+        return mask.to(self.device).reshape(1, -1).index_select(1, self.midx)
 
     def dim(self) -> int:
         r"""Number of dimensions of ``shape``."""
