@@ -52,11 +52,36 @@ def _param(t: Optional[Tensor], N: int, nM: int, per_batch_only=False) -> _cabi.
     return p
 
 
+_const_cache = {}
+
+
+def on_device(x: Optional[Tensor], device, dtype=None) -> Optional[Tensor]:
+    """``x`` on ``device`` (and ``dtype`` when given).  Small host-resident constants -- the module defaults γH, dt0,
+    T1G, T2G or a user's CPU scalars -- map to the SAME device tensor on every call (keyed by object and in-place version,
+    weak references guard against id reuse): repeated calls neither pay a pageable host-to-device copy per constant
+    nor defeat the per-tensor cache of `pick_ckpt_interval`.  The result is shared: callers never write to it."""
+    if x is None:
+        return None
+    if x.device == device and (dtype is None or x.dtype == dtype):
+        return x
+    if x.device.type == 'cpu' and x.numel() <= 16 and not x.requires_grad:
+        key = (id(x), device, dtype)
+        hit = _const_cache.get(key)
+        if hit is not None and hit[0]() is x and hit[1] == x._version:
+            return hit[2]
+        y = x.to(device=device) if dtype is None else x.to(device=device, dtype=dtype)
+        if len(_const_cache) > 256:
+            _const_cache.clear()
+        _const_cache[key] = (weakref.ref(x), x._version, y)
+        return y
+    return x.to(device=device) if dtype is None else x.to(device=device, dtype=dtype)
+
+
 def flat_param(x: Optional[Tensor], N: int, Nd: tuple, device) -> Optional[Tensor]:
     """(), (N|1,), (N|1, *Nd|1.., [1, 1])-style constant -> (N|1, nM|1) view (copy only for partial broadcasts)."""
     if x is None:
         return None
-    x = x.to(device=device)
+    x = on_device(x, device)
     while x.ndim > 1 + len(Nd):
         assert x.shape[-1] == 1
         x = x[..., 0]
@@ -530,7 +555,7 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
     assert M_.shape == (N, nM, 3) and loc_.shape == (N, nM, 3)
     assert rf.shape[0] == N and rf.shape[1] == 2 and gr.shape == (N, 3, rf.shape[2])
     cast = lambda x: None if x is None else x.to(device=dev, dtype=dtype)
-    move = lambda x: None if x is None else (x.to(device=dev) if x.dtype in _F else x.to(device=dev, dtype=dtype))
+    move = lambda x: None if x is None else (on_device(x, dev) if x.dtype in _F else on_device(x, dev, dtype))
     rf, gr = cast(rf), cast(gr)
     Mi = _inner_contig(cast(M_), 1)
     loc = _inner_contig(cast(loc_), 1)

@@ -70,7 +70,7 @@ def beff2uϕ(beff: Tensor, γ2πdt: Tensor, *, dim=-1) -> Tuple[Tensor, Tensor]:
     b = beff if dim == last else beff.movedim(dim, last)
     if b.ndim == 1:
         b = b[None]
-    U, Φ = _Beff2UPhi.apply(b, _working(γ2πdt.to(beff.device), beff))
+    U, Φ = _Beff2UPhi.apply(b, _working(_ops.on_device(γ2πdt, beff.device), beff))
     if beff.ndim == 1:
         U, Φ = U[0], Φ[0]
     return (U if dim == last else U.movedim(last, dim)), Φ
@@ -87,7 +87,7 @@ class _Beff2AB(torch.autograd.Function):
         N, Nd, dev = beff.shape[0], tuple(beff.shape[1:-2]), beff.device
         b = _ops._inner_contig(beff.reshape(N, -1, beff.shape[-2], 3), 2)
         E1f, E2f, γf = (_ops.flat_param(x, N, Nd, dev) for x in (E1, E2, γ))
-        dtf = dt.to(dev).reshape(-1)
+        dtf = _ops.on_device(dt, dev).reshape(-1)
         flags = _ops.default_flags()
         K = 0
         if any(ctx.needs_input_grad):
@@ -142,7 +142,8 @@ def beff2ab(
     """
     _ops._require_cuda(beff)
     dev = beff.device
-    return _Beff2AB.apply(beff, E1.to(dev), E2.to(dev), γ.to(dev), dt.to(dev))
+    mv = lambda x: _ops.on_device(x, dev)
+    return _Beff2AB.apply(beff, mv(E1), mv(E2), mv(γ), mv(dt))
 
 
 class _RfGr2Beff(torch.autograd.Function):
@@ -217,4 +218,4 @@ def rfgr2beff(
     _ops._require_cuda(rf)
     dev = rf.device
     cast = lambda x: None if x is None else _working(x.to(dev), rf)
-    return _RfGr2Beff.apply(rf, cast(gr), cast(loc), cast(Δf), cast(b1Map), γ.to(dev))
+    return _RfGr2Beff.apply(rf, cast(gr), cast(loc), cast(Δf), cast(b1Map), _ops.on_device(γ, dev))

@@ -51,7 +51,7 @@ class BlochSim(Function):
         B = _ops._inner_contig(B, 2)
         M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)
         T1f, T2f, gf = (_flat_param(x, N, Nd, dev) for x in (T1, T2, γ))
-        dtf = dt.to(device=dev).reshape(-1)
+        dtf = _ops.on_device(dt, dev).reshape(-1)
         K = _ops.beff_ckpt_interval(_ops.pick_ckpt_interval(dtf, T1f, T2f))
         flags = _ops.default_flags()
         Mo, ckpt = _ops.blochsim_beff_fwd(M, B, T1f, T2f, gf, dtf, K, flags)
@@ -97,6 +97,9 @@ def blochsim(
     """
     assert (Mi.shape[:-1] == Beff.shape[:-2])        # sims.py:305
     Beff, ndim = Beff.to(Mi.device), Beff.ndim
+    # host-resident constants (the defaults γH, dt0) first become their cached device copies, THEN views: the views'
+    # base is then the same object on every call and the checkpoint-interval cache (no host sync) can hit
+    γ, dt, T1, T2 = (_ops.on_device(x, Mi.device) for x in (γ, dt, T1, T2))
     γ, dt = (x.reshape(x.shape + (ndim - x.ndim) * (1,)) for x in (γ, dt))
     assert ((T1 is None) == (T2 is None))            # sims.py:311
     if T1 is not None:
@@ -116,7 +119,7 @@ class FreePrec(Function):
         assert (T1 is None) == (T2 is None)
         _ops._require_cuda(Mi)
         N, Nd, dev = Mi.shape[0], tuple(Mi.shape[1:-1]), Mi.device
-        args = (dur.to(dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
+        args = (_ops.on_device(dur, dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
                 _flat_param(Δf, N, Nd, dev))
         ctx.args, ctx.shape = args, Mi.shape
         M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)

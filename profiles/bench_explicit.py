@@ -48,13 +48,14 @@ for _ in range(a.reps):
     del beff, Mo
 # the whole API-faithful chain  rf,gr -> rfgr2beff -> sims.blochsim -> loss -> rf.grad, gr.grad  (4 kernels + finalize)
 rfg, grg = rf.clone().requires_grad_(True), gr.clone().requires_grad_(True)
+T1c, T2c, Mic = torch.tensor(1.47, device=dev), torch.tensor(0.07, device=dev), Mi.detach()
 chain = []
 for _ in range(a.reps):
     rfg.grad = grg.grad = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     beff = beffective.rfgr2beff(rfg, grg, loc, Δf=df, b1Map=b1)
-    Mo = sims.blochsim(Mi.detach(), beff, T1=torch.tensor(1.47, device=dev), T2=torch.tensor(0.07, device=dev))
+    Mo = sims.blochsim(Mic, beff, T1=T1c, T2=T2c)
     Mo.sum().backward()
     e1.record()
     torch.cuda.synchronize()
