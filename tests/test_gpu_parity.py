@@ -462,6 +462,25 @@ def test_beff2uphi_kernel_and_adjoint(dev, dtype):
     assert mx(bt.grad, -2 * torch.nn.functional.normalize(bt.detach(), dim=-1)) < 1e-12
 
 
+def test_host_constants_are_cached_per_object_and_version(dev):
+    """`_ops.on_device`: a small CPU constant maps to ONE device tensor per (object, in-place version) -- the default
+    γH / dt0 therefore cost no copy and no synchronisation per call -- and an in-place edit or a tensor that requires
+    grad is never served from the cache."""
+    from mrphy import _ops, dt0
+    a, b = _ops.on_device(dt0, dev), _ops.on_device(dt0, dev)
+    assert a is b and a.device == dev and float(a) == float(dt0)
+    c = torch.tensor([1.5, 2.5], dtype=f64)
+    c1 = _ops.on_device(c, dev)
+    c.mul_(2)
+    c2 = _ops.on_device(c, dev)
+    assert c2 is not c1 and c2.tolist() == [3.0, 5.0] and c1.tolist() == [1.5, 2.5]
+    g = torch.tensor(2.0, requires_grad=True)
+    assert _ops.on_device(g, dev) is not _ops.on_device(g, dev) and _ops.on_device(g, dev).requires_grad
+    big = torch.zeros(64)
+    assert _ops.on_device(big, dev) is not _ops.on_device(big, dev)
+    assert _ops.on_device(a, dev) is a and _ops.on_device(None, dev) is None
+
+
 def test_freeprec_kernel(dev, golden):
     """tests/test_slowsims.py:100-122, tests/test_sims.py:145-198, tests/test_mobjs.py:133-158 on CUDA."""
     from mrphy import sims, mobjs, γH
