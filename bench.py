@@ -86,9 +86,11 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def synth(N, n_x, n, nT, dtype, seed=0, x_off=0, n_x_total=None):
+def synth(N, n_x, n, nT, dtype, seed=0, x_off=0, n_x_total=None, interp=1):
     """Seeded synthetic slab (SURVEY 8d distributions), generated in fp64 then rounded to `dtype`.
-    Slab = x-indices [x_off, x_off+n_x) of a (n_x_total, n, n) grid with 24 cm fov per 64 voxels."""
+    Slab = x-indices [x_off, x_off+n_x) of a (n_x_total, n, n) grid with 24 cm fov per 64 voxels.
+    interp > 1 (BASELINE config C3, "multi-scale interpT design"): the waveform is drawn with nT/interp samples at
+    interp*4 us in fp64 and brought to nT samples at 4 us by `Pulse.interpT` (fp64, or the grid is 1 short)."""
     n_x_total = n_x if n_x_total is None else n_x_total
     gen = torch.Generator().manual_seed(seed + 1000 * x_off)
     U = lambda *s: torch.rand(s, generator=gen, dtype=torch.float64) * 2 - 1
@@ -100,7 +102,17 @@ def synth(N, n_x, n, nT, dtype, seed=0, x_off=0, n_x_total=None):
     nM = loc.shape[1]
     wgen = torch.Generator().manual_seed(seed)          # the waveform is the same on every rank
     W = lambda *s: torch.rand(s, generator=wgen, dtype=torch.float64) * 2 - 1
-    rf, gr = W(N, 2, nT) * 0.1, W(N, 3, nT) * 2
+    if interp > 1:
+        from mrphy import mobjs
+        assert nT % interp == 0
+        f8 = torch.float64
+        coarse = mobjs.Pulse(rf=W(N, 2, nT // interp) * 0.1, gr=W(N, 3, nT // interp) * 2,
+                             dt=torch.tensor(4e-6 * interp, dtype=f8), dtype=f8)
+        fine = coarse.interpT(dt=torch.tensor(4e-6, dtype=f8))
+        rf, gr = fine.rf, fine.gr
+        assert rf.shape[2] == nT, rf.shape
+    else:
+        rf, gr = W(N, 2, nT) * 0.1, W(N, 3, nT) * 2
     df = U(N, nM) * 200
     b1 = U(N, nM, 2) * 0.1
     b1[:, :, 0] += 1
@@ -112,7 +124,8 @@ def workload_desc(args, world):
     N, n, nT = WORKLOADS[args.workload]
     return (f'{args.workload.upper()}: SpinCube {n}^3 x N={N} ' +
             ('per GPU' if args.scaling == 'weak' else f'split over {world} GPUs') +
-            f', nT={nT}, dt=4us, b1Map+df+relaxation, fwd+adjoint bwd')
+            f', nT={nT}, dt=4us' + (f' (Pulse.interpT from {nT // 5} x 20us)' if args.workload == 'c3' else '') +
+            ', b1Map+df+relaxation, fwd+adjoint bwd')
 
 
 def run_ours(args):
@@ -128,11 +141,12 @@ def run_ours(args):
     N, n, nT = WORKLOADS[args.workload]
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
     kw = {'dtype': dtype, 'device': dev}
+    itp = 5 if args.workload == 'c3' else 1    # C3: the pulse comes out of Pulse.interpT (400 x 20 us -> 2000 x 4 us)
     if args.scaling == 'strong':      # the whole n^3 cube split into x-slabs (BASELINE config C5)
         assert n % world == 0
-        host = synth(N, n // world, n, nT, dtype, x_off=rank * (n // world), n_x_total=n)
+        host = synth(N, n // world, n, nT, dtype, x_off=rank * (n // world), n_x_total=n, interp=itp)
     else:                             # weak: every rank owns an n^3 slab of an (n*world) x n x n cube
-        host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world)
+        host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world, interp=itp)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     nM = host['loc'].shape[1]
     tgt = torch.tensor([0., 1., 0.], **kw)
