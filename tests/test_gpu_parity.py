@@ -462,6 +462,53 @@ def test_beff2uphi_kernel_and_adjoint(dev, dtype):
     assert mx(bt.grad, -2 * torch.nn.functional.normalize(bt.detach(), dim=-1)) < 1e-12
 
 
+def test_multiscale_design_loop_through_public_api(dev):
+    """The use the reference is built for (BASELINE config C3 in miniature): optimise a pulse through its
+    re-parametrisation (utils.tρθ2rf / ts2s / s2g), refine it with Pulse.interpT on the device, keep optimising.
+    The loss must fall at both scales, and the interpolated pulse must reproduce the coarse pulse's magnetisation
+    to first order (same waveform, 5x finer steps)."""
+    from mrphy import mobjs, utils
+    kw = {'dtype': f32, 'device': dev}
+    cube = mobjs.SpinCube((1, 8, 8, 8), tensor([[24., 24., 24.]]), **kw)
+    cube.Δf = (torch.rand(1, 8, 8, 8, generator=torch.Generator().manual_seed(0)) * 100 - 50).to(dev)
+    tgt = tensor([0., 1., 0.], **kw)
+
+    def loss_of(pulse):
+        cube.M = tensor([0., 0., 1.], **kw)
+        return ((cube.applypulse(pulse, doEmbed=False) - tgt) ** 2).mean()
+
+    def descend(p0, iters, lr):
+        rfmax, smax = p0.rfmax, p0.smax
+        tρ, θ = (x.detach().clone().requires_grad_(True) for x in utils.rf2tρθ(p0.rf, rfmax))
+        ts = utils.s2ts(utils.g2s(p0.gr, p0.dt), smax).detach().clone().requires_grad_(True)
+        hist = []
+        for _ in range(iters):
+            p = mobjs.Pulse(rf=utils.tρθ2rf(tρ, θ, rfmax), gr=utils.s2g(utils.ts2s(ts, smax), p0.dt), dt=p0.dt, **kw)
+            L = loss_of(p)
+            L.backward()
+            hist.append(float(L.detach()))
+            with torch.no_grad():
+                for v in (tρ, θ, ts):
+                    v -= lr * v.grad / (v.grad.abs().max() + 1e-12)
+                    v.grad = None
+        return p, hist
+
+    gen = torch.Generator().manual_seed(1)
+    nT = 40
+    rf0 = (torch.rand(1, 2, nT, generator=gen) * 2 - 1) * 0.02
+    gr0 = torch.cumsum((torch.rand(1, 3, nT, generator=gen) * 2 - 1) * 0.02, dim=2)
+    coarse = mobjs.Pulse(rf=rf0, gr=gr0, dt=tensor(20e-6, dtype=f64), **kw)
+    coarse, h1 = descend(coarse, 6, 0.05)
+    assert h1[-1] < h1[0]
+    fine = mobjs.Pulse(rf=coarse.rf.detach().double(), gr=coarse.gr.detach().double(), dt=tensor(20e-6, dtype=f64),
+                       dtype=f64, device=dev).interpT(dt=tensor(4e-6, dtype=f64)).to(device=dev, dtype=f32)
+    assert fine.rf.shape[2] == 5 * nT and fine.rf.device.type == 'cuda'
+    with torch.no_grad():
+        assert abs(float(loss_of(fine)) - float(loss_of(coarse))) < 0.05
+    _, h2 = descend(fine, 4, 0.02)
+    assert h2[-1] < h2[0]
+
+
 def test_host_constants_are_cached_per_object_and_version(dev):
     """`_ops.on_device`: a small CPU constant maps to ONE device tensor per (object, in-place version) -- the default
     γH / dt0 therefore cost no copy and no synchronisation per call -- and an in-place edit or a tensor that requires
