@@ -157,10 +157,14 @@ def run_ours(args):
         pulse = mobjs.Pulse(rf=d['rf'].requires_grad_(True), gr=d['gr'].requires_grad_(True), **kw)
         return sp, pulse, d
 
-    def step(sp, pulse, d):
+    def local_step(sp, pulse, d):
         M = sp.applypulse(pulse, loc_=d['loc'], Δf_=d['df'], b1Map_=d['b1'])
         loss = ((M - tgt) ** 2).sum()
         loss.backward()
+        return loss
+
+    def step(sp, pulse, d):
+        loss = local_step(sp, pulse, d)
         if world > 1:
             parallel.allreduce_waveform_grads(pulse.rf, pulse.gr, loss.detach().reshape(1))
         return loss
@@ -180,21 +184,56 @@ def run_ours(args):
         pulse.rf.grad = pulse.gr.grad = None
         step(sp, pulse, d)
     barrier()
-    # ---- timed region: resident inputs, per-step CUDA events, L2 flushed between steps
-    launches0 = _cabi.launch_counter
-    evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.fill_(1.0)
+    # ---- timed region: resident inputs, per-step CUDA events, L2 flushed between steps.  The local part of a step
+    # (forward, loss, adjoint backward: 4 of our kernels + the loss kernels) is recorded once into a CUDA graph and
+    # replayed; the gradient all-reduce (N > 1) stays eager.  --no-graph, or a failed capture, falls back to eager
+    # launches of the same calls.
+    def timed_region():
+        graph, g_loss, per_step = None, None, None
+        if not args.no_graph:
+            try:
+                pulse.rf.grad = pulse.gr.grad = None
+                l0 = _cabi.launch_counter
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    g_loss = local_step(sp, pulse, d)
+                per_step = _cabi.launch_counter - l0
+                for _ in range(2):
+                    g_.replay()
+                graph = g_
+            except Exception as e:                  # noqa: BLE001 -- any capture problem: measure eagerly instead
+                print(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches',
+                      file=sys.stderr)
+                torch.cuda.synchronize()
+                graph = None
+
+        def one():
+            if graph is None:
+                pulse.rf.grad = pulse.gr.grad = None
+                step(sp, pulse, d)
+            else:
+                graph.replay()
+                if world > 1:
+                    parallel.allreduce_waveform_grads(pulse.rf, pulse.gr, g_loss.detach().reshape(1))
+
+        barrier()
+        l0 = _cabi.launch_counter
+        evs = []
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            one()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(x.elapsed_time(y) for x, y in evs)
+        n_launch = per_step * args.steps if graph is not None else _cabi.launch_counter - l0
+        mode = 'eager' if graph is None else 'CUDA graph replay of the step (pack, fwd, loss, bwd, finalize)'
         pulse.rf.grad = pulse.gr.grad = None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step(sp, pulse, d)
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    launches = _cabi.launch_counter - launches0
+        return ms, n_launch, mode
+
+    ms_total, launches, launch_mode = timed_region()
     # ---- end-to-end: pinned host inputs -> device every step, loss + gradients read back.  The objects live
     # across steps as in a design loop; every step overwrites ALL their device data from pinned host memory.
     sp2, pulse2, d2 = make_objects(host)
@@ -243,25 +282,15 @@ def run_ours(args):
         ((M - tgt) ** 2).sum().backward()
         k_bwd.append(L.mrphy_last_kernel_ms())
     L.mrphy_kernel_timing(0)
-    # ---- the opt-in MUFU trigonometry (MRPHY_B200_TRIG=fast), same timed loop, reported as an extra
+    del M          # a live autograd graph would pin AccumulateGrad nodes to this stream and spoil the next capture
+    # ---- the opt-in MUFU trigonometry (MRPHY_B200_TRIG=fast), same timed region, reported as an extra
     alt_ms = None
     if dtype == torch.float32:
         os.environ['MRPHY_B200_TRIG'] = 'fast'
         for _ in range(2):
             pulse.rf.grad = pulse.gr.grad = None
             step(sp, pulse, d)
-        barrier()
-        ev2 = []
-        for _ in range(args.steps):
-            flush.fill_(1.0)
-            pulse.rf.grad = pulse.gr.grad = None
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step(sp, pulse, d)
-            e1.record()
-            ev2.append((e0, e1))
-        barrier()
-        alt_ms = sum(a.elapsed_time(b) for a, b in ev2)
+        alt_ms = timed_region()[0]
         del os.environ['MRPHY_B200_TRIG']
     clocks = sampler.stop() if rank == 0 else None
     # ---- reduce over ranks (max time), aggregate
@@ -294,7 +323,7 @@ def run_ours(args):
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
             'config': {'workload': workload_desc(args, world), 'spins_per_gpu': N * nM, 'nT': nT,
-                       'l2': 'flushed between steps (256 MB write)', 'sharding': f'spin slabs x{world}, waveform '
+                       'l2': 'flushed between steps (256 MB write)', 'launch': launch_mode, 'sharding': f'spin slabs x{world}, waveform '
                        'replicated, 1 allreduce of grads' if world > 1 else 'single GPU'},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches,
@@ -418,6 +447,7 @@ if __name__ == '__main__':
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph replay')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     (run_ours if a.impl == 'ours' else run_reference)(a)
