@@ -540,21 +540,12 @@ def test_step_is_cuda_graph_capturable(dev):
         return L.detach().clone(), pulse.rf.grad.clone(), pulse.gr.grad.clone()
 
     want = [eager(rf, gr) for rf, gr in zip(rfs, grs)]
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            pulse.rf.grad = pulse.gr.grad = None
-            step()
-    torch.cuda.current_stream().wait_stream(side)
-    pulse.rf.grad = pulse.gr.grad = None
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        static_loss = step()
+    from mrphy import graphs
+    captured = graphs.capture(step, params=(pulse.rf, pulse.gr))
     for (L, grf, ggr), rf, gr in zip(want, rfs, grs):
         with torch.no_grad():
             pulse.rf.copy_(rf); pulse.gr.copy_(gr)
-        graph.replay()
+        static_loss = captured.replay()
         torch.cuda.synchronize()
         assert torch.equal(static_loss, L) and torch.equal(pulse.rf.grad, grf) and torch.equal(pulse.gr.grad, ggr)
     assert torch.equal(sp.M_, M0)          # doUpdate=False: the stored state is untouched
