@@ -31,6 +31,21 @@ namespace mrphy {
 
 constexpr int TCMAX = 64;   // max steps per staged waveform chunk (== max checkpoint interval)
 
+#ifdef MRPHY_CTA_TRACE
+// measurement build only (profiles/cta_trace.py): per CTA of the backward kernel (SM id, start, end) in ns
+__device__ unsigned long long g_cta_trace[8192][3];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned s;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(s));
+  return s;
+}
+#endif
+
 // value type of a thread: one spin (T) or two spins packed for FFMA2 (f2)
 template <typename T, int PK> struct Pack { typedef T type; };
 template <> struct Pack<float, 2> { typedef f2 type; };
@@ -371,6 +386,9 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
     for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
     return;
   }
+#ifdef MRPHY_CTA_TRACE
+  if (tid == 0 && blockIdx.x < 8192 && n == 0) { g_cta_trace[blockIdx.x][0] = smid(); g_cta_trace[blockIdx.x][1] = gtime(); }
+#endif
   uint32_t it = 0, red_par = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
@@ -489,6 +507,9 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
       }
     }
   }
+#ifdef MRPHY_CTA_TRACE
+  if (tid == 0 && blockIdx.x < 8192 && n == 0) g_cta_trace[blockIdx.x][2] = gtime();
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -758,6 +779,11 @@ extern "C" float mrphy_last_kernel_ms(void) {
   return ms;
 }
 
+#ifdef MRPHY_CTA_TRACE
+extern "C" int mrphy_debug_cta_trace(unsigned long long* host_out, int n_ctas) {
+  return cudaMemcpyFromSymbol(host_out, mrphy::g_cta_trace, sizeof(unsigned long long) * 3 * (size_t)n_ctas) == cudaSuccess ? 0 : -2;
+}
+#endif
 extern "C" int mrphy_abi_version(void) { return MRPHY_ABI_VERSION; }
 extern "C" const char* mrphy_last_error(void) { return g_err; }
 extern "C" int mrphy_last_launch_count(void) { return g_launches; }
