@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(256) k(float2* out, float a, float b) {
       if (MODE == 4) y[i] = __fmul2_rn(y[j], y[l]);                                 // FMUL2, 2 varying pairs
       if (MODE == 5) x[i] = fmaf(x[j], x[l], x[i]);                                 // scalar FFMA, 3 varying
       if (MODE == 6) { y[i].x = fmaf(y[j].x, y[l].x, y[i].x); y[i].y = fmaf(y[j].y, y[l].y, y[i].y); }   // 2 scalar FFMAs on pairs
+      if (MODE == 8) x[i] = fmaf(x[(i + 1) % U], x[(i + 2) % U], x[i]);                      // scalar FFMA, 3 varying, registers of both parities
+      if (MODE == 9) x[i] = fmaf(x[(i + 1) % U], x[(i + 3) % U], x[i]);                      // scalar FFMA, 3 varying, another mix
       if (MODE == 7) y[i] = __ffma2_rn(y[j], y[l], make_float2(0.5f, 0.5f));        // 2 pairs + immediate
     }
   }
@@ -57,5 +59,7 @@ int main() {
   run<5>("FFMA scalar 3 varying", 1, out, sms);
   run<6>("2x FFMA scalar on pair halves (2 instr)", 2, out, sms);
   run<7>("FFMA2 2 pairs + immediate", 1, out, sms);
+  run<8>("FFMA scalar 3 varying (i,i+1,i+2)", 1, out, sms);
+  run<9>("FFMA scalar 3 varying (i,i+1,i+3)", 1, out, sms);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
