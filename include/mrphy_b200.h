@@ -194,9 +194,49 @@ typedef struct mrphy_freeprec_args {
 } mrphy_freeprec_args;
 int mrphy_freeprec(const mrphy_freeprec_args* a, void* cuda_stream);
 
+/* Waveform re-parametrisation of the design loop, replacing the elementwise chains of
+ * utils.t-rho-theta2rf / l-rho-theta2rf (utils.py:114-131, 311-330), utils.ts2s (utils.py:293-308) and utils.s2g
+ * (utils.py:239-256) and their autograd -- what the optimiser differentiates through on either side of applypulse:
+ *   rf[n,:,t,c] = A(rho[n,0,t,c]) * rfmax[n,c] * (cos theta, sin theta),  A = atan(.)*2/pi (rf_kind 1) | sigmoid (rf_kind 2)
+ *   s[n,x,t]    = atan(ts[n,x,t])*2/pi * smax[n,x]                        (gr_kind 1 and 3; gr_kind 2 takes s as `ts`)
+ *   g[n,x,t]    = dt[n] * sum_{t' <= t} s[n,x,t']                          (gr_kind 1 and 2; gr_kind 3 returns s)
+ * ONE launch does both halves (either may be absent: kind 0).  adjoint != 0: from grf, ggr write grho, gtheta, gts
+ * (the reversed running sum for the gradient half).  Everything is contiguous in the reference layouts.          */
+typedef struct mrphy_reparam_args {
+  int32_t dtype, adjoint;
+  int32_t N, nT, nC;                    /* nC: trailing coil dimension of rho/theta/rf (1 when absent)            */
+  int32_t rf_kind;                      /* 0 none, 1 t-rho (atan), 2 l-rho (sigmoid)                              */
+  int32_t gr_kind;                      /* 0 none, 1 ts -> g, 2 s -> g, 3 ts -> s                                 */
+  int32_t _pad;
+  const void* rho; const void* theta;   /* (N,1,nT,nC)                                                            */
+  const void* rfmax; int64_t rfmax_sn, rfmax_sc;   /* element (n,c) at rfmax[n*sn + c*sc] (strides 0 broadcast)    */
+  const void* ts;                       /* (N,3,nT)                                                               */
+  const void* smax; int64_t smax_sn, smax_sx;      /* element (n,x) at smax[n*sn + x*sx]                           */
+  mrphy_param dt;                       /* (N,) s                                                                 */
+  void* rf; void* gr;                   /* forward out: (N,2,nT,nC), (N,3,nT)                                     */
+  const void* grf; const void* ggr;     /* adjoint in, like rf, gr                                                */
+  void* grho; void* gtheta; void* gts;  /* adjoint out, like rho, theta, ts                                       */
+} mrphy_reparam_args;
+int mrphy_design_waveform(const mrphy_reparam_args* a, void* cuda_stream);
+
+/* Mask gather of the spin axis (mobjs.SpinArray.extract / .embed, mobjs.py:512-553) as ONE pass over the output:
+ *   out[n, j, :] = idx[j] >= 0 ? in[n, idx[j], :] : NaN        j in [0, nOut), `inner` trailing elements per spin
+ * extract: idx = row-major positions of the mask's True entries (nOut = nM, nIn = prod(Nd));
+ * embed:   idx = the inverse map, -1 outside the mask (nOut = prod(Nd), nIn = nM) -- NaN padding as mobjs.py:525.
+ * in (N,nIn,inner) and out (N,nOut,inner) contiguous.                                                             */
+typedef struct mrphy_mask_args {
+  int32_t dtype, N;
+  int32_t fill_zero, _pad;          /* != 0: rows with idx < 0 are 0 instead of NaN (the transposed map of the other direction) */
+  int64_t nOut, nIn, inner;
+  const int64_t* idx;
+  const void* in;
+  void* out;
+} mrphy_mask_args;
+int mrphy_mask_copy(const mrphy_mask_args* a, void* cuda_stream);
+
 /* sizeof() of the argument structs as this library was compiled, for bindings to check their mirror of the layout:
  * which = 0 mrphy_param, 1 mrphy_fused_args, 2 mrphy_beff_args, 3 mrphy_rfgr2beff_args, 4 mrphy_beff2ab_args,
- * 5 mrphy_beff2uphi_args, 6 mrphy_freeprec_args; 0 for any other value. */
+ * 5 mrphy_beff2uphi_args, 6 mrphy_freeprec_args, 7 mrphy_reparam_args, 8 mrphy_mask_args; 0 for any other value. */
 size_t mrphy_sizeof_args(int which);
 
 /* Number of kernel launches the last forward / backward call on this thread issued. */

@@ -12,9 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmrphy_b200.so')
-SOURCES = ['blochsim_fused.cu', 'blochsim_beff.cu', 'aux_ops.cu']
+SOURCES = ['blochsim_fused.cu', 'blochsim_beff.cu', 'aux_ops.cu', 'design_ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo', '-ftz=true',
-              '--threads', '3', '--shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include')]
+              '--threads', '4', '--shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include')]
 
 
 def _stale():

@@ -445,6 +445,8 @@ extern "C" size_t mrphy_sizeof_args(int which) {
     case 4: return sizeof(mrphy_beff2ab_args);
     case 5: return sizeof(mrphy_beff2uphi_args);
     case 6: return sizeof(mrphy_freeprec_args);
+    case 7: return sizeof(mrphy_reparam_args);
+    case 8: return sizeof(mrphy_mask_args);
   }
   return 0;
 }

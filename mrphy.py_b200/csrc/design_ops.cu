@@ -1,0 +1,194 @@
+// Waveform-sized and mask-sized companions of the simulation path, sm_100a.
+//
+//   design_waveform_kernel<T>   the optimiser's re-parametrisation chain in ONE launch (and its adjoint in one):
+//                               rf = A(rho)*rfmax*(cos theta, sin theta)   utils.py:114-131 (l-rho), 311-330 (t-rho)
+//                               s  = atan(ts)*2/pi*smax                     utils.py:293-308 (ts2s)
+//                               g  = dt*cumsum(s)                           utils.py:239-256 (s2g)
+//                               upstream: ~10 elementwise launches + a scan forward, ~25 launches backward.
+//   mask_copy_kernel<T>         SpinArray.extract / .embed (mobjs.py:512-553) as one pass over the output with the NaN
+//                               padding fused (upstream: full() + masked assignment).
+//
+// These are O(N*nT) / O(N*prod(Nd)) and HBM- or latency-bound; all arithmetic is done in double and rounded once, so
+// the fp32 results are correctly rounded images of the reference's formula.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/mrphy_b200.h"
+#include "abi_common.cuh"
+
+namespace mrphy {
+
+constexpr int RP_THREADS = 256;
+constexpr double TWO_OVER_PI = 0.63661977236758134307553505349006;
+
+// inclusive scan of one value per thread across the CTA (256 threads); returns the CTA total through `total`
+__device__ __forceinline__ double block_scan_incl(double v, double* warp_tot, double& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += u;
+  }
+  if (lane == 31) warp_tot[w] = v;
+  __syncthreads();
+  double pre = 0.0, tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < RP_THREADS / 32; ++q) {
+    const double x = warp_tot[q];
+    if (q < w) pre += x;
+    tot += x;
+  }
+  __syncthreads();   // warp_tot is reused by the next chunk
+  total = tot;
+  return v + pre;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RP_THREADS) design_waveform_kernel(const mrphy_reparam_args a, const int gr_rows) {
+  __shared__ double warp_tot[RP_THREADS / 32];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < gr_rows) {
+    // ---- gradient half: one CTA per (n, xyz) row, chunks of 256 samples, running carry between chunks
+    const int row = blockIdx.x, n = row / 3, x = row % 3, nT = a.nT;
+    const bool use_atan = a.gr_kind != 2, scan = a.gr_kind != 3;
+    const double smax = use_atan ? (double)((const T*)a.smax)[(int64_t)n * a.smax_sn + (int64_t)x * a.smax_sx] : 1.0;
+    const double dt = scan ? ld_param(a.dt, n, 0) : 1.0;
+    const T* in = (const T*)a.ts + (int64_t)row * nT;
+    if (!a.adjoint) {
+      T* out = (T*)a.gr + (int64_t)row * nT;
+      double carry = 0.0;
+      for (int base = 0; base < nT; base += RP_THREADS) {
+        const int t = base + tid;
+        double s = 0.0;
+        if (t < nT) s = use_atan ? atan((double)in[t]) * TWO_OVER_PI * smax : (double)in[t];
+        if (!scan) {
+          if (t < nT) out[t] = (T)s;
+          continue;
+        }
+        double tot;
+        const double inc = block_scan_incl(s, warp_tot, tot);
+        if (t < nT) out[t] = (T)(dt * (carry + inc));
+        carry += tot;
+      }
+    } else {
+      // dL/ds[t] = dt * sum_{t' >= t} dL/dg[t']  (reversed running sum), then through atan
+      const T* gg = (const T*)a.ggr + (int64_t)row * nT;
+      T* out = (T*)a.gts + (int64_t)row * nT;
+      double carry = 0.0;
+      for (int base = 0; base < nT; base += RP_THREADS) {
+        const int t = nT - 1 - (base + tid);
+        double g = t >= 0 ? (double)gg[t] : 0.0;
+        if (scan) {
+          double tot;
+          const double inc = block_scan_incl(g, warp_tot, tot);
+          g = dt * (carry + inc);
+          carry += tot;
+        }
+        if (t >= 0) {
+          if (use_atan) {
+            const double v = (double)in[t];
+            g *= TWO_OVER_PI * smax / (1.0 + v * v);
+          }
+          out[t] = (T)g;
+        }
+      }
+    }
+    return;
+  }
+  // ---- rf half: one thread per (n, t, c)
+  const int64_t per = (int64_t)a.nT * a.nC;
+  const int64_t e = (int64_t)(blockIdx.x - gr_rows) * RP_THREADS + tid;
+  if (e >= (int64_t)a.N * per) return;
+  const int n = (int)(e / per);
+  const int64_t r = e - (int64_t)n * per;
+  const int c = (int)(r % a.nC);
+  const double rho = (double)((const T*)a.rho)[e], th = (double)((const T*)a.theta)[e];
+  const double rfmax = (double)((const T*)a.rfmax)[(int64_t)n * a.rfmax_sn + (int64_t)c * a.rfmax_sc];
+  double A, dA;
+  if (a.rf_kind == 1) {
+    A = atan(rho) * TWO_OVER_PI;
+    dA = TWO_OVER_PI / (1.0 + rho * rho);
+  } else {
+    A = 1.0 / (1.0 + exp(-rho));
+    dA = A * (1.0 - A);
+  }
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  const int64_t ox = (int64_t)n * 2 * per + r, oy = ox + per;
+  if (!a.adjoint) {
+    T* rf = (T*)a.rf;
+    rf[ox] = (T)(A * rfmax * cs);
+    rf[oy] = (T)(A * rfmax * sn);
+  } else {
+    const double gx = (double)((const T*)a.grf)[ox], gy = (double)((const T*)a.grf)[oy];
+    ((T*)a.grho)[e] = (T)(dA * rfmax * (cs * gx + sn * gy));
+    ((T*)a.gtheta)[e] = (T)(A * rfmax * (cs * gy - sn * gx));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mask_copy_kernel(const mrphy_mask_args a, const int64_t total) {
+  const int64_t per = a.nOut * a.inner;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int64_t n = e / per, r = e - n * per;
+    const int64_t j = r / a.inner, k = r - j * a.inner;
+    const int64_t src = a.idx[j];
+    T v;
+    if (src >= 0) v = ((const T*)a.in)[(n * a.nIn + src) * a.inner + k];
+    else v = a.fill_zero ? (T)0 : (T)NAN;
+    ((T*)a.out)[e] = v;
+  }
+}
+
+}  // namespace mrphy
+
+using namespace mrphy;
+
+extern "C" int mrphy_design_waveform(const mrphy_reparam_args* a, void* cuda_stream) {
+  launch_count() = 0;
+  err_buf()[0] = 0;
+  if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
+  if ((a->dtype != MRPHY_F32 && a->dtype != MRPHY_F64) || a->N < 1 || a->nT < 1 || a->nC < 1)
+    return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (a->rf_kind < 0 || a->rf_kind > 2 || a->gr_kind < 0 || a->gr_kind > 3 || (a->rf_kind == 0 && a->gr_kind == 0))
+    return fail(MRPHY_ERR_ARG, "rf_kind must be 0..2 and gr_kind 0..3, not both 0%s");
+  if (a->rf_kind) {
+    if (!a->rho || !a->theta || !a->rfmax) return fail(MRPHY_ERR_ARG, "rho, theta, rfmax are required%s");
+    if (a->adjoint ? (!a->grf || !a->grho || !a->gtheta) : !a->rf) return fail(MRPHY_ERR_ARG, "rf half: output (or gradient) buffers missing%s");
+  }
+  if (a->gr_kind) {
+    if (!a->ts) return fail(MRPHY_ERR_ARG, "ts is required%s");
+    if (a->gr_kind != 2 && !a->smax) return fail(MRPHY_ERR_ARG, "smax is required%s");
+    if (a->gr_kind != 3 && !a->dt.ptr) return fail(MRPHY_ERR_ARG, "dt is required%s");
+    if (a->adjoint ? (!a->ggr || !a->gts) : !a->gr) return fail(MRPHY_ERR_ARG, "gradient half: output (or gradient) buffers missing%s");
+  }
+  const int64_t rows = a->gr_kind ? (int64_t)a->N * 3 : 0;
+  const int64_t blocks = a->rf_kind ? ((int64_t)a->N * a->nT * a->nC + RP_THREADS - 1) / RP_THREADS : 0;
+  if (rows + blocks > 2147483647LL) return fail(MRPHY_ERR_ARG, "too many elements for one launch%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (a->dtype == MRPHY_F64) design_waveform_kernel<double><<<(unsigned)(rows + blocks), RP_THREADS, 0, st>>>(*a, (int)rows);
+  else design_waveform_kernel<float><<<(unsigned)(rows + blocks), RP_THREADS, 0, st>>>(*a, (int)rows);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
+extern "C" int mrphy_mask_copy(const mrphy_mask_args* a, void* cuda_stream) {
+  launch_count() = 0;
+  err_buf()[0] = 0;
+  if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
+  if ((a->dtype != MRPHY_F32 && a->dtype != MRPHY_F64) || a->N < 1 || a->nOut < 0 || a->nIn < 0 || a->inner < 1)
+    return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  const int64_t total = (int64_t)a->N * a->nOut * a->inner;
+  if (total == 0) return MRPHY_OK;
+  if (!a->idx || !a->in || !a->out) return fail(MRPHY_ERR_ARG, "idx, in, out are required%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);   // grid-stride above 32 CTAs per SM
+  if (a->dtype == MRPHY_F64) mask_copy_kernel<double><<<grid, 256, 0, st>>>(*a, total);
+  else mask_copy_kernel<float><<<grid, 256, 0, st>>>(*a, total);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}

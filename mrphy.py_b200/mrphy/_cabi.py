@@ -89,6 +89,25 @@ class FreePrecArgs(ctypes.Structure):
     ]
 
 
+class ReparamArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('adjoint', c_i32), ('N', c_i32), ('nT', c_i32), ('nC', c_i32), ('rf_kind', c_i32),
+        ('gr_kind', c_i32), ('_pad', c_i32),
+        ('rho', c_vp), ('theta', c_vp), ('rfmax', c_vp), ('rfmax_sn', c_i64), ('rfmax_sc', c_i64),
+        ('ts', c_vp), ('smax', c_vp), ('smax_sn', c_i64), ('smax_sx', c_i64),
+        ('dt', Param),
+        ('rf', c_vp), ('gr', c_vp), ('grf', c_vp), ('ggr', c_vp), ('grho', c_vp), ('gtheta', c_vp), ('gts', c_vp),
+    ]
+
+
+class MaskArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('N', c_i32), ('fill_zero', c_i32), ('_pad', c_i32), ('nOut', c_i64), ('nIn', c_i64),
+        ('inner', c_i64),
+        ('idx', c_vp), ('inp', c_vp), ('out', c_vp),
+    ]
+
+
 EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mrphy_b200.h declares
     'mrphy_abi_version': (ctypes.c_int, []),
     'mrphy_last_error': (ctypes.c_char_p, []),
@@ -113,6 +132,8 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_beff2ab_bwd': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),
     'mrphy_beff2uphi': (ctypes.c_int, [ctypes.POINTER(Beff2uphiArgs), c_vp]),
     'mrphy_freeprec': (ctypes.c_int, [ctypes.POINTER(FreePrecArgs), c_vp]),
+    'mrphy_design_waveform': (ctypes.c_int, [ctypes.POINTER(ReparamArgs), c_vp]),
+    'mrphy_mask_copy': (ctypes.c_int, [ctypes.POINTER(MaskArgs), c_vp]),
 }
 
 _lib = None
@@ -138,7 +159,8 @@ def lib():
                 if L.mrphy_abi_version() != ABI_VERSION:
                     raise RuntimeError(f'mrphy (B200): ABI version mismatch: library {L.mrphy_abi_version()} '
                                        f'!= binding {ABI_VERSION}; rebuild with mrphy.py_b200/build.py')
-                mirrors = (Param, FusedArgs, BeffArgs, RfGr2BeffArgs, Beff2abArgs, Beff2uphiArgs, FreePrecArgs)
+                mirrors = (Param, FusedArgs, BeffArgs, RfGr2BeffArgs, Beff2abArgs, Beff2uphiArgs, FreePrecArgs, ReparamArgs,
+                           MaskArgs)
                 for which, cls in enumerate(mirrors):
                     if L.mrphy_sizeof_args(which) != ctypes.sizeof(cls):
                         raise RuntimeError(f'mrphy (B200): layout of {cls.__name__} ({ctypes.sizeof(cls)} B) differs from '

@@ -454,11 +454,129 @@ def _fake_freeprec(Mi, dur, T1, T2, df, adjoint):
     return Mi.new_empty(Mi.shape)
 
 
+def _reparam_args(rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind, adjoint):
+    """Fill the C struct from (already validated, contiguous) tensors; returns (args, N, nT, nC, dtype, device)."""
+    a = _cabi.ReparamArgs()
+    lead = rho if rf_kind else ts
+    N, nT = lead.shape[0], lead.shape[2]
+    nC = rho.shape[3] if (rf_kind and rho.ndim == 4) else 1
+    a.dtype = _cabi.MRPHY_F64 if lead.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.adjoint, a.N, a.nT, a.nC, a.rf_kind, a.gr_kind = int(adjoint), N, nT, nC, rf_kind, gr_kind
+    if rf_kind:
+        a.rho, a.theta = rho.data_ptr(), theta.data_ptr()
+        v = rfmax.expand((N, nC))                      # (N|1, nC|1) -> strides, 0 where broadcast
+        a.rfmax, a.rfmax_sn, a.rfmax_sc = v.data_ptr(), v.stride(0), v.stride(1)
+    if gr_kind:
+        a.ts = ts.data_ptr()
+        if gr_kind != 2:
+            v = smax.expand((N, 3))
+            a.smax, a.smax_sn, a.smax_sx = v.data_ptr(), v.stride(0), v.stride(1)
+        if gr_kind != 3:
+            a.dt = _param(dt, N, 1, per_batch_only=True)
+    return a, lead
+
+
+def _impl_design_waveform(rho: Optional[Tensor], theta: Optional[Tensor], rfmax: Optional[Tensor], ts: Optional[Tensor],
+                          smax: Optional[Tensor], dt: Optional[Tensor], rf_kind: int, gr_kind: int) -> Tuple[Tensor, Tensor]:
+    """One launch: (rho, theta, rfmax) -> rf (N,2,nT[,nC]) and/or (ts|s, smax, dt) -> gr|s (N,3,nT); an absent half
+    returns an empty tensor.  rfmax is (N|1, nC|1), smax (N|1, 3|1) (see utils._design_call)."""
+    L = _cabi.lib()
+    a, lead = _reparam_args(rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind, False)
+    rf = torch.empty((rho.shape[0], 2) + tuple(rho.shape[2:]) if rf_kind else (0,), dtype=lead.dtype, device=lead.device)
+    gr = torch.empty(ts.shape if gr_kind else (0,), dtype=lead.dtype, device=lead.device)
+    a.rf, a.gr = rf.data_ptr(), gr.data_ptr()
+    with torch.cuda.device(lead.device):
+        _cabi.check(L.mrphy_design_waveform(a, _stream()), 'design_waveform')
+    _cabi.count_launches()
+    return rf, gr
+
+
+def _fake_design_waveform(rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind):
+    lead = rho if rf_kind else ts
+    return (lead.new_empty((rho.shape[0], 2) + tuple(rho.shape[2:]) if rf_kind else (0,)),
+            lead.new_empty(ts.shape if gr_kind else (0,)))
+
+
+def _impl_design_waveform_bwd(grf: Optional[Tensor], ggr: Optional[Tensor], rho: Optional[Tensor], theta: Optional[Tensor],
+                              rfmax: Optional[Tensor], ts: Optional[Tensor], smax: Optional[Tensor], dt: Optional[Tensor],
+                              rf_kind: int, gr_kind: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Adjoint in one launch: (dL/drf, dL/dgr) -> (dL/drho, dL/dtheta, dL/dts); absent halves come back empty."""
+    L = _cabi.lib()
+    a, lead = _reparam_args(rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind, True)
+    e = lambda like, on: torch.empty(like.shape if on else (0,), dtype=lead.dtype, device=lead.device)
+    grho, gtheta, gts = e(rho if rf_kind else lead, rf_kind), e(theta if rf_kind else lead, rf_kind), e(ts if gr_kind else lead, gr_kind)
+    if rf_kind:
+        grf = grf.contiguous()
+        a.grf, a.grho, a.gtheta = grf.data_ptr(), grho.data_ptr(), gtheta.data_ptr()
+    if gr_kind:
+        ggr = ggr.contiguous()
+        a.ggr, a.gts = ggr.data_ptr(), gts.data_ptr()
+    with torch.cuda.device(lead.device):
+        _cabi.check(L.mrphy_design_waveform(a, _stream()), 'design_waveform (adjoint)')
+    _cabi.count_launches()
+    return grho, gtheta, gts
+
+
+def _fake_design_waveform_bwd(grf, ggr, rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind):
+    lead = rho if rf_kind else ts
+    e = lambda like, on: lead.new_empty(like.shape if on else (0,))
+    return e(rho if rf_kind else lead, rf_kind), e(theta if rf_kind else lead, rf_kind), e(ts if gr_kind else lead, gr_kind)
+
+
+def _design_setup(ctx, inputs, output):
+    rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind = inputs
+    ctx.save_for_backward(rho, theta, rfmax, ts, smax, dt)
+    ctx.kinds = (rf_kind, gr_kind)
+
+
+def _design_backward(ctx, grf, ggr):
+    rho, theta, rfmax, ts, smax, dt = ctx.saved_tensors
+    rf_kind, gr_kind = ctx.kinds
+    if rf_kind and grf is None:
+        grf = torch.zeros((rho.shape[0], 2) + tuple(rho.shape[2:]), dtype=rho.dtype, device=rho.device)
+    if gr_kind and ggr is None:
+        ggr = torch.zeros_like(ts)
+    grho, gtheta, gts = design_waveform_bwd_cuda(grf if rf_kind else None, ggr if gr_kind else None, rho, theta, rfmax, ts,
+                                                 smax, dt, rf_kind, gr_kind)
+    return (grho if rf_kind else None, gtheta if rf_kind else None, None, gts if gr_kind else None, None, None, None, None)
+
+
+def _impl_mask_copy(v: Tensor, idx: Tensor, inv: Tensor, fill_zero: bool) -> Tensor:
+    """v (N,nIn,inner) contiguous, idx (nOut,) int64 -> out[n,j] = v[n,idx[j]], rows with idx[j] < 0 are NaN (or 0).
+    ``inv`` (nIn,) is the inverse map; only the backward uses it."""
+    L = _cabi.lib()
+    a = _cabi.MaskArgs()
+    n_out = idx.numel()
+    a.dtype = _cabi.MRPHY_F64 if v.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.N, a.fill_zero, a.nOut, a.nIn, a.inner = v.shape[0], int(fill_zero), n_out, v.shape[1], v.shape[2]
+    out = torch.empty((v.shape[0], n_out, v.shape[2]), dtype=v.dtype, device=v.device)
+    a.idx, a.inp, a.out = idx.data_ptr(), v.data_ptr(), out.data_ptr()
+    with torch.cuda.device(v.device):
+        _cabi.check(L.mrphy_mask_copy(a, _stream()), 'mask_copy')
+    _cabi.count_launches()
+    return out
+
+
+def _fake_mask_copy(v, idx, inv, fill_zero):
+    return v.new_empty((v.shape[0], idx.numel(), v.shape[2]))
+
+
+def _mask_setup(ctx, inputs, output):
+    v, idx, inv, fill_zero = inputs
+    ctx.save_for_backward(idx, inv)
+
+
+def _mask_backward(ctx, g):
+    # the transposed map of a gather with distinct sources is the gather with the inverse index, zeros where unused
+    idx, inv = ctx.saved_tensors
+    return mask_copy_cuda(g.contiguous(), inv, idx, True), None, None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -479,7 +597,12 @@ beff2ab_bwd_cuda = _register('beff2ab_bwd', _impl_beff2ab_bwd, _fake_beff2ab_bwd
 beff2uphi_cuda = _register('beff2uphi', _impl_beff2uphi, _fake_beff2uphi)
 beff2uphi_bwd_cuda = _register('beff2uphi_bwd', _impl_beff2uphi_bwd, _fake_beff2uphi_bwd)
 freeprec_cuda = _register('freeprec', _impl_freeprec, _fake_freeprec)
+design_waveform_cuda = _register('design_waveform', _impl_design_waveform, _fake_design_waveform)
+design_waveform_bwd_cuda = _register('design_waveform_bwd', _impl_design_waveform_bwd, _fake_design_waveform_bwd)
+mask_copy_cuda = _register('mask_copy', _impl_mask_copy, _fake_mask_copy)
 torch.library.register_autograd('mrphy_b200::blochsim_fused_fwd', _fused_backward, setup_context=_fused_setup, lib=_LIB)
+torch.library.register_autograd('mrphy_b200::design_waveform', _design_backward, setup_context=_design_setup, lib=_LIB)
+torch.library.register_autograd('mrphy_b200::mask_copy', _mask_backward, setup_context=_mask_setup, lib=_LIB)
 
 
 # ------------------------------------------------------------------------------------------------

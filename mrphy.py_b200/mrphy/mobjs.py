@@ -51,6 +51,13 @@ def _one_of(full, compact, extract):
     return compact if full is None else extract(full)
 
 
+
+def _mask_kernel_ok(v: Tensor) -> bool:
+    """embed/extract run the one-pass CUDA gather for floating CUDA tensors; anything else (CPU objects, integer or
+    boolean payloads) takes the equivalent torch indexing."""
+    return v.is_cuda and v.dtype in (torch.float32, torch.float64) and v.numel() > 0 and v.ndim >= 2
+
+
 class _Obj(object):
     """Attribute writes go through ``_store`` (validation + normalisation); deepcopy copies slots verbatim."""
     __slots__ = ()
@@ -203,9 +210,9 @@ class SpinArray(_Obj):
     reach the compact data -- index the compact arrays through :meth:`crds_` instead.
     """
 
-    _readonly = ('shape', 'mask', 'device', 'dtype', 'is_cuda', 'ndim', 'nM', 'midx')
+    _readonly = ('shape', 'mask', 'device', 'dtype', 'is_cuda', 'ndim', 'nM', 'midx', 'minv')
     _compact = ('T1_', 'T2_', 'γ_', 'M_')
-    __slots__ = {'T1_', 'T2_', 'γ_', 'M_', 'shape', 'mask', 'ndim', 'nM', 'device', 'dtype', 'is_cuda', 'midx'}
+    __slots__ = {'T1_', 'T2_', 'γ_', 'M_', 'shape', 'mask', 'ndim', 'nM', 'device', 'dtype', 'is_cuda', 'midx', 'minv'}
 
     def __init__(
         self,
@@ -232,8 +239,11 @@ class SpinArray(_Obj):
         # flat positions of the stored spins, found once: embed/extract are then an index_copy_/index_select on the
         # device with no host synchronisation (boolean-mask indexing would run nonzero() + a sync on every call)
         midx = mask.reshape(-1).nonzero().reshape(-1)
+        # inverse map (-1 outside the mask): embed is then ONE gather pass with the NaN padding fused (mask_copy kernel)
+        minv = torch.full((mask.numel(),), -1, dtype=torch.int64, device=device)
+        minv[midx] = torch.arange(midx.numel(), dtype=torch.int64, device=device)
         self._put(shape=shape, mask=mask, ndim=len(shape), nM=int(midx.numel()), device=device,
-                  dtype=dtype, is_cuda=(device.type == 'cuda'), midx=midx)
+                  dtype=dtype, is_cuda=(device.type == 'cuda'), midx=midx, minv=minv)
         fallback = {'T1': T1G, 'T2': T2G, 'γ': γH, 'M': tensor([0., 0., 1.])}
         for name, full, compact in (('T1', T1, T1_), ('T2', T2, T2_), ('γ', γ, γ_), ('M', M, M_)):
             assert (full is None) or (compact is None)
@@ -269,6 +279,9 @@ class SpinArray(_Obj):
     # ---- mask plumbing
     def embed(self, v_: Tensor, *, out: OptT = None) -> Tensor:
         r"""Compact `(N,nM,...)` -> `(N,*Nd,...)`; positions outside the mask are NaN (or keep ``out``'s content)."""
+        if out is None and _mask_kernel_ok(v_):
+            flat = _ops.mask_copy_cuda(v_.reshape(v_.shape[0], v_.shape[1], -1).contiguous(), self.minv, self.midx, False)
+            return flat.reshape((v_.shape[0],) + self.shape[1:] + v_.shape[2:])
         if out is None:
             out = v_.new_full(self.shape + v_.shape[2:], float('nan'))
         if out.is_contiguous():
@@ -280,7 +293,11 @@ class SpinArray(_Obj):
     def extract(self, v: Tensor, *, out_: OptT = None) -> Tensor:
         r"""`(N,*Nd,...)` -> compact `(N,nM,...)`, row-major over `*Nd`."""
         tail = v.shape[self.ndim:]
-        chosen = v.reshape((v.shape[0], -1) + tail).index_select(1, self.midx)
+        if _mask_kernel_ok(v):
+            chosen = _ops.mask_copy_cuda(v.reshape(v.shape[0], self.minv.numel(), -1).contiguous(), self.midx, self.minv, False)
+            chosen = chosen.reshape((v.shape[0], self.nM) + tail)
+        else:
+            chosen = v.reshape((v.shape[0], -1) + tail).index_select(1, self.midx)
         if out_ is None:
             return chosen
         out_.copy_(chosen)

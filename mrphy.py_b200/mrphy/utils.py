@@ -1,7 +1,13 @@
 r"""MRphy utilities: indexing helpers, k-space/gradient/slew conversions, RF re-parametrisations,
 axis-angle rotation.  Same names and behaviour as ``/root/reference/mrphy/utils.py``; these are
-O(nT) waveform-sized torch expressions (not part of the CUDA hot path) and run on any device.
+O(nT) waveform-sized expressions.  The design-loop chain the optimiser differentiates through -- ``tρθ2rf`` /
+``lρθ2rf``, ``ts2s``, ``s2g`` -- runs as ONE CUDA launch per call (and one for its adjoint) when its
+tensors live on the GPU (``csrc/design_ops.cu``); ``ts2g`` and ``tρθts2rfgr`` fuse the whole chain into a single
+launch.  CPU tensors, and the rare cases the kernel does not cover (gradients w.r.t. ``rfmax``/``smax``/``dt``, dtype
+promotion, irregular broadcast shapes), evaluate the reference's torch expression, which is what these host utilities
+are upstream.
 """
+import os
 from numbers import Number
 from typing import Any, Tuple, Union
 
@@ -20,6 +26,71 @@ else:
 
 __all__ = ['ctrsub', 'g2k', 'g2s', 'k2g', 'rf_c2r', 'rf_r2c', 'rf2tρθ',
            'rfclamp', 's2g', 's2ts', 'sclamp', 'ts2s', 'tρθ2rf', 'uφrot']
+
+_FLOATS = (torch.float32, torch.float64)
+
+
+def _frozen(*ts) -> bool:
+    return not any(t is not None and t.requires_grad for t in ts)
+
+
+def _aux(x: Tensor, like: Tensor, rows: int, cols: int):
+    """A small constant (rfmax / smax) as a `(rows|1, cols|1)` tensor on ``like``'s device and dtype, or None when its
+    shape is not one the kernel broadcasts."""
+    from mrphy import _ops
+    v = _ops.on_device(x, like.device, like.dtype)
+    if v.ndim == 0:
+        v = v.reshape(1, 1)
+    elif v.ndim == 1:
+        v = v.reshape(-1, 1)                       # per pulse, like upstream's rfmax[:, None, None]
+    if v.ndim != 2 or v.shape[0] not in (1, rows) or v.shape[1] not in (1, cols):
+        return None
+    return v
+
+
+def _rf_half(ρ: Tensor, θ: Tensor, rfmax: Tensor):
+    """(ρ, θ, rfmax2) ready for the kernel, or None -> torch expression."""
+    if os.environ.get('MRPHY_B200_REPARAM') == 'torch':      # measurement switch (profiles/design_step.py)
+        return None
+    if not (ρ.is_cuda and θ.is_cuda and ρ.dtype in _FLOATS and θ.dtype == ρ.dtype and ρ.shape == θ.shape
+            and ρ.ndim in (3, 4) and ρ.shape[1] == 1 and ρ.numel() > 0 and _frozen(rfmax)):
+        return None
+    if rfmax.ndim > 0 and torch.result_type(ρ, rfmax) != ρ.dtype:
+        return None
+    if (rfmax.ndim == 2) != (ρ.ndim == 4) and rfmax.ndim > 0:   # upstream broadcasting needs (N,) with 3-D, (N,nCoils) with 4-D
+        return None
+    r = _aux(rfmax, ρ, ρ.shape[0], ρ.shape[3] if ρ.ndim == 4 else 1)
+    return None if r is None else (ρ.contiguous(), θ.contiguous(), r)
+
+
+def _gr_half(ts: Tensor, smax, dt):
+    """(ts, smax2, dt) ready for the kernel (smax / dt may be None when unused), or None -> torch expression."""
+    from mrphy import _ops
+    if os.environ.get('MRPHY_B200_REPARAM') == 'torch':
+        return None
+    if not (ts.is_cuda and ts.dtype in _FLOATS and ts.ndim == 3 and ts.shape[1] == 3 and ts.numel() > 0
+            and _frozen(smax, dt)):
+        return None
+    s2 = None
+    if smax is not None:
+        if smax.ndim > 0 and torch.result_type(ts, smax) != ts.dtype:
+            return None
+        if smax.ndim == 1:                       # smax[..., None] of a 1-D smax is per-axis (3,1) -> (1,3) here
+            if smax.shape[0] not in (1, 3):
+                return None
+            s2 = _ops.on_device(smax, ts.device, ts.dtype).reshape(1, -1)
+        else:
+            s2 = _aux(smax, ts, ts.shape[0], 3)
+        if s2 is None:
+            return None
+    d = None
+    if dt is not None:
+        if dt.numel() not in (1, ts.shape[0]) or (dt.ndim > 0 and torch.result_type(ts, dt) != ts.dtype):
+            return None
+        if dt.ndim > 1 and dt.shape[1:].numel() != 1:
+            return None
+        d = _ops.on_device(dt, ts.device)
+    return ts.contiguous(), s2, d
 
 
 def _tail(x: Tensor, ndim: int) -> Tensor:
@@ -64,6 +135,10 @@ def k2g(k: Tensor, isTx: bool, dt: Tensor = dt0, *, γ: Tensor = γH) -> Tensor:
 
 def s2g(s: Tensor, dt: Tensor = dt0) -> Tensor:
     r"""Slew rate `(N,xyz,nT)` -> gradient (running sum * dt)."""
+    h = _gr_half(s, None, dt)
+    if h is not None:
+        from mrphy import _ops
+        return _ops.design_waveform_cuda(None, None, None, h[0], None, h[2], 0, 2)[1]
     return _tail(dt, s.ndim) * torch.cumsum(s, dim=2)
 
 
@@ -73,11 +148,19 @@ def _unit(θ: Tensor) -> Tensor:
 
 def lρθ2rf(lρ: Tensor, θ: Tensor, rfmax: Tensor) -> Tensor:
     r"""logit(ρ/rfmax), θ `(N,1,nT,(nCoils))` -> rf `(N,xy,nT,(nCoils))`."""
+    h = _rf_half(lρ, θ, rfmax)
+    if h is not None:
+        from mrphy import _ops
+        return _ops.design_waveform_cuda(h[0], h[1], h[2], None, None, None, 2, 0)[0]
     return lρ.sigmoid() * _per_pulse(rfmax) * _unit(θ)
 
 
 def tρθ2rf(tρ: Tensor, θ: Tensor, rfmax: Tensor) -> Tensor:
     r"""tan(ρ/rfmax·π/2), θ `(N,1,nT,(nCoils))` -> rf `(N,xy,nT,(nCoils))`."""
+    h = _rf_half(tρ, θ, rfmax)
+    if h is not None:
+        from mrphy import _ops
+        return _ops.design_waveform_cuda(h[0], h[1], h[2], None, None, None, 1, 0)[0]
     return tρ.atan() / π * 2 * _per_pulse(rfmax) * _unit(θ)
 
 
@@ -108,7 +191,32 @@ def s2ts(s: Tensor, smax: Tensor) -> Tensor:
 
 def ts2s(ts: Tensor, smax: Tensor) -> Tensor:
     r"""tan(s/smax·π/2) -> slew `(N,xyz,nT)`."""
+    h = _gr_half(ts, smax, None)
+    if h is not None:
+        from mrphy import _ops
+        return _ops.design_waveform_cuda(None, None, None, h[0], h[1], None, 0, 3)[1]
     return ts.atan() / π * 2 * smax[..., None]
+
+
+def ts2g(ts: Tensor, smax: Tensor, dt: Tensor = dt0) -> Tensor:
+    r"""``s2g(ts2s(ts, smax), dt)`` in one launch (not in the reference; the chain every slew-constrained design runs)."""
+    h = _gr_half(ts, smax, dt)
+    if h is not None:
+        from mrphy import _ops
+        return _ops.design_waveform_cuda(None, None, None, h[0], h[1], h[2], 0, 1)[1]
+    return s2g(ts2s(ts, smax), dt)
+
+
+def tρθts2rfgr(tρ: Tensor, θ: Tensor, ts: Tensor, rfmax: Tensor, smax: Tensor, dt: Tensor = dt0, *,
+               logit: bool = False) -> Tuple[Tensor, Tensor]:
+    r"""The whole re-parametrisation of a design step, ``(tρθ2rf | lρθ2rf)(ρ, θ, rfmax)`` and
+    ``s2g(ts2s(ts, smax), dt)``, as ONE launch forward and ONE backward -> ``(rf, gr)``."""
+    hr, hg = _rf_half(tρ, θ, rfmax), _gr_half(ts, smax, dt)
+    if hr is not None and hg is not None and hr[0].dtype == hg[0].dtype and hr[0].shape[0] == hg[0].shape[0] \
+            and hr[0].shape[2] == hg[0].shape[2] and hr[0].device == hg[0].device:
+        from mrphy import _ops
+        return tuple(_ops.design_waveform_cuda(hr[0], hr[1], hr[2], hg[0], hg[1], hg[2], 2 if logit else 1, 1))
+    return (lρθ2rf if logit else tρθ2rf)(tρ, θ, rfmax), ts2g(ts, smax, dt)
 
 
 def sclamp(s: Tensor, smax: Tensor) -> Tensor:

@@ -19,6 +19,7 @@ Cases (see SURVEY.md section 8c for the reference tests they mirror):
   rand_nob1 random N=2, nM=5, nT=40, 3 coils summed, no b1Map, no df, per-batch dt
   bench8    8^3 cube, BASELINE.md workload distributions, nT=1000, fp32 and fp64
   freeprec  tests/test_slowsims.py:100-122 + random case
+  reparam   utils.tρθ2rf / lρθ2rf / ts2s / s2g with autograd gradients; SpinArray.embed / extract on a random mask
 """
 import os
 import sys
@@ -350,6 +351,40 @@ def case_freeprec():
          b_Mo=npy(Mor), b_gMi=npy(Mr.grad))
 
 
+def case_reparam():
+    from mrphy import utils
+    g = torch.Generator().manual_seed(77)
+    R = lambda *s: torch.randn(s, generator=g, dtype=f64)
+    out = {}
+    for tag, nC in (('sc', 0), ('mc', 3)):
+        N, nT = 2, 300
+        shp = (N, 1, nT) + ((nC,) if nC else ())
+        rho, theta, ts = (R(*shp) * 2).requires_grad_(True), (R(*shp) * 3).requires_grad_(True), (R(N, 3, nT) * 1.5).requires_grad_(True)
+        rfmax = torch.rand((N, nC) if nC else (N,), generator=g, dtype=f64) * 0.2 + 0.05
+        smax = torch.rand((N, 3), generator=g, dtype=f64) * 1e4 + 5e3
+        dt = torch.tensor([4e-6, 1e-5], dtype=f64)
+        wrf, wg = R(N, 2, *shp[2:]), R(N, 3, nT)
+        rf_t = utils.tρθ2rf(rho, theta, rfmax)
+        rf_l = utils.lρθ2rf(rho, theta, rfmax)
+        s = utils.ts2s(ts, smax)
+        gr = utils.s2g(s, dt)
+        grho_t, gtheta_t = torch.autograd.grad((rf_t * wrf).sum(), (rho, theta))
+        grho_l, gtheta_l = torch.autograd.grad((rf_l * wrf).sum(), (rho, theta))
+        gts, = torch.autograd.grad((gr * wg).sum(), (ts,))
+        gts_s, = torch.autograd.grad((utils.ts2s(ts, smax) * wg).sum(), (ts,))
+        loc = dict(rho=rho, theta=theta, ts=ts, rfmax=rfmax, smax=smax, dt=dt, wrf=wrf, wg=wg, rf_t=rf_t, rf_l=rf_l, s=s,
+                   gr=gr, grho_t=grho_t, gtheta_t=gtheta_t, grho_l=grho_l, gtheta_l=gtheta_l, gts=gts, gts_s=gts_s)
+        out.update({f'{tag}_{k}': npy(v) for k, v in loc.items()})
+    # mask plumbing: SpinArray.embed / extract (mobjs.py:512-553)
+    mask = torch.rand((1, 5, 4, 3), generator=g) > 0.4
+    sa = mobjs.SpinArray((2, 5, 4, 3), mask=mask, dtype=f64)
+    v_ = R(2, sa.nM, 3)
+    emb = sa.embed(v_)
+    full = R(2, 5, 4, 3, 2)
+    out.update(mask=npy(mask), mask_v_=npy(v_), mask_embedded=npy(emb), mask_full=npy(full), mask_extracted=npy(sa.extract(full)))
+    save('reparam', **out)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     case_kat3()
@@ -364,3 +399,4 @@ if __name__ == '__main__':
                                                   relax=False, per_spin=False, per_batch_dt=False, scale=5))
     case_bench8()
     case_freeprec()
+    case_reparam()

@@ -697,3 +697,101 @@ def test_all_fp32_kernel_variants_agree_with_oracle(dev, monkeypatch, pack, trig
     tol = 1e-5 if trig == 'precise' else 3e-5
     assert mx(Mo, ref['Mo']) < tol
     assert rel(grf, ref['grf']) < RTOL_G32 and rel(ggr, ref['ggr']) < RTOL_G32 and rel(gM0, ref['gM0']) < RTOL_G32
+
+
+# ---- re-parametrisation chain and mask plumbing as single launches -------------------------
+@pytest.mark.parametrize('tag', ['sc', 'mc'])
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_design_waveform_kernel_matches_reference(dev, golden, tag, dtype):
+    """utils.tρθ2rf / lρθ2rf / ts2s / s2g / ts2g / tρθts2rfgr on CUDA tensors (one launch each way, csrc/design_ops.cu)
+    against the unmodified reference's outputs and autograd gradients and against the numpy oracle.
+    Tolerance: fp64 1e-12 relative; fp32 2e-6 relative to the largest value (inputs rounded to fp32, arithmetic in
+    double with one final rounding; the fp32 running sum of the reference itself differs by ~1e-6)."""
+    from mrphy import utils, _cabi
+    from oracle import bloch_oracle as orc
+    g = {k[len(tag) + 1:]: v for k, v in golden('reparam').items() if k.startswith(tag + '_')}
+    tol = 1e-12 if dtype == f64 else 2e-6
+    t = {k: T(v, dev, dtype) for k, v in g.items()}
+    near = lambda a, b: mx(a, b) <= tol * float(np.abs(b).max())
+    rho, theta, ts = (t[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
+    n0 = _cabi.launch_counter
+    for kind, fn, logit in (('t', utils.tρθ2rf, False), ('l', utils.lρθ2rf, True)):
+        rf = fn(rho, theta, t['rfmax'])
+        assert rf.dtype == dtype and near(rf, g['rf_' + kind])
+        grho, gtheta = torch.autograd.grad((rf * t['wrf']).sum(), (rho, theta))
+        assert near(grho, g['grho_' + kind]) and near(gtheta, g['gtheta_' + kind])
+        o_rf = orc.reparam_fwd(rho.detach().cpu().numpy(), theta.detach().cpu().numpy(), t['rfmax'].cpu().numpy(),
+                               ts.detach().cpu().numpy(), t['smax'].cpu().numpy(), t['dt'].cpu().numpy(), logit=logit)[0]
+        assert mx(rf, o_rf) <= (1e-13 if dtype == f64 else 1e-7) * float(np.abs(o_rf).max())   # same (rounded) inputs
+    assert _cabi.launch_counter - n0 == 4          # two forwards + two adjoints, one launch each
+    s = utils.ts2s(ts, t['smax'])
+    gr = utils.s2g(s, t['dt'])
+    assert near(s, g['s']) and near(gr, g['gr'])
+    gts_s, = torch.autograd.grad((s * t['wg']).sum(), (ts,), retain_graph=True)
+    assert near(gts_s, g['gts_s'])
+    gts, = torch.autograd.grad((gr * t['wg']).sum(), (ts,))
+    assert near(gts, g['gts'])
+    assert near(utils.ts2g(ts, t['smax'], t['dt']), g['gr'])
+    n0 = _cabi.launch_counter
+    rf2, gr2 = utils.tρθts2rfgr(rho, theta, ts, t['rfmax'], t['smax'], t['dt'])
+    ((rf2 * t['wrf']).sum() + (gr2 * t['wg']).sum()).backward()
+    assert _cabi.launch_counter - n0 == 2          # the whole chain: ONE launch forward, ONE backward
+    assert near(rf2, g['rf_t']) and near(gr2, g['gr'])
+    assert near(rho.grad, g['grho_t']) and near(theta.grad, g['gtheta_t']) and near(ts.grad, g['gts'])
+
+
+def test_design_waveform_long_and_scalar_constants(dev):
+    """nT = 4001 (16 chunks of the running sum, ragged tail), scalar rfmax / smax / default fp64 dt0 like upstream's
+    defaults, against the torch expressions the reference is made of; and the cases the kernel leaves to torch."""
+    from mrphy import utils, dt0, rfmax0, smax0, π
+    gen = torch.Generator().manual_seed(5)
+    N, nT = 3, 4001
+    rho, theta, ts = (torch.randn((N, c, nT), generator=gen, dtype=f64).to(dev) for c in (1, 1, 3))
+    rf, gr = utils.tρθts2rfgr(rho, theta, ts, rfmax0, smax0)
+    rf_ref = rho.atan() / π * 2 * rfmax0.to(dev) * torch.cat((theta.cos(), theta.sin()), dim=1)
+    gr_ref = dt0.to(dev) * torch.cumsum(ts.atan() / π * 2 * smax0.to(dev), dim=2)
+    assert rel(rf, rf_ref) < 1e-14 and rel(gr, gr_ref) < 1e-13
+    # per-axis 1-D smax, per-pulse dt
+    smax = tensor([1e3, 2e3, 3e3], dtype=f64, device=dev)
+    dtn = tensor([4e-6, 2e-6, 1e-5], dtype=f64, device=dev)
+    g2 = utils.ts2g(ts, smax, dtn)
+    g2_ref = dtn[:, None, None] * torch.cumsum(ts.atan() / π * 2 * smax[..., None], dim=2)
+    assert rel(g2, g2_ref) < 1e-13
+    # gradients w.r.t. the constants are not the kernel's business: torch expression, same numbers
+    smax_g = smax.clone().requires_grad_(True)
+    s = utils.ts2s(ts, smax_g)
+    s.sum().backward()
+    assert smax_g.grad is not None and rel(s, ts.atan() / π * 2 * smax[..., None]) < 1e-15
+
+
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_mask_kernel_embed_extract(dev, golden, dtype):
+    """SpinArray.embed / extract through the one-pass gather kernel: bit-exact against the reference's outputs (NaN
+    pattern included) and differentiable (transposed map)."""
+    from mrphy import mobjs, _cabi
+    g = golden('reparam')
+    sa = mobjs.SpinArray((2, 5, 4, 3), mask=tensor(g['mask']).to(dev), dtype=dtype, device=dev)
+    v_ = T(g['mask_v_'], dev, dtype).requires_grad_(True)
+    n0 = _cabi.launch_counter
+    emb = sa.embed(v_)
+    assert _cabi.launch_counter == n0 + 1
+    want = tensor(g['mask_embedded']).to(dtype).numpy()
+    got = emb.detach().cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(want))
+    w = torch.randn(emb.shape, device=dev, dtype=dtype)
+    torch.nan_to_num(emb * w).sum().backward()
+    assert torch.equal(v_.grad, sa.extract(w))
+    full = T(g['mask_full'], dev, dtype).requires_grad_(True)
+    ex = sa.extract(full)
+    assert np.array_equal(ex.detach().cpu().numpy(), tensor(g['mask_extracted']).to(dtype).numpy())
+    w2 = torch.randn(ex.shape, device=dev, dtype=dtype)
+    (ex * w2).sum().backward()
+    assert torch.equal(full.grad, torch.nan_to_num(sa.embed(w2)))
+    # a full-size cube: 64^3 with a spherical mask, round trip
+    n = 64
+    ax = torch.arange(n, device=dev) - n // 2
+    mask = ((ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2) < (n // 2) ** 2)[None]
+    big = mobjs.SpinArray((1, n, n, n), mask=mask, dtype=dtype, device=dev)
+    m_ = torch.randn((1, big.nM, 3), device=dev, dtype=dtype)
+    e = big.embed(m_)
+    assert torch.equal(big.extract(e), m_) and bool(torch.isnan(e[~mask.expand(1, n, n, n)]).all())

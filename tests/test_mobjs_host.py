@@ -197,3 +197,34 @@ class TestUtils:
         s0 = utils.sclamp(smax0 * ((torch.rand((1, 3, 10)) - 0.5) * 4), smax0)
         assert torch.all(s0.abs() <= smax0)
         assert s0.numpy() == pytest.approx(utils.ts2s(utils.s2ts(s0, smax0), smax0).numpy(), abs=self.atol)
+
+
+@pytest.mark.parametrize('tag', ['sc', 'mc'])
+def test_reparam_utils_match_reference_on_cpu(golden, tag):
+    """tρθ2rf / lρθ2rf / ts2s / s2g (+ the fused conveniences) on CPU tensors against outputs and autograd gradients
+    of the unmodified reference (tests/golden/reparam.npz)."""
+    g = {k[len(tag) + 1:]: tensor(v) for k, v in golden('reparam').items() if k.startswith(tag + '_')}
+    rho, theta, ts = (g[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
+    for kind, fn in (('t', utils.tρθ2rf), ('l', utils.lρθ2rf)):
+        rf = fn(rho, theta, g['rfmax'])
+        assert torch.allclose(rf, g['rf_' + kind], rtol=0, atol=1e-14)
+        grho, gtheta = torch.autograd.grad((rf * g['wrf']).sum(), (rho, theta))
+        assert torch.allclose(grho, g['grho_' + kind], rtol=1e-12, atol=1e-15)
+        assert torch.allclose(gtheta, g['gtheta_' + kind], rtol=1e-12, atol=1e-15)
+    s = utils.ts2s(ts, g['smax'])
+    gr = utils.s2g(s, g['dt'])
+    assert torch.allclose(s, g['s'], rtol=1e-14, atol=0) and torch.allclose(gr, g['gr'], rtol=1e-13, atol=1e-15)
+    assert torch.allclose(utils.ts2g(ts, g['smax'], g['dt']), g['gr'], rtol=1e-13, atol=1e-15)
+    rf2, gr2 = utils.tρθts2rfgr(rho, theta, ts, g['rfmax'], g['smax'], g['dt'])
+    assert torch.allclose(rf2, g['rf_t'], rtol=0, atol=1e-14) and torch.allclose(gr2, g['gr'], rtol=1e-13, atol=1e-15)
+    gts, = torch.autograd.grad((gr2 * g['wg']).sum(), (ts,))
+    assert torch.allclose(gts, g['gts'], rtol=1e-12, atol=1e-18)
+
+
+def test_embed_extract_match_reference_on_cpu(golden):
+    g = golden('reparam')
+    sa = mobjs.SpinArray((2, 5, 4, 3), mask=tensor(g['mask']), dtype=f64)
+    emb = sa.embed(tensor(g['mask_v_'])).numpy()
+    assert np.array_equal(np.isnan(emb), np.isnan(g['mask_embedded']))
+    assert np.array_equal(np.nan_to_num(emb), np.nan_to_num(g['mask_embedded']))
+    assert np.array_equal(sa.extract(tensor(g['mask_full'])).numpy(), g['mask_extracted'])

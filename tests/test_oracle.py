@@ -112,3 +112,24 @@ def test_interp(golden):
     assert mx(orc.interp_linear(g['b_gr'], 4e-6, 2e-6), g['b_gr_new']) < 1e-12
     assert orc.interp_grid(40, 20e-6, 4e-6)[1].shape[0] == int(g['c_nT'][0]) == 200
     assert orc.interp_grid(40, float(np.float32(20e-6)), 4e-6)[1].shape[0] == int(g['c_nT'][1]) == 199
+
+
+@pytest.mark.parametrize('tag', ['sc', 'mc'])
+def test_reparam(golden, tag):
+    """utils.tρθ2rf / lρθ2rf / ts2s / s2g and their autograd, as the unmodified reference computes them."""
+    g = {k[len(tag) + 1:]: v for k, v in golden('reparam').items() if k.startswith(tag + '_')}
+    for kind, logit in (('t', False), ('l', True)):
+        rf, s, gr = orc.reparam_fwd(g['rho'], g['theta'], g['rfmax'], g['ts'], g['smax'], g['dt'], logit=logit)
+        assert rel(rf, g['rf_' + kind]) < 1e-14 and rel(s, g['s']) < 1e-14 and rel(gr, g['gr']) < 1e-13
+        grho, gtheta, gts = orc.reparam_adj(g['wrf'], g['wg'], g['rho'], g['theta'], g['rfmax'], g['ts'], g['smax'], g['dt'],
+                                            logit=logit)
+        assert rel(grho, g['grho_' + kind]) < 1e-13 and rel(gtheta, g['gtheta_' + kind]) < 1e-13
+        assert rel(gts, g['gts']) < 1e-13
+
+
+def test_mask_plumbing(golden):
+    g = golden('reparam')
+    emb = orc.mask_embed(g['mask_v_'], g['mask'])
+    assert np.array_equal(np.isnan(emb), np.isnan(g['mask_embedded']))
+    assert np.array_equal(np.nan_to_num(emb), np.nan_to_num(g['mask_embedded']))
+    assert np.array_equal(orc.mask_extract(g['mask_full'], g['mask']), g['mask_extracted'])
