@@ -33,7 +33,7 @@ constexpr int TCMAX = 64;   // max steps per staged waveform chunk (== max check
 
 #ifdef MRPHY_CTA_TRACE
 // measurement build only (profiles/cta_trace.py): per CTA of the backward kernel (SM id, start, end) in ns
-__device__ unsigned long long g_cta_trace[8192][3];
+__device__ unsigned long long g_cta_trace[8192][4];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -58,6 +58,10 @@ template <> struct Pack<float, 2> { typedef f2 type; };
 #endif
 #ifndef MRPHY_BWD_MINB
 #define MRPHY_BWD_MINB 8     // spin-packed backward: 128 registers, 8 CTAs (16 warps) per SM -- measured best of 6..10
+#endif
+#ifndef MRPHY_BWD_BLKT
+#define MRPHY_BWD_BLKT 128   // threads per CTA of the spin-packed backward: one warp on each SM sub-partition, so the four
+                             // schedulers of an SM always carry the same load (64-thread CTAs: 7 per SM = 4,4,3,3 warps)
 #endif
 constexpr int pick_tr(int W, int elem) {
   int tr = 16;
@@ -90,7 +94,26 @@ template <typename T> struct KArgs {
   const T* gMo; int64_t gMo_sn, gMo_sm;
   T* gMi;
   T* partials;
+  int* sched;          // SM-aware tile ownership of the backward (null: CTA b owns tiles b, b+P, ...), see SCHED_* below
+  int n_sm, c_per_sm;
 };
+
+// Scheduling workspace of the backward kernel (ints, zeroed before every launch; lives behind the partial sums).
+// The hardware spreads the P = c * n_sm co-resident CTAs breadth-first over the SMs, but not in blockIdx order (measured,
+// profiles/cta_trace.py): with tiles owned by blockIdx some SMs end up with one tile more than ceil(tiles / n_sm) and
+// the kernel waits for them.  Instead a CTA asks which SM it is on and which arrival it is there (rank), and serves the
+// VIRTUAL id rank * n_sm + smid: ids, their tiles and their partial-sum slot are static, so the result stays bitwise
+// reproducible whichever CTA serves an id.  Ids are claimed with a CAS, and a CTA that is done (or found no free home
+// id: an SM with more than c arrivals) sweeps for unclaimed ids, so every id is served exactly once whatever the
+// placement -- no waiting on other CTAs anywhere.
+constexpr int SCHED_SM_SLOTS = 256;                     // [0, 256): arrivals per SM
+constexpr int SCHED_NCLAIMED = 256;                     // [256]: ids claimed so far
+constexpr int SCHED_CLAIM = 264;                        // [264, 264 + P): claim flag per id
+__device__ __forceinline__ unsigned my_smid() {
+  unsigned s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
+}
 
 __device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
   const float4 q = *reinterpret_cast<const float4*>(p);
@@ -354,7 +377,7 @@ __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int la
 // ------------------------------------------------------------------------------------------
 // backward
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
-__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) == 8 && NC == 1 ? 4 : 1))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : (sizeof(T) == 8 && NC == 1 ? 4 : 1))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
   typedef typename Pack<T, PK>::type V;
   using L = BwdSmem<T, NC, BLKT>;
   constexpr int W = L::W, TR = L::TR, NW = L::NW;
@@ -369,29 +392,49 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
   const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
   const T* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
   const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);
-  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
-  T* part = a.partials + ((size_t)n * a.P + blockIdx.x) * W * (size_t)nT;
+#define NCTA ((int)gridDim.x)   /* constant-bank operand, not a register */
+  __shared__ int s_vid, s_sweep;
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     fence_barrier_init();
   }
+  // which virtual id does this CTA serve first (see SCHED_*)
+  int vid = blockIdx.x;
+  if (a.sched && tid == 0) {
+    int* const sched = a.sched;
+    s_sweep = 0;
+    const int s = (int)my_smid();
+    int v0 = -1;
+    if (s < a.n_sm && s < SCHED_SM_SLOTS) {
+      const int rank = atomicAdd(&sched[s], 1);
+      const int cand = rank * a.n_sm + s;
+      if (rank < a.c_per_sm && cand < NCTA && atomicCAS(&sched[SCHED_CLAIM + cand], 0, 1) == 0) {
+        v0 = cand;
+        atomicAdd(&sched[SCHED_NCLAIMED], 1);
+      }
+    }
+    s_vid = v0;
+  }
   __syncthreads();
-  if (tid == 0 && total > 0) {
-    mbar_arrive_expect_tx(&full[0], chunk_bytes);
-    bulk_g2s(wbuf[0], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[0]);
-  }
-  if (my_tiles == 0) {   // a CTA without work still owns a partial slot: zero it
-    for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
-    return;
-  }
+  if (a.sched) vid = s_vid;
 #ifdef MRPHY_CTA_TRACE
-  if (tid == 0 && blockIdx.x < 8192 && n == 0) { g_cta_trace[blockIdx.x][0] = smid(); g_cta_trace[blockIdx.x][1] = gtime(); }
+  if (tid == 0 && blockIdx.x < 8192 && n == 0) { g_cta_trace[blockIdx.x][0] = smid(); g_cta_trace[blockIdx.x][1] = gtime(); g_cta_trace[blockIdx.x][3] = (unsigned long long)(long long)vid; }
 #endif
   uint32_t it = 0, red_par = 0;
+  for (;;) {
+   if (vid >= 0) {
+    const int my_tiles = (vid < tiles) ? (tiles - vid + NCTA - 1) / NCTA : 0;
+    const uint32_t total = it + (uint32_t)my_tiles * (uint32_t)nChunks;   // `it` once this id's last chunk is consumed
+    T* part = a.partials + ((size_t)n * a.P + vid) * W * (size_t)nT;
+    if (my_tiles == 0) {   // an id without work still owns a partial slot: zero it
+      for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
+    } else if (tid == 0) {
+      mbar_arrive_expect_tx(&full[it & 1], chunk_bytes);
+      bulk_g2s(wbuf[it & 1], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[it & 1]);
+    }
   bool first = true;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
+  for (int tile = vid; tile < tiles; tile += NCTA, first = false) {
     SpinConst<V, NC> k;
     V mx, my, mz, hx, hy, hz;
     int idx[PK];
@@ -507,6 +550,30 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB : (sizeof(T) =
       }
     }
   }
+   }   // vid >= 0
+   if (!a.sched) break;
+   // done with this id: is any id still unclaimed (an SM that received fewer CTAs than planned)?  Normally one load.
+   __syncthreads();
+   if (tid == 0) {
+     int* const sched = a.sched;
+     int f = -1, sweep = s_sweep;
+     if (*(volatile int*)&sched[SCHED_NCLAIMED] < NCTA) {
+       for (; sweep < NCTA; ++sweep) {
+         if (*(volatile int*)&sched[SCHED_CLAIM + sweep] == 0 && atomicCAS(&sched[SCHED_CLAIM + sweep], 0, 1) == 0) {
+           f = sweep++;
+           atomicAdd(&sched[SCHED_NCLAIMED], 1);
+           break;
+         }
+       }
+     }
+     s_sweep = sweep;
+     s_vid = f;
+   }
+   __syncthreads();
+   vid = s_vid;
+   if (vid < 0) break;
+  }
+#undef NCTA
 #ifdef MRPHY_CTA_TRACE
   if (tid == 0 && blockIdx.x < 8192 && n == 0) g_cta_trace[blockIdx.x][2] = gtime();
 #endif
@@ -781,7 +848,7 @@ extern "C" float mrphy_last_kernel_ms(void) {
 
 #ifdef MRPHY_CTA_TRACE
 extern "C" int mrphy_debug_cta_trace(unsigned long long* host_out, int n_ctas) {
-  return cudaMemcpyFromSymbol(host_out, mrphy::g_cta_trace, sizeof(unsigned long long) * 3 * (size_t)n_ctas) == cudaSuccess ? 0 : -2;
+  return cudaMemcpyFromSymbol(host_out, mrphy::g_cta_trace, sizeof(unsigned long long) * 4 * (size_t)n_ctas) == cudaSuccess ? 0 : -2;
 }
 #endif
 extern "C" int mrphy_abi_version(void) { return MRPHY_ABI_VERSION; }
@@ -858,10 +925,16 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
 
 // CTAs per batch entry: all CTAs co-resident (one wave), c CTAs per SM chosen so that the tiles split
 // evenly -- minimise passes(c) * c over c in [occ/2, occ]; e.g. 64^3 spins on 148 SMs: c = 7, 2 passes.
-int pick_ctas(const Plan& p, int N, int occ) {
+int pick_ctas(const Plan& p, int N, int occ, bool sm_aware = false) {
   const int sms = sm_count_cached();
   occ = occ < 1 ? 1 : occ;
   const int forced = env_int("MRPHY_B200_CTAS_PER_SM", 0);
+  // With SM-aware tile ownership (backward, one batch entry) every SM serves ceil or floor(tiles / sms) tiles whatever
+  // c is, so take all the resident slots the tiles can fill.
+  if (sm_aware && N == 1 && !forced && p.tiles >= 2 * sms) {
+    const int c = p.tiles / sms < occ ? p.tiles / sms : occ;
+    return sms * c;
+  }
   int best_P = 1, best_cost = 1 << 30;
   for (int c = occ; c >= (occ + 1) / 2; --c) {
     if (forced) c = forced < occ ? forced : occ;
@@ -892,7 +965,7 @@ extern "C" size_t mrphy_fused_wave_elems(const mrphy_fused_args* a) {
 extern "C" size_t mrphy_fused_partial_elems(const mrphy_fused_args* a) {
   Plan p;
   if (make_plan(a, &p, true) != MRPHY_OK) return 0;
-  return (size_t)a->N * p.Pmax * p.W * (size_t)a->nT;
+  return (size_t)a->N * p.Pmax * p.W * (size_t)a->nT + (size_t)(SCHED_CLAIM + p.Pmax);   // + the scheduling ints
 }
 
 namespace {
@@ -921,6 +994,7 @@ KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
   k.Mo = (T*)a->Mo; k.ckpt = (T*)a->ckpt; k.wave = (const T*)a->wave;
   k.gMo = (const T*)a->gMo; k.gMo_sn = a->gMo_sn; k.gMo_sm = a->gMo_sm;
   k.gMi = (T*)a->gMi; k.partials = (T*)a->partials;
+  k.sched = nullptr; k.n_sm = 0; k.c_per_sm = 0;
   return k;
 }
 
@@ -961,12 +1035,24 @@ int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
-  k.P = pick_ctas(p, k.N, occ);
+  Plan q = p;   // the backward may use larger CTAs than the forward the plan was sized for: fewer, larger tiles
+  q.tiles = (k.nM + BLKT * PK - 1) / (BLKT * PK);
+  if (q.Pmax > q.tiles) q.Pmax = q.tiles;
+  const bool sm_aware = env_int("MRPHY_B200_SCHED", 1) != 2;
+  k.P = pick_ctas(q, k.N, occ, sm_aware);
   g_last_P = k.P;
   dim3 grid(k.P, k.N);
+  // SM-aware tile ownership when the grid is exactly c CTAs on each SM of one batch entry (see SCHED_*)
+  const int sms = sm_count_cached();
+  if (k.N == 1 && k.P % sms == 0 && k.P > sms && sms <= SCHED_SM_SLOTS && sm_aware) {
+    k.sched = reinterpret_cast<int*>(k.partials + (size_t)k.N * p.Pmax * p.W * (size_t)k.nT);
+    k.n_sm = sms;
+    k.c_per_sm = k.P / sms;
+    CK(cudaMemsetAsync(k.sched, 0, sizeof(int) * (size_t)(SCHED_CLAIM + k.P), st));
+  }
   if (getenv("MRPHY_B200_DEBUG"))
     fprintf(stderr, "[mrphy_b200] fused_bwd<%s,NC=%d,PK=%d,BLK=%d,%s> grid=(%d,%d) tiles=%d occ=%d smem=%zu K=%d\n",
-            sizeof(T) == 4 ? "f32" : "f64", NC, PK, BLKT, POL == TRIG_PRECISE ? "precise" : "fast", k.P, k.N, p.tiles, occ,
+            sizeof(T) == 4 ? "f32" : "f64", NC, PK, BLKT, POL == TRIG_PRECISE ? "precise" : "fast", k.P, k.N, q.tiles, occ,
             smem, p.K);
   timing_begin(st);
   kern<<<grid, BLKT, smem, st>>>(k, need_gmi);
@@ -1012,7 +1098,9 @@ template <typename T, int POL, bool RELAX>
 int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
   if constexpr (sizeof(T) == 4) {
     if (p.PK == 3) return launch_tp<POL, RELAX, 128>(bwd, k, p, need_gmi, st);
-    if (p.PK == 2) return launch_any<T, POL, RELAX, 1, 2, 64>(bwd, k, p, need_gmi, st);
+    if (p.PK == 2)
+      return bwd ? launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT>(k, p, need_gmi, st)
+                 : launch_fwd_s<T, POL, RELAX, 1, 2, 64>(k, p, st);
   }
   switch (p.NC) {
     case 1: return launch_any<T, POL, RELAX, 1, 1, 128>(bwd, k, p, need_gmi, st);

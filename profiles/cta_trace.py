@@ -23,9 +23,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 L = ctypes.CDLL(_cabi.LIB_PATH)
 P = 8192
-buf = (ctypes.c_ulonglong * (3 * P))()
+buf = (ctypes.c_ulonglong * (4 * P))()
 assert L.mrphy_debug_cta_trace(buf, P) == 0
-a = np.frombuffer(buf, dtype=np.uint64).reshape(P, 3).astype(np.int64)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(P, 4).astype(np.int64)
 a = a[a[:, 2] > 0]
 t0 = a[:, 1].min()
 start, end = (a[:, 1] - t0) / 1e3, (a[:, 2] - t0) / 1e3
@@ -40,3 +40,16 @@ by = collections.defaultdict(list)
 for smi, du in zip(a[:, 0].tolist(), dur.tolist()):
     by[per_sm[smi]].append(du)
 print('mean CTA duration by CTAs-per-SM:', {k: round(float(np.mean(v)), 1) for k, v in sorted(by.items())})
+# tiles per SM under the static assignment (CTA b takes tiles b, b+P, ...): the per-SM load the kernel time follows
+blkt = int(os.environ.get('TRACE_BLKT', '64'))
+tiles = (d['loc'].shape[1] + 2 * blkt - 1) // (2 * blkt)
+P_ = len(a)
+ids = np.nonzero(np.frombuffer(buf, dtype=np.uint64).reshape(P, 4)[:, 2] > 0)[0]
+vids = a[:, 3]   # virtual id served first (== blockIdx without the SM-aware ownership)
+per_cta = np.array([(tiles - b + P_ - 1) // P_ if 0 <= b < tiles else 0 for b in vids])
+load = collections.Counter()
+for smi, t in zip(a[:, 0].tolist(), per_cta.tolist()):
+    load[smi] += t
+print('tiles', tiles, 'CTAs', P_, 'tiles per SM histogram', sorted(collections.Counter(load.values()).items()))
+order = np.argsort(ids)
+print('SM of the first 16 CTAs', a[order[:16], 0].tolist(), '... CTAs 148..156', a[order[148:156], 0].tolist())

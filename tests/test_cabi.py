@@ -44,7 +44,7 @@ def test_abi_version_and_struct_layout(cabi):
     assert ctypes.sizeof(cabi.BeffArgs) == 6 * 4 + 8 * 3 + 8 * 4 + 32 * 4 + 8 * 2 + 8 * 3 + 8 * 2
     # ... and the C side agrees with every ctypes mirror (the loader checks the same and refuses a mismatch)
     for which, cls in enumerate((cabi.Param, cabi.FusedArgs, cabi.BeffArgs, cabi.RfGr2BeffArgs, cabi.Beff2abArgs,
-                                 cabi.Beff2uphiArgs, cabi.FreePrecArgs)):
+                                 cabi.Beff2uphiArgs, cabi.FreePrecArgs, cabi.ReparamArgs, cabi.MaskArgs)):
         assert L.mrphy_sizeof_args(which) == ctypes.sizeof(cls), cls.__name__
     assert L.mrphy_sizeof_args(99) == 0
 
@@ -56,7 +56,8 @@ def test_sizing_entry_points(cabi):
     a.b1 = 1  # non-null: per-coil path
     assert L.mrphy_fused_ckpt_elems(a) == 2 * 15 * 3 * 1000          # ceil(1000/64)-1 = 15 checkpoints
     assert L.mrphy_fused_wave_elems(a) == 2 * 16 * 5 * 64
-    assert L.mrphy_fused_partial_elems(a) == 2 * 8 * 5 * 1000        # ceil(1000/128) = 8 CTAs per batch
+    # ceil(1000/128) = 8 CTAs per batch entry, plus the backward's scheduling ints (264 + 8) behind the partial sums
+    assert L.mrphy_fused_partial_elems(a) == 2 * 8 * 5 * 1000 + 264 + 8
     a.K = 0
     assert L.mrphy_fused_ckpt_elems(a) == 0 and b'K must be' in L.mrphy_last_error()
 
