@@ -26,6 +26,14 @@ WANT = [
     'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__cycles_elapsed.avg.per_second', 'sm__cycles_active.avg',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
     'gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+    'smsp__warps_active.avg.per_cycle_active', 'smsp__warps_eligible.avg.per_cycle_active',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
 ]
 TAGS = (('fused_bwd', 'bwd'), ('fused_fwd', 'fwd'), ('grad_finalize', 'finalize'), ('pack_waveform', 'pack'),
         ('rfgr2beff_bwd', 'rfgr2beff_bwd'), ('rfgr2beff', 'rfgr2beff'), ('beff_v2', 'beff'))
