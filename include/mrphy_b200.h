@@ -43,7 +43,8 @@ enum mrphy_flags {
   MRPHY_TRIG_PRECISE = 1 << 0, /* fp32 only: Newton rsqrt + polynomial sincos instead of MUFU   */
   MRPHY_NEED_GMI = 1 << 1,     /* backward: also write dL/dMi                                   */
   MRPHY_RF_COIL_DIM = 1 << 2,  /* rf (and its gradient) carry the trailing nCoils dimension     */
-  MRPHY_NEED_GBEFF = 1 << 3    /* explicit-field backward: also write dL/dBeff                  */
+  MRPHY_NEED_GBEFF = 1 << 3,   /* explicit-field backward: also write dL/dBeff                  */
+  MRPHY_TRIG_FAST_BWD = 1 << 4 /* with MRPHY_TRIG_PRECISE: the BACKWARD kernel uses MUFU trigonometry (M unchanged) */
 };
 
 /* A strided per-spin scalar: element (n, i) lives at ptr[n*sn + i*sm]; f64 selects the type. */

@@ -1116,7 +1116,7 @@ template <typename T>
 int dispatch(bool bwd, const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
   const KArgs<T> k = make_kargs<T>(a, p);
   const bool relax = a->T1.ptr != nullptr;
-  const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0 && sizeof(T) == 4;
+  const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0 && sizeof(T) == 4 && !(bwd && (a->flags & MRPHY_TRIG_FAST_BWD));
   const int need_gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0;
   if (precise) {
     return relax ? dispatch_nc<T, TRIG_PRECISE, true>(bwd, k, p, need_gmi, st)

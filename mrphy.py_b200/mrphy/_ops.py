@@ -658,7 +658,10 @@ def default_flags() -> int:
     """fp32 trigonometry policy.  Default 'precise' (Newton-refined rsqrt + polynomial sincos on the FMA pipe):
     on the reference's own fixtures it is ~0.6x the reference's fp32 error, whereas raw MUFU.SIN/COS
     ('fast', MRPHY_B200_TRIG=fast) doubles it at nT~1000.  Ignored for fp64."""
-    return 0 if os.environ.get('MRPHY_B200_TRIG', 'precise') == 'fast' else _cabi.FLAG_TRIG_PRECISE
+    pol = os.environ.get('MRPHY_B200_TRIG', 'precise')
+    if pol == 'mixed':      # precise forward (M as in 'precise'), MUFU trigonometry in the adjoint kernel only
+        return _cabi.FLAG_TRIG_PRECISE | _cabi.FLAG_TRIG_FAST_BWD
+    return 0 if pol == 'fast' else _cabi.FLAG_TRIG_PRECISE
 
 
 def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: Optional[Tensor] = None,
