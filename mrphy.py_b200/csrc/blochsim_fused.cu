@@ -925,7 +925,7 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
 
 // CTAs per batch entry: all CTAs co-resident (one wave), c CTAs per SM chosen so that the tiles split
 // evenly -- minimise passes(c) * c over c in [occ/2, occ]; e.g. 64^3 spins on 148 SMs: c = 7, 2 passes.
-int pick_ctas(const Plan& p, int N, int occ, bool sm_aware = false) {
+int pick_ctas(const Plan& p, int N, int occ, bool sm_aware = false, int warps_per_cta = 4) {
   const int sms = sm_count_cached();
   occ = occ < 1 ? 1 : occ;
   const int forced = env_int("MRPHY_B200_CTAS_PER_SM", 0);
@@ -938,6 +938,9 @@ int pick_ctas(const Plan& p, int N, int occ, bool sm_aware = false) {
   int best_P = 1, best_cost = 1 << 30;
   for (int c = occ; c >= (occ + 1) / 2; --c) {
     if (forced) c = forced < occ ? forced : occ;
+    // the four schedulers of an SM must carry the same number of warps (the kernels are throughput-bound per scheduler:
+    // 11 two-warp CTAs = 6,6,5,5 warps cost 9 % at C4): skip CTA counts that do not fill them evenly
+    if (!forced && (c * warps_per_cta) % 4 != 0 && c > 1 && occ > 2) continue;
     int P = (int)((int64_t)sms * c / N);
     if (P < 1) P = 1;
     if (P > p.Pmax) P = p.Pmax;
@@ -1019,7 +1022,7 @@ int launch_fwd_s(KArgs<T> k, const Plan& p, cudaStream_t st) {
   auto kern = fused_fwd_kernel<T, POL, RELAX, NC, PK, BLKT>;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, 0));
-  k.P = pick_ctas(p, k.N, occ);
+  k.P = pick_ctas(p, k.N, occ, false, BLKT / 32);
   dim3 grid(k.P, k.N);
   timing_begin(st);
   kern<<<grid, BLKT, 0, st>>>(k);
@@ -1039,7 +1042,7 @@ int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   q.tiles = (k.nM + BLKT * PK - 1) / (BLKT * PK);
   if (q.Pmax > q.tiles) q.Pmax = q.tiles;
   const bool sm_aware = env_int("MRPHY_B200_SCHED", 1) != 2;
-  k.P = pick_ctas(q, k.N, occ, sm_aware);
+  k.P = pick_ctas(q, k.N, occ, sm_aware, BLKT / 32);
   g_last_P = k.P;
   dim3 grid(k.P, k.N);
   // SM-aware tile ownership when the grid is exactly c CTAs on each SM of one batch entry (see SCHED_*)
