@@ -623,34 +623,65 @@ def _root(t: Tensor) -> Tensor:
     return t._base if t._base is not None else t
 
 
+_host_max = {}
+
+
+def note_host_max(t: Tensor, value: float) -> None:
+    """Remember max(t) for a small device tensor whose value was known on the host when it was made (a Pulse's ``dt`` built
+    from a CPU scalar): `pick_ckpt_interval` then needs no device->host read for it."""
+    r = _root(t)
+    if len(_host_max) > 1024:
+        _host_max.clear()
+    _host_max[id(r)] = (weakref.ref(r), r._version, float(value))
+
+
+def _cached_max(t: Tensor) -> float:
+    """max(t) on the host: from `note_host_max`, else ONE device->host read, cached per tensor object and version."""
+    r = _root(t)
+    hit = _host_max.get(id(r))
+    if hit is not None and hit[0]() is r and hit[1] == r._version and t.numel() == r.numel():
+        return hit[2]
+    with torch.no_grad():
+        v = float(t.max().double().item())
+    if t.numel() == r.numel():
+        note_host_max(t, v)
+    return v
+
+
+def _cached_tmin(T1: Tensor, T2: Tensor) -> float:
+    """min(T1, T2) on the host, one read per (T1, T2) tensor objects and in-place versions."""
+    roots = (_root(T1), _root(T2))
+    key = tuple(id(r) for r in roots) + tuple(tuple(x.shape) + tuple(x.stride()) + (x.storage_offset(),) for x in (T1, T2))
+    hit = _ratio_cache.get(key)
+    if hit is not None:
+        refs, vers, v = hit
+        if all(w() is r for w, r in zip(refs, roots)) and vers == tuple(r._version for r in roots):
+            return v
+    with torch.no_grad():
+        v = float(torch.minimum(_collapse(T1).min(), _collapse(T2).min()).double().item())
+    if len(_ratio_cache) > 256:
+        _ratio_cache.clear()
+    _ratio_cache[key] = (tuple(weakref.ref(r) for r in roots), tuple(r._version for r in roots), v)
+    return v
+
+
 def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -> int:
     """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at K_MAX.
 
-    Needs max(dt)/min(T) on the host: one device->host read, then cached per (dt, T1, T2) tensor OBJECT and
-    in-place version (weak references guard against id reuse), so a design loop that keeps its SpinCube / Pulse
-    stays asynchronous.  MRPHY_B200_CKPT overrides."""
+    Needs max(dt) and min(T1, T2) on the host.  Both are cached per tensor OBJECT and in-place version (weak references
+    guard against id reuse) and SEPARATELY: the spin object keeps its T1/T2 across a design loop, while every iteration
+    builds a new Pulse -- whose ``dt`` normally comes from a host scalar and is registered by `note_host_max` -- so the
+    loop stays free of device->host reads.  MRPHY_B200_CKPT overrides."""
     env = os.environ.get('MRPHY_B200_CKPT')
     if env:
         return max(1, min(K_MAX, int(env)))
     if T1 is None:
         return K_MAX
-    roots = tuple(_root(x) for x in (dt, T1, T2))
-    key = tuple(id(r) for r in roots) + tuple(tuple(x.shape) + tuple(x.stride()) + (x.storage_offset(),)
-                                              for x in (dt, T1, T2))
-    hit = _ratio_cache.get(key)
-    if hit is not None:
-        refs, vers, K = hit
-        if all(w() is r for w, r in zip(refs, roots)) and vers == tuple(r._version for r in roots):
-            return K
-    with torch.no_grad():
-        tmin = torch.minimum(_collapse(T1).min(), _collapse(T2).min()).double()
-        r = float((dt.max().double() / tmin).item())
+    tmin = _cached_tmin(T1, T2)
+    r = _cached_max(dt) / tmin if tmin > 0 else float('nan')
     K = K_MAX if not (r > 0) else int(max(1, min(K_MAX, _AMPLIFY_BUDGET / r)))
     if K >= 16:
         K -= K % 16
-    if len(_ratio_cache) > 256:
-        _ratio_cache.clear()
-    _ratio_cache[key] = (tuple(weakref.ref(r) for r in roots), tuple(r._version for r in roots), K)
     return K
 
 

@@ -130,6 +130,9 @@ class Pulse(_Obj):
         elif name == 'dt':
             t = t.reshape(1) if t.ndim == 0 else t
             assert t.ndim == 1
+            if t.is_cuda and (not isinstance(value, Tensor) or (value.device.type == 'cpu' and not value.requires_grad)):
+                # the value is known here without a device->host read: the checkpoint policy wants max(dt) on the host
+                _ops.note_host_max(t, float(torch.as_tensor(value).to(self.dtype).max()))
         elif name == 'rfmax':
             if t.ndim == 0:
                 t = t.reshape(1)

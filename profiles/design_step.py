@@ -18,7 +18,7 @@ rfmax0, smax0, dt0 = rfmax0.to(**kw), smax0.to(**kw), dt0.to(**kw)   # the torch
 
 def iteration(mode, sp, d, v, tgt):
     tρ, θ, ts = v
-    if mode == 'fused':
+    if mode.startswith('fused'):
         rf, gr = utils.tρθts2rfgr(tρ, θ, ts, rfmax0, smax0, dt0)
     else:
         rf = utils.tρθ2rf(tρ, θ, rfmax0)
@@ -47,23 +47,29 @@ for n, nT in ((16, 256), (32, 512), (64, 1000)):
     g = torch.Generator(device='cuda').manual_seed(1)
     v = [torch.randn((1, c, nT), generator=g, **kw).mul_(0.3).requires_grad_(True) for c in (1, 1, 3)]
     ref = None
-    for mode in ('torch', 'per-function', 'fused'):
+    for mode in ('torch', 'per-function', 'fused', 'fused+graph'):
         os.environ['MRPHY_B200_REPARAM'] = 'torch' if mode == 'torch' else 'cuda'
         for _ in range(5):
             iteration(mode, sp, d, v, tgt)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = 50 if n < 64 else 20
+        run = lambda: iteration(mode, sp, d, v, tgt)
+        if mode == 'fused+graph':           # the whole iteration as one CUDA graph (it is free of host synchronisation)
+            from mrphy import graphs
+            loss = None
+            cap = graphs.capture(run, params=v)
+            run = cap.replay
         e0.record()
         for _ in range(K):
-            loss = iteration(mode, sp, d, v, tgt)
+            loss = run()
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
         grads = torch.cat([x.grad.reshape(-1) for x in v])
         if ref is None:
             ref = grads.clone()
         try:
-            nk = count_kernels(lambda: iteration(mode, sp, d, v, tgt))
+            nk = count_kernels(run)
         except Exception as ex:   # profiler unavailable: report time only
             nk = f'n/a ({type(ex).__name__})'
         print(f'{n}^3 x {nT}: {mode:13s} {ms:7.3f} ms/iteration  kernels/iteration {nk}  loss {float(loss):.6e}  '

@@ -797,3 +797,53 @@ def test_mask_kernel_embed_extract(dev, golden, dtype):
     m_ = torch.randn((1, big.nM, 3), device=dev, dtype=dtype)
     e = big.embed(m_)
     assert torch.equal(big.extract(e), m_) and bool(torch.isnan(e[~mask.expand(1, n, n, n)]).all())
+
+
+def test_design_loop_with_fresh_pulses_has_no_host_sync(dev):
+    """Every design iteration builds a NEW Pulse from the optimiser's variables (so `dt` is a new device tensor each time):
+    after the first iteration nothing on the path may read the device (checkpoint policy, mask indices, constants) --
+    `torch.cuda.set_sync_debug_mode('error')` turns any synchronising call into an exception."""
+    from mrphy import mobjs, utils, rfmax0, smax0
+    kw = {'dtype': f32, 'device': dev}
+    n, nT = 12, 96
+    gen = torch.Generator().manual_seed(3)
+    ax = torch.arange(n) - n // 2
+    mask = ((ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2) < (n // 2) ** 2)[None].to(dev)
+    cube = mobjs.SpinCube((1, n, n, n), tensor([[24., 24., 24.]]), mask=mask, **kw)
+    v = [(torch.randn((1, c, nT), generator=gen) * 0.3).to(**kw).requires_grad_(True) for c in (1, 1, 3)]
+    tgt = tensor([0., 1., 0.], **kw)
+
+    def iteration():
+        rf, gr = utils.tρθts2rfgr(v[0], v[1], v[2], rfmax0, smax0)
+        M = cube.applypulse(mobjs.Pulse(rf=rf, gr=gr, **kw), doEmbed=True)
+        loss = ((cube.extract(M) - tgt) ** 2).sum()
+        for x in v:
+            x.grad = None
+        loss.backward()
+        return loss
+
+    first = iteration()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode('error')
+    try:
+        for _ in range(3):
+            again = iteration()
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert torch.equal(first, again) and all(x.grad is not None and bool(torch.isfinite(x.grad).all()) for x in v)
+    # ... which is what lets the WHOLE iteration (re-parametrisation, fresh Pulse, mask kernels, simulation, adjoint) record
+    # into one CUDA graph; a replay after an in-place update of the variables equals the eager iteration bit for bit
+    from mrphy import graphs
+    eager_grads = [x.grad.clone() for x in v]
+    del first, again
+    captured = graphs.capture(iteration, params=v)
+    captured.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(x.grad, g) for x, g in zip(v, eager_grads))
+    with torch.no_grad():
+        for x in v:
+            x.mul_(0.9)
+    captured.replay()
+    replayed = [x.grad.clone() for x in v]
+    iteration()
+    assert all(torch.equal(x.grad, g) for x, g in zip(v, replayed))
