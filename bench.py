@@ -363,6 +363,23 @@ def run_ours(args):
                 traffic = (m['dram__bytes_read.sum']['value'] + m['dram__bytes_write.sum']['value']) * 1e6
         except Exception:
             traffic = None
+        operand = None
+        try:   # the bound that actually binds these kernels: register-operand bandwidth, static SASS model
+            if args.dtype == 'f32':
+                with open(os.path.join(ROOT, 'profiles', 'r1_operand_model.json')) as f:
+                    om = json.load(f)
+                clk = sm_mhz * 1e6
+                lanes = 148 * 4 * 32
+                meas = lambda ms: ms * 1e-3 * clk * lanes / (per_launch / 2)        # cycles per thread-step (2 spins/thread)
+                mf, mb = om['fwd']['model_cycles_per_thread_step'], om['bwd']['model_cycles_per_thread_step'] + 25.0
+                operand = {'what': 'cycles per thread-step (two spins) of one SM sub-partition: static register-operand-'
+                                   'bandwidth model of the SASS main loops (+25 for the backward spin reduction) vs measured',
+                           'fwd': {'model': mf, 'measured': meas(ms_f), 'frac': mf / meas(ms_f)},
+                           'bwd': {'model': mb, 'measured': meas(ms_b), 'frac': mb / meas(ms_b)},
+                           'fwd_bwd_frac': (mf + mb) / (meas(ms_f) + meas(ms_b)),
+                           'source': 'profiles/r1_operand_model.json, profiles/ubench_ffma2_operands.txt'}
+        except Exception:
+            operand = None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
@@ -381,6 +398,7 @@ def run_ours(args):
                          'peak_source': f'148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({src} {sm_mhz:.0f} MHz); the path '
                                         'is FP32-issue-bound (SURVEY 8d), not HBM- or tensor-bound',
                          'ms_per_launch': ms_b, 'algorithmic_flop_per_spin_step': FLOP_BWD,
+                         'register_operand_bound': operand,
                          'fwd_kernel': {'ms_per_launch': ms_f, 'achieved': per_launch * FLOP_FWD / (ms_f * 1e-3) / 1e12,
                                         'frac': per_launch * FLOP_FWD / (ms_f * 1e-3) / 1e12 / peak_tf},
                          'fwd_bwd_frac_of_issue_roofline': value / world / (148 * 128 * sm_mhz * 1e6 / 151.0),
