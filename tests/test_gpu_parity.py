@@ -283,15 +283,17 @@ def test_bitwise_reproducible_gradients(dev):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+@pytest.mark.parametrize('cfg', ['c2', 'c3'])
 @pytest.mark.parametrize('dtype', [f32, f64])
-def test_full_size_properties_c2(dev, dtype):
-    """BASELINE config C2 (64^3 spins, nT=1000): properties that do not need the reference at this size.
+def test_full_size_properties_c2(dev, dtype, cfg):
+    """BASELINE configs C2 (64^3 spins, nT=1000) and C3 (128^3, nT=2000): properties that do not need the reference at
+    these sizes (the reference would need 13.6 GB / 218 GB).
     (1) a random subset of spins matches the oracle; (2) without relaxation |M| is preserved;
     (3) rf/gr gradients match the oracle-summed contribution of that subset when the other spins get zero
     upstream gradient; (4) finite-difference check of one rf sample (fp64)."""
     from mrphy import mobjs, _ops
     from oracle import bloch_oracle as orc
-    n, nT = 64, 1000
+    n, nT = (64, 1000) if cfg == 'c2' else (128, 2000)
     kw = {'dtype': dtype, 'device': dev}
     gen = torch.Generator().manual_seed(0)
     U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
@@ -315,12 +317,13 @@ def test_full_size_properties_c2(dev, dtype):
                                  gamma=float(np.float32(4257.6)) if dtype == f32 else 4257.6,
                                  dt=float(np.float32(4e-6)) if dtype == f32 else 4e-6)
     tolM, tolG = (ATOL64, RTOL_G64) if dtype == f64 else (5e-5, RTOL_G32)
-    print(f'[C2 {dtype}] max|dM|={mx(Mo[:, sub.to(dev)], ref["Mo"]):.2e} grf rel={rel(p.rf.grad, ref["grf"]):.2e} '
+    print(f'[{cfg.upper()} {dtype}] max|dM|={mx(Mo[:, sub.to(dev)], ref["Mo"]):.2e} grf rel={rel(p.rf.grad, ref["grf"]):.2e} '
           f'ggr rel={rel(p.gr.grad, ref["ggr"]):.2e}')
     assert mx(Mo[:, sub.to(dev)], ref['Mo']) < tolM
     assert rel(p.rf.grad, ref['grf']) < tolG and rel(p.gr.grad, ref['ggr']) < tolG
     Mn = cube.applypulse(p, b1Map_=b1.to(dev), doRelax=False).detach()
-    assert float((Mn.norm(dim=-1) - 1).abs().max()) < (1e-12 if dtype == f64 else 2e-5)
+    # fp32 rounding of the state lets |M| drift by ~2e-8 per step (measured 1.3e-5 at nT=1000, 2.6e-5 at nT=2000)
+    assert float((Mn.norm(dim=-1) - 1).abs().max()) < (1e-12 if dtype == f64 else 2e-5 * nT / 1000)
     if dtype == f64:
         eps, t0 = 1e-6, 417
         f = lambda r: float((cube.applypulse(mobjs.Pulse(rf=r, gr=gr.to(dev), **kw), b1Map_=b1.to(dev)).detach()
