@@ -1100,11 +1100,16 @@ int launch_tp(bool bwd, KArgs<float> k, const Plan& p, int need_gmi, cudaStream_
 template <typename T, int POL, bool RELAX>
 int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
   if constexpr (sizeof(T) == 4) {
+#ifndef MRPHY_ONLY_PK2
     if (p.PK == 3) return launch_tp<POL, RELAX, 128>(bwd, k, p, need_gmi, st);
+#endif
     if (p.PK == 2)
       return bwd ? launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT>(k, p, need_gmi, st)
                  : launch_fwd_s<T, POL, RELAX, 1, 2, 64>(k, p, st);
   }
+#ifdef MRPHY_ONLY_PK2   /* tuning builds (profiles/operand_model.py): compile the default fp32 kernels only */
+  return fail(MRPHY_ERR_ARG, "built with MRPHY_ONLY_PK2%s");
+#else
   switch (p.NC) {
     case 1: return launch_any<T, POL, RELAX, 1, 1, 128>(bwd, k, p, need_gmi, st);
     case 2: return launch_any<T, POL, RELAX, 2, 1, 128>(bwd, k, p, need_gmi, st);
@@ -1113,6 +1118,7 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
     case 16: return launch_any<T, POL, RELAX, 16, 1, 128>(bwd, k, p, need_gmi, st);
   }
   return fail(MRPHY_ERR_ARG, "internal: bad NC%s");
+#endif
 }
 
 template <typename T>
