@@ -160,9 +160,10 @@ template <> struct Fn<float, TRIG_FAST> {
   }
 };
 
-// Cody-Waite reduction by pi/2 with the round-to-nearest-via-magic-constant trick (valid for
-// 0 <= x < 2^22 * pi/2; two reduction terms are exact to < 1e-8 rad for x < ~1e4 rad), then the
-// minimax sin/cos polynomials on [-pi/4, pi/4].  ~21 FP32-pipe/ALU instructions, no XU, no branches.
+// Cody-Waite reduction with the round-to-nearest-via-magic-constant trick (two-term constant: exact to < 1e-8 rad
+// for x < ~1e4 rad), then minimax sin/cos polynomials and a bit-level fix-up; no XU, no branches.  Shipped form
+// (MRPHY_SC_MODPI, below): reduce by pi, polynomials on [-pi/2, pi/2], both results flip sign with the parity of the
+// multiple.  -DMRPHY_SC_MODPI=0 is the earlier form: reduce by pi/2, polynomials on [-pi/4, pi/4], swap + signs.
 #define MRPHY_SC_MAGIC 12582912.0f   /* 1.5 * 2^23 */
 #ifndef MRPHY_PRECISE_NEWTON
 #define MRPHY_PRECISE_NEWTON 1
