@@ -138,8 +138,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / debug output goes to stderr instead
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            del os.environ['NCCL_DEBUG']          # the banner ignores NCCL_DEBUG_FILE (checked: profiles/nccl_stdout_check.py)
         dist.init_process_group('nccl', device_id=dev)
     N, n, nT = WORKLOADS[args.workload]
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
