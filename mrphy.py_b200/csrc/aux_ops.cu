@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128) beff2ab_bwd_kernel(const mrphy_beff2ab_ar
   T* G = (T*)a.gBeff + ((size_t)n * nM + i) * (size_t)nT * 3;
   const T* ck = (const T*)a.ckpt + (size_t)n * ((nT - 1) / K) * 12 * nM + i;
   SpinConst<T, 1> kd;   // apply_bwd<RELAX=false> never reads it
-  kd.e1 = kd.e2 = (T)0; kd.iE1 = kd.iE2 = (T)1;
+  kd.e1 = kd.e2 = kd.e1i = (T)0; kd.iE1 = kd.iE2 = (T)1;
   T sE1 = 0, sE2 = 0, sg = 0;
   for (int t = nT - 1; t >= 0; --t) {
     const T Bx = Bf[3 * t], By = Bf[3 * t + 1], Bz = Bf[3 * t + 2];

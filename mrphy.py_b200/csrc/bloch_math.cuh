@@ -316,6 +316,7 @@ template <typename T, int NC> struct SpinConst {
   T gbz0;               // g*df/gamma = 2*pi*dt*df      (beffective.py:142)
   T e1, e2;             // E1-1, E2-1 (expm1, full relative precision); 0 when no relaxation
   T iE1, iE2;           // 1/E1, 1/E2  (backward only)
+  T e1i;                // (E1-1)/E1 = -expm1(dt/T1): m~z = (m'z + E1 - 1)/E1 = m'z*iE1 + e1i in ONE fma (backward only)
 };
 
 // Built once per spin, in double, from the inputs as given (gamma, dt, T1, T2, df may be fp32 or
@@ -338,10 +339,12 @@ MRPHY_HD void make_consts(SpinConst<T, NC>& k, double gamma, double dt, bool rel
     k.e1 = (T)expm1(x1);
     k.e2 = (T)expm1(x2);
     k.iE1 = (T)exp(-x1);
+    k.e1i = (T)(-expm1(-x1));
     k.iE2 = (T)exp(-x2);
   } else {
     k.e1 = k.e2 = (T)0;
     k.iE1 = k.iE2 = (T)1;
+    k.e1i = (T)0;
   }
 }
 
@@ -352,7 +355,7 @@ MRPHY_HD SpinConst<f2, NC> pack2(const SpinConst<float, NC>& a, const SpinConst<
 #pragma unroll
   for (int c = 0; c < NC; ++c) { k.cbr[c] = f2(a.cbr[c], b.cbr[c]); k.cbi[c] = f2(a.cbi[c], b.cbi[c]); }
   k.glx = f2(a.glx, b.glx); k.gly = f2(a.gly, b.gly); k.glz = f2(a.glz, b.glz); k.gbz0 = f2(a.gbz0, b.gbz0);
-  k.e1 = f2(a.e1, b.e1); k.e2 = f2(a.e2, b.e2); k.iE1 = f2(a.iE1, b.iE1); k.iE2 = f2(a.iE2, b.iE2);
+  k.e1 = f2(a.e1, b.e1); k.e2 = f2(a.e2, b.e2); k.iE1 = f2(a.iE1, b.iE1); k.iE2 = f2(a.iE2, b.iE2); k.e1i = f2(a.e1i, b.e1i);
   return k;
 }
 
@@ -435,7 +438,7 @@ MRPHY_HD void apply_bwd(const SpinConst<T, NC>& k, const RotCoef<T>& r, T bx, T 
   if (RELAX) {
     tx = mx * k.iE2;
     ty = my * k.iE2;
-    tz = (mz + k.e1) * k.iE1;
+    tz = fma_(mz, k.iE1, k.e1i);
     gx = fma_(k.e2, hx, hx);
     gy = fma_(k.e2, hy, hy);
     gz = fma_(k.e1, hz, hz);
