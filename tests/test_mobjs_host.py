@@ -228,3 +228,37 @@ def test_embed_extract_match_reference_on_cpu(golden):
     assert np.array_equal(np.isnan(emb), np.isnan(g['mask_embedded']))
     assert np.array_equal(np.nan_to_num(emb), np.nan_to_num(g['mask_embedded']))
     assert np.array_equal(sa.extract(tensor(g['mask_full'])).numpy(), g['mask_extracted'])
+
+
+def test_checkpoint_policy_and_its_caches():
+    """K = floor(0.4 / (max(dt) / min(T1, T2))) capped at 64 and rounded down to a multiple of 16 when >= 16; min(T1, T2)
+    and max(dt) are cached per tensor object AND in-place version, separately (a design loop keeps its spins but builds
+    a new Pulse, hence a new dt, every iteration)."""
+    from mrphy import _ops
+    T1, T2 = torch.full((1, 5), 1.0, dtype=f64), torch.full((1, 5), 0.05, dtype=f64)
+    dt = tensor([4e-6], dtype=f64)
+    assert _ops.pick_ckpt_interval(dt, None, None) == 64                       # no relaxation: nothing to amplify
+    assert _ops.pick_ckpt_interval(dt, T1, T2) == 64                           # 0.4 / (4e-6 / 0.05) = 5000 -> cap
+    T2s = torch.full((1, 5), 1e-4, dtype=f64)
+    assert _ops.pick_ckpt_interval(dt, T1, T2s) == 10                          # 0.4 / 0.04
+    assert _ops.pick_ckpt_interval(tensor([1e-5], dtype=f64), T1, T2s) == 4    # a NEW dt object: its own entry
+    T2s[0, 3] = 2e-5                                                           # in-place edit bumps the version
+    assert _ops.pick_ckpt_interval(dt, T1, T2s) == 2                           # 0.4 / (4e-6 / 2e-5)
+    T2e = tensor(1e-3, dtype=f64).expand(1, 5)                                 # stride-0 storage as mobjs keeps it
+    assert _ops.pick_ckpt_interval(dt, T1.expand(1, 5), T2e) == 64             # 100 -> cap 64
+    _ops.note_host_max(dt, 8e-6)                                               # a registered host value wins over a read
+    assert _ops.pick_ckpt_interval(dt, T1, T2s) == 1
+    dt.mul_(1.0)                                                               # ... until the tensor changes
+    assert _ops.pick_ckpt_interval(dt, T1, T2s) == 2
+
+
+def test_reparam_falls_back_to_torch_when_constants_need_grad():
+    """Gradients w.r.t. rfmax / smax / dt are not the kernel's business: those calls evaluate the reference's expression."""
+    tr, th, ts = torch.randn(2, 1, 9, dtype=f64), torch.randn(2, 1, 9, dtype=f64), torch.randn(2, 3, 9, dtype=f64)
+    rfmax = tensor([0.1, 0.2], dtype=f64, requires_grad=True)
+    smax = tensor([[1., 2., 3.], [4., 5., 6.]], dtype=f64, requires_grad=True)
+    rf, gr = utils.tρθts2rfgr(tr, th, ts, rfmax, smax, tensor(4e-6, dtype=f64))
+    (rf.sum() + gr.sum()).backward()
+    assert rfmax.grad is not None and smax.grad is not None
+    want = tr.atan() / π * 2 * rfmax.detach()[:, None, None] * torch.cat((th.cos(), th.sin()), dim=1)
+    assert torch.allclose(rf, want, rtol=1e-14, atol=0)
