@@ -344,12 +344,12 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
 // fp32, TR == 16: lane l takes row l/2 and the half (l&1) of its 32 source lanes with four 128-bit loads whose
 // chunk order is rotated by the row -- the 8 lanes of a quarter-warp then touch 8 distinct 16-byte bank groups
 // (conflict-free).  Otherwise scalar loads with a rotated start (conflict-free).
-template <typename T, int W, int TR>
+template <typename T, int W, int TR, int W0 = 0, int W1 = W>
 __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int lane, T (*out)[TR]) {
   if constexpr (sizeof(T) == 4 && TR == 16) {
     const int r = lane >> 1, half = (lane & 1) << 4;
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
+    for (int w = W0; w < W1; ++w) {
       const float4* row = reinterpret_cast<const float4*>(&tile[w][r][half]);
       T sum = (T)0;
 #pragma unroll
@@ -363,7 +363,7 @@ __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int la
   } else {
     const int r = lane & (TR - 1), grp = lane & ~(TR - 1);
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
+    for (int w = W0; w < W1; ++w) {
       T sum = (T)0;
 #pragma unroll
       for (int q = 0; q < TR; ++q) sum += tile[w][r][grp + ((q + lane) & (TR - 1))];
@@ -376,11 +376,15 @@ __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int la
 
 // ------------------------------------------------------------------------------------------
 // backward
-template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+// ROWS: which gradients the caller wants -- bit 0 dL/drf (rows [0, 2 NC)), bit 1 dL/dgr (rows [2 NC, W)); the other rows
+// of the spin reduction are neither formed nor reduced (an RF-only design skips 3 of its 5 rows).
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT, int ROWS = 3>
 __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : (sizeof(T) == 8 && NC == 1 ? 4 : 1))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
   typedef typename Pack<T, PK>::type V;
   using L = BwdSmem<T, NC, BLKT>;
   constexpr int W = L::W, TR = L::TR, NW = L::NW;
+  constexpr bool WANT_RF = (ROWS & 1) != 0, WANT_GR = (ROWS & 2) != 0;
+  constexpr int W0 = WANT_RF ? 0 : 2 * NC, W1 = WANT_GR ? W : 2 * NC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T(*wbuf)[W * TCMAX] = reinterpret_cast<T(*)[W * TCMAX]>(smem_raw + L::wbuf);
   T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile
@@ -482,14 +486,18 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         for (int q = 0; q < NC; ++q) { rx[q] = V(s[q]); ry[q] = V(s[NC + q]); }
         field<V, NC>(k, rx, ry, V(s[2 * NC]), V(s[2 * NC + 1]), V(s[2 * NC + 2]), bx, by, bz);
         step_bwd<V, POL, RELAX, NC>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+        if constexpr (WANT_RF) {
 #pragma unroll
-        for (int q = 0; q < NC; ++q) {
-          red[warp][q][row][lane] = hsum(fma_(k.cbr[q], Fx, k.cbi[q] * Fy));
-          red[warp][NC + q][row][lane] = hsum(fnma_(k.cbi[q], Fx, k.cbr[q] * Fy));
+          for (int q = 0; q < NC; ++q) {
+            red[warp][q][row][lane] = hsum(fma_(k.cbr[q], Fx, k.cbi[q] * Fy));
+            red[warp][NC + q][row][lane] = hsum(fnma_(k.cbi[q], Fx, k.cbr[q] * Fy));
+          }
         }
-        red[warp][2 * NC][row][lane] = hsum(k.glx * Fz);
-        red[warp][2 * NC + 1][row][lane] = hsum(k.gly * Fz);
-        red[warp][2 * NC + 2][row][lane] = hsum(k.glz * Fz);
+        if constexpr (WANT_GR) {
+          red[warp][2 * NC][row][lane] = hsum(k.glx * Fz);
+          red[warp][2 * NC + 1][row][lane] = hsum(k.gly * Fz);
+          red[warp][2 * NC + 2][row][lane] = hsum(k.glz * Fz);
+        }
       };
       for (int j1 = ns; j1 > 0;) {
         const int j0 = ((j1 - 1) / TR) * TR;   // tile [j0, j1), at most TR steps
@@ -518,10 +526,10 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         }
         __syncwarp();
         T(*ctab)[W][TR] = cta + (size_t)(red_par & 1) * NW;   // this tile's half of the double buffer
-        warp_tile_reduce<T, W, TR>(red[warp], lane, ctab[warp]);
+        warp_tile_reduce<T, W, TR, W0, W1>(red[warp], lane, ctab[warp]);
         __syncthreads();   // the only CTA barrier per tile: `cta` alternates, `red` is re-written after it
-        for (int e = tid; e < W * TR; e += BLKT) {   // fixed-order combine of the warps
-          const int w = e / TR, r = e % TR;
+        for (int e = tid; e < (W1 - W0) * TR; e += BLKT) {   // fixed-order combine of the warps
+          const int w = W0 + e / TR, r = e % TR;
           if (j0 + r < j1) {
             T sum = ctab[0][w][r];
 #pragma unroll
@@ -875,6 +883,7 @@ struct Plan {
   int sum_coils; // no b1Map
   int tiles;     // spin tiles per batch entry (BLKT*PK spins each)
   int Pmax;      // upper bound on CTAs per batch entry (sizes the partial-sum workspace)
+  int rows;      // gradients wanted by the backward: bit 0 dL/drf, bit 1 dL/dgr (MRPHY_SKIP_GRF / _GGR clear them)
 };
 
 int sm_count_cached() {
@@ -920,6 +929,7 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   int P = p->tiles;
   if ((int64_t)P * a->N > cap) P = cap / a->N > 0 ? cap / a->N : 1;
   p->Pmax = P;
+  p->rows = ((a->flags & MRPHY_SKIP_GRF) ? 0 : 1) | ((a->flags & MRPHY_SKIP_GGR) ? 0 : 2);
   return MRPHY_OK;
 }
 
@@ -980,7 +990,9 @@ int check_common(const mrphy_fused_args* a, bool bwd) {
   if (!a->gamma.ptr || !a->dt.ptr) return fail(MRPHY_ERR_ARG, "gamma and dt are required%s");
   if ((a->T1.ptr == nullptr) != (a->T2.ptr == nullptr)) return fail(MRPHY_ERR_ARG, "T1 and T2: both or neither (sims.py:68)%s");
   if (!a->Mo || !a->ckpt || !a->wave) return fail(MRPHY_ERR_ARG, "Mo, ckpt and wave buffers are required%s");
-  if (bwd && (!a->gMo || !a->grf || !a->ggr || !a->partials)) return fail(MRPHY_ERR_ARG, "gMo, grf, ggr, partials are required%s");
+  if (bwd && (!a->gMo || !a->partials)) return fail(MRPHY_ERR_ARG, "gMo and partials are required%s");
+  if (bwd && ((!a->grf && !(a->flags & MRPHY_SKIP_GRF)) || (!a->ggr && !(a->flags & MRPHY_SKIP_GGR))))
+    return fail(MRPHY_ERR_ARG, "grf / ggr are required unless MRPHY_SKIP_GRF / MRPHY_SKIP_GGR is set%s");
   if (bwd && (a->flags & MRPHY_NEED_GMI) && !a->gMi) return fail(MRPHY_ERR_ARG, "gMi is null but MRPHY_NEED_GMI is set%s");
   return MRPHY_OK;
 }
@@ -1031,10 +1043,10 @@ int launch_fwd_s(KArgs<T> k, const Plan& p, cudaStream_t st) {
   CK(cudaGetLastError());
   return MRPHY_OK;
 }
-template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
+template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT, int ROWS = 3>
 int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   constexpr size_t smem = BwdSmem<T, NC, BLKT>::bytes;
-  auto kern = fused_bwd_kernel<T, POL, RELAX, NC, PK, BLKT>;
+  auto kern = fused_bwd_kernel<T, POL, RELAX, NC, PK, BLKT, ROWS>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
@@ -1103,9 +1115,12 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
 #ifndef MRPHY_ONLY_PK2
     if (p.PK == 3) return launch_tp<POL, RELAX, 128>(bwd, k, p, need_gmi, st);
 #endif
-    if (p.PK == 2)
-      return bwd ? launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT>(k, p, need_gmi, st)
-                 : launch_fwd_s<T, POL, RELAX, 1, 2, 64>(k, p, st);
+    if (p.PK == 2) {
+      if (!bwd) return launch_fwd_s<T, POL, RELAX, 1, 2, 64>(k, p, st);
+      if (p.rows == 1) return launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT, 1>(k, p, need_gmi, st);   // dL/drf only
+      if (p.rows == 2) return launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT, 2>(k, p, need_gmi, st);   // dL/dgr only
+      return launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT>(k, p, need_gmi, st);
+    }
   }
 #ifdef MRPHY_ONLY_PK2   /* tuning builds (profiles/operand_model.py): compile the default fp32 kernels only */
   return fail(MRPHY_ERR_ARG, "built with MRPHY_ONLY_PK2%s");
@@ -1156,7 +1171,7 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, cudaStream_t st) {
   dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 32);
   grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT,
                                                   (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T)-1, (T*)a->grf,
-                                                  (T*)a->ggr);
+                                                  (T*)a->ggr, (p.rows & 1) ? 0 : 2 * p.NC, (p.rows & 2) ? p.W : 2 * p.NC);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;

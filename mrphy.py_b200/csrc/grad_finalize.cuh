@@ -8,11 +8,13 @@ namespace mrphy {
 
 template <typename T>
 __global__ void grad_finalize_kernel(const T* __restrict__ partials, int P, int W, int NC, int nC, int nT,
-                                     int coil_dim, int bcast_coils, T sign, T* __restrict__ grf, T* __restrict__ ggr) {
+                                     int coil_dim, int bcast_coils, T sign, T* __restrict__ grf, T* __restrict__ ggr,
+                                     int w_lo = 0, int w_hi = 1 << 30) {
   constexpr int NY = 32;   // slices of the partial index summed in parallel, then combined in fixed order
   __shared__ T sm[NY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int t = blockIdx.x * 32 + tx, w = blockIdx.y, n = blockIdx.z;
+  if (w < w_lo || w >= w_hi) return;   // rows the caller did not ask for (and the backward did not produce)
   T sum = (T)0;
   if (t < nT) {
     const T* p = partials + ((size_t)n * P * W + w) * (size_t)nT + t;

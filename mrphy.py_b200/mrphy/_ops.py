@@ -162,20 +162,21 @@ def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flag
 def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
                        df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
                        gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (gMi (N,nM,3) or empty, grf like rf, ggr (N,3,nT))."""
+    """-> (gMi (N,nM,3) or empty, grf like rf or empty (FLAG_SKIP_GRF), ggr (N,3,nT) or empty (FLAG_SKIP_GGR))."""
     L = _cabi.lib()
     a = _cabi.FusedArgs()
     _fill_common(a, None, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
     kw = {'dtype': Mo.dtype, 'device': Mo.device}
     need_gmi = bool(flags & _cabi.FLAG_NEED_GMI)
     gMi = torch.empty((a.N, a.nM, 3) if need_gmi else (0,), **kw)
-    grf = torch.empty(rf.shape, **kw)
-    ggr = torch.empty((a.N, 3, a.nT), **kw)
+    want_rf, want_gr = not flags & _cabi.FLAG_SKIP_GRF, not flags & _cabi.FLAG_SKIP_GGR
+    grf = torch.empty(rf.shape if want_rf else (0,), **kw)
+    ggr = torch.empty((a.N, 3, a.nT) if want_gr else (0,), **kw)
     partials = torch.empty(L.mrphy_fused_partial_elems(a), **kw)
     a.Mo, a.ckpt, a.wave = Mo.data_ptr(), ckpt.data_ptr(), wave.data_ptr()
     a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
-    a.gMi, a.grf, a.ggr, a.partials = (gMi.data_ptr() if need_gmi else None), grf.data_ptr(), ggr.data_ptr(), \
-        partials.data_ptr()
+    a.gMi, a.grf, a.ggr, a.partials = (gMi.data_ptr() if need_gmi else None), (grf.data_ptr() if want_rf else None), \
+        (ggr.data_ptr() if want_gr else None), partials.data_ptr()
     with torch.cuda.device(Mo.device):
         _cabi.check(L.mrphy_blochsim_fused_bwd(a, 1, _stream()), 'blochsim_fused_bwd')
     _cabi.count_launches()
@@ -183,8 +184,9 @@ def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor
 
 
 def _fake_blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
-    return (Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)), Mo.new_empty(rf.shape),
-            Mo.new_empty((rf.shape[0], 3, rf.shape[2])))
+    return (Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)),
+            Mo.new_empty((0,) if flags & _cabi.FLAG_SKIP_GRF else rf.shape),
+            Mo.new_empty((0,) if flags & _cabi.FLAG_SKIP_GGR else (rf.shape[0], 3, rf.shape[2])))
 
 
 def _fused_setup(ctx, inputs, output):
@@ -206,7 +208,9 @@ def _fused_backward(ctx, gMo, _gckpt, _gwave):
         gMo = torch.zeros_like(Mo)
     if gMo.stride(-1) != 1 or gMo.dtype != Mo.dtype:
         gMo = gMo.to(Mo.dtype).contiguous()
-    flags = ctx.flags | (_cabi.FLAG_NEED_GMI if need[0] else 0)
+    # only the gradients autograd asks for: the rows of the spin reduction of the others are not even formed
+    flags = ctx.flags | (_cabi.FLAG_NEED_GMI if need[0] else 0) | (0 if need[1] else _cabi.FLAG_SKIP_GRF) | \
+        (0 if need[2] else _cabi.FLAG_SKIP_GGR)
     gMi, grf, ggr = blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags)
     return (gMi if need[0] else None, grf if need[1] else None, ggr if need[2] else None) + (None,) * 9
 

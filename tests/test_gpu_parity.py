@@ -850,3 +850,33 @@ def test_design_loop_with_fresh_pulses_has_no_host_sync(dev):
     replayed = [x.grad.clone() for x in v]
     iteration()
     assert all(torch.equal(x.grad, g) for x, g in zip(v, replayed))
+
+
+@pytest.mark.parametrize('dtype', [f32, f64])
+def test_gradient_rows_on_demand(dev, dtype):
+    """When only rf (an RF-only design on a fixed trajectory) or only gr needs a gradient, the backward neither forms nor
+    reduces the other rows (flags MRPHY_SKIP_GRF / MRPHY_SKIP_GGR): the gradients that ARE asked for must be bitwise
+    those of the full backward, the others None -- on the default kernels (big enough for the SM-aware grid) and on a
+    multi-coil problem (generic kernels: rows skipped in the finalize only)."""
+    from mrphy import _ops
+    gen = torch.Generator().manual_seed(9)
+    U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
+    for N, nM, nT, nC in ((1, 148 * 4 * 256 + 77, 130, 0), (2, 300, 97, 2)):
+        rf = (U(N, 2, nT, nC) if nC else U(N, 2, nT)) * 0.1
+        b1 = U(N, nM, 2, max(nC, 1)) * 0.1
+        b1[:, :, 0] += 1
+        t = lambda x: x.to(dtype).to(dev)
+        args = dict(loc_=t(U(N, nM, 3) * 12), Δf_=t(U(N, nM) * 200), b1Map_=t(b1), T1_=t(1.0 + 0.5 * U(N, nM)),
+                    T2_=t(0.06 + 0.05 * U(N, nM)), γ_=tensor(4257.6, dtype=f64, device=dev), dt=tensor([4e-6], dtype=f64, device=dev))
+        M0, w = t(torch.nn.functional.normalize(U(N, nM, 3), dim=-1)), t(U(N, nM, 3))
+        grads = {}
+        for which in ('both', 'rf', 'gr', 'M'):
+            r = t(rf).requires_grad_(which in ('both', 'rf'))
+            g = t(U(N, 3, nT) * 0 + 1.3).requires_grad_(which in ('both', 'gr'))
+            m = M0.clone().requires_grad_(which == 'M')
+            Mo = _ops.fused_applypulse(m, r, g, **args)
+            (Mo * w).sum().backward()
+            grads[which] = (r.grad, g.grad, m.grad)
+        assert grads['rf'][1] is None and grads['gr'][0] is None and grads['M'][0] is None and grads['M'][1] is None
+        assert torch.equal(grads['rf'][0], grads['both'][0]) and torch.equal(grads['gr'][1], grads['both'][1])
+        assert grads['M'][2] is not None and bool(torch.isfinite(grads['M'][2]).all())
