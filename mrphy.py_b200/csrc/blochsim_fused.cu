@@ -7,14 +7,16 @@
 //   pack_waveform_kernel      rf (N,2,nT[,nC]), gr (N,3,nT) -> wave[N][chunk][W][TCP]  (W = 2*NC+3)
 //   fused_fwd_kernel<T,..>    one spin, or two spins packed in an f2 (FFMA2), per thread; checkpoint every K steps
 //   fused_*_tp_kernel         time-packed fp32 variant (one spin per thread, two steps' coefficients per f2)
-//   fused_bwd_kernel<T,..>    time-reversed state reconstruction + adjoint + spin reduction
+//   fused_bwd_kernel<T,..>    time-reversed state reconstruction + adjoint + spin reduction (only the gradient rows
+//                             asked for: ROWS); tiles owned through SM-aware virtual CTA ids (SCHED_*)
 //   grad_finalize_kernel<T>   deterministic sum of the per-CTA partials, reference layout out (grad_finalize.cuh)
 //
 // Data layout in HBM (T = float | double):
 //   wave      [N][nChunks][W][TCP]   one chunk = K steps (TCP = K rounded up to 4): a chunk is
 //                                    ONE contiguous 16-byte-aligned block -> one 1-D TMA bulk copy
 //   ckpt      [N][nChunks-1][3][nM]  state after (c+1)*K steps, SoA so warps store 128-B lines
-//   partials  [N][P][W][nT]          per-CTA gradient partial sums (P CTAs per batch entry)
+//   partials  [N][P][W][nT]          gradient partial sums, one slot per (virtual) CTA id, P ids per batch entry;
+//                                    behind them 264 + P ints of scheduling state of the backward (SCHED_*)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
