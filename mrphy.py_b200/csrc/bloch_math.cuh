@@ -192,7 +192,10 @@ MRPHY_HD void sc_quadrant(int j, float sr, float cr, float& s, float& c) {
 // Reduction by pi instead of pi/2 (MRPHY_SC_MODPI, default on): sin and cos of the reduced argument only change SIGN with
 // the parity of the multiple, so the per-lane quadrant fix-up shrinks from a swap + two sign computations (8 scalar
 // instructions per spin, which cannot be packed) to one shift + two XORs, for one more (packed) term in each polynomial:
-// minimax on [-pi/2, pi/2], max error 1.1e-7 / 9.0e-8, rms 1.9e-8 / 2.1e-8, unbiased (profiles/fit_sincos.py).
+// minimax on [-pi/2, pi/2]: max error 1.1e-7 / 9.0e-8, rms 1.9e-8 / 2.1e-8, mean angle error < 7e-9, mean of sin^2 + cos^2 - 1
+// -7.7e-9 (profiles/fit_sincos.py).  Moving two coefficients by 3 and 8 ulp brings that radius mean to 2e-11, but the simulated
+// magnetisation got WORSE with it (bench8: max|dM| 1.53e-5 -> 2.02e-5): the fp32 state update has a drift of its own that the
+// small shrink happens to offset, so the plain minimax coefficients stay.
 #ifndef MRPHY_SC_MODPI
 #define MRPHY_SC_MODPI 1
 #endif

@@ -23,37 +23,18 @@ __device__ __forceinline__ void sc_corr_rz(float x, float& s, float& c) {
   s = fmaf(d, c0, s0);
   c = fmaf(-d, s0, c0);
 }
-// evaluate MUFU at a grid point of 2^-QB revolutions (exactly representable whatever the unit's input format) and
-// correct to first order for the distance to it (<= 2^-(QB+1) rev = 1.5e-6 rad at QB = 21: second order 1e-12)
-template <int QB>
-__device__ __forceinline__ void sc_grid(float x, float& s, float& c) {
-  const float magic = 12582912.0f / (float)(1 << QB);        // 1.5 * 2^(23-QB)
-  const float t = fmaf(x, INV_2PI, magic);
-  const float tq = t - magic;                                 // x/2pi rounded to 2^-QB
-  float d = fmaf(-tq, TWO_PI_HI, x);
-  d = fmaf(-tq, TWO_PI_LO, d);
-  // hand MUFU an argument whose FMUL.RZ by 1/2pi lands just above tq, never below (tq is far from fp32 resolution)
-  const float xq = tq * TWO_PI_HI * 1.0000002f;
-  float s0, c0;
-  __sincosf(xq, &s0, &c0);
-  s = fmaf(d, c0, s0);
-  c = fmaf(-d, s0, c0);
-}
-
 __global__ void k(const float* x, int n, float* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s, c;
   __sincosf(x[i], &s, &c); out[i] = s; out[n + i] = c;
   sc_corr_rz(x[i], s, c); out[2 * n + i] = s; out[3 * n + i] = c;
-  sc_grid<21>(x[i], s, c); out[4 * n + i] = s; out[5 * n + i] = c;
-  sc_grid<18>(x[i], s, c); out[6 * n + i] = s; out[7 * n + i] = c;
-  Fn<float, TRIG_PRECISE>::sc(x[i], s, c); out[8 * n + i] = s; out[9 * n + i] = c;
+  Fn<float, TRIG_PRECISE>::sc(x[i], s, c); out[4 * n + i] = s; out[5 * n + i] = c;
 }
 
 int main() {
-  const int n = 1 << 22, NV = 5;
-  const char* names[NV] = {"mufu raw", "mufu + corr (rz product)", "mufu on 2^-21 rev grid + corr", "mufu on 2^-18 rev grid + corr", "polynomial"};
+  const int n = 1 << 22, NV = 3;
+  const char* names[NV] = {"mufu raw", "mufu + corr (rz product)", "polynomial (shipped)"};
   float *dx, *dout; cudaMalloc(&dx, n * 4); cudaMalloc(&dout, 2 * NV * (size_t)n * 4);
   std::vector<float> x(n), out(2 * NV * (size_t)n);
   const double ranges[3][2] = {{0, 0.8}, {0, 3.2}, {0, 6.3}};
