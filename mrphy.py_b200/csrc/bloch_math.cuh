@@ -365,17 +365,77 @@ MRPHY_HD SpinConst<f2, NC> pack2(const SpinConst<float, NC>& a, const SpinConst<
 // Rotation coefficients shared by forward and backward.
 template <typename T> struct RotCoef { T c, a, d, rs2; };
 
+// fp32 "precise", common case |b| <= 2 pi: the rotation only needs a = sin(phi)/phi and d = (1 - cos(phi))/phi^2, both
+// EVEN entire functions of phi, i.e. functions of p2 = |b|^2 -- so neither the angle nor 1/phi is ever formed.  With the
+// half angle h = phi/2:  a = sinc(h) cos(h),  d = sinc(h)^2 / 2, and sinc(h), cos(h) are 7-term polynomials in p2 on
+// phi <= 2 pi (h <= pi: terms <= 1.7, no cancellation trouble).  Against MUFU.RSQ + Newton + Cody-Waite reduction + two
+// polynomials + sign fix-ups this is 12 FMAs with immediate coefficients and 3 multiplies: 21 FP32-pipe operations and 2
+// MUFU fewer per spin-step, at the same error (profiles/fit_halfangle.py: angle rms 4e-8, radius rms 1e-7, means 1e-8
+// on the bench distribution; the reduce-by-pi path: 8e-8, 1e-7, 8e-9).  Leading coefficients are exactly 1, so there is
+// no systematic scale (radius) error.  A step with |b| > MRPHY_HALF_PHIMAX (1.3e-5 of the spin-steps of the bench
+// distributions) takes the reduce-by-pi path below: one rarely taken branch per step.
+#ifndef MRPHY_HALF_ANGLE
+#define MRPHY_HALF_ANGLE 1
+#endif
+#define MRPHY_HALF_P2MAX 40.0f   /* (2 pi * 1.0066)^2; the polynomials are fitted on [0, (2 pi * 1.02)^2] */
+MRPHY_HD bool any_gt(float a, float lim) { return a > lim; }
+MRPHY_HD bool any_gt(double a, double lim) { return a > lim; }
+MRPHY_HD bool any_gt(f2 a, float lim) { return fmaxf(a.v.x, a.v.y) > lim; }
+MRPHY_HD float rcp_(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // MUFU.RCP, 1 ulp: only scales the (1 - a)/|b|^2 term of the adjoint
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+MRPHY_HD f2 rcp_(f2 x) { return f2(rcp_(x.v.x), rcp_(x.v.y)); }
+template <typename V> MRPHY_HD RotCoef<V> rot_coef_half(V p2) {
+#ifndef MRPHY_HALF_SET
+#define MRPHY_HALF_SET 0
+#endif
+#if MRPHY_HALF_SET == 2
+  V A = fma_(p2, V(-7.486010352e-17f), V(4.369235483e-14f));
+  A = fma_(A, p2, V(-2.472151477e-11f));
+  A = fma_(A, p2, V(1.077164669e-08f));
+  A = fma_(A, p2, V(-3.100295771e-06f));
+  A = fma_(A, p2, V(5.208339426e-04f));
+  A = fma_(A, p2, V(-4.166666791e-02f));
+#else
+  V A = fma_(p2, V(3.280267225e-14f), V(-2.409831189e-11f));
+  A = fma_(A, p2, V(1.075399236e-08f));
+  A = fma_(A, p2, V(-3.100041567e-06f));
+  A = fma_(A, p2, V(5.208322546e-04f));
+  A = fma_(A, p2, V(-4.166666418e-02f));
+#endif
+  A = fma_(A, p2, V(1.0f));                       // sinc(phi/2)
+#if MRPHY_HALF_SET == 0
+  V C = fma_(p2, V(4.191810202e-13f), V(-2.642699393e-10f));
+  C = fma_(C, p2, V(9.675193269e-08f));
+  C = fma_(C, p2, V(-2.169963955e-05f));
+  C = fma_(C, p2, V(2.604155801e-03f));
+  C = fma_(C, p2, V(-1.249999776e-01f));
+#else
+  V C = fma_(p2, V(-5.813414228e-16f), V(5.015682964e-13f));
+  C = fma_(C, p2, V(-2.688312073e-10f));
+  C = fma_(C, p2, V(9.687599345e-08f));
+  C = fma_(C, p2, V(-2.170134212e-05f));
+  C = fma_(C, p2, V(2.604166511e-03f));
+  C = fma_(C, p2, V(-1.250000000e-01f));
+#endif
+  C = fma_(C, p2, V(1.0f));                       // cos(phi/2)
+  RotCoef<V> r;
+  r.a = A * C;
+  r.d = (A * V(0.5f)) * A;
+  r.c = fnma_(p2, r.d, V(1.0f));
+  r.rs2 = rcp_(p2);                               // backward only (dead code in the forward)
+  return r;
+}
+
+// any angle: rsqrt, phi, sincos by the policy
 template <typename T, int POL>
-MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
-  T p2;
-  if (sizeof(typename Scalar<T>::type) == 4) {
-    // fp32: the reference's phi >= 1e-12 clamp as +1e-24 under the root -- invisible next to any |b|^2 >= 1e-17 (fp32
-    // resolution), the same 1e-24 for a zero field (exact identity step), and two FMNMX per thread-step cheaper
-    p2 = fma_(bx, bx, fma_(by, by, fma_(bz, bz, (T)1e-24f)));
-  } else {
-    p2 = fma_(bx, bx, fma_(by, by, bz * bz));
-    p2 = max_(p2, (T)1e-24f);
-  }
+MRPHY_HD RotCoef<T> rot_coef_reduced(T p2) {
   T rs = Fn<T, POL>::rsq(p2);
   T phi = p2 * rs;
   T s, c;
@@ -386,6 +446,32 @@ MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
   r.rs2 = rs * rs;
   r.d = fnma_(c, r.rs2, r.rs2);   // (1 - cos) / phi^2
   return r;
+}
+
+#ifndef MRPHY_HALF_BWD
+#define MRPHY_HALF_BWD 1
+#endif
+template <typename T, int POL, bool HALF_OK = true>
+MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
+  T p2;
+  if (sizeof(typename Scalar<T>::type) == 4) {
+    // fp32: the reference's phi >= 1e-12 clamp as +1e-24 under the root -- invisible next to any |b|^2 >= 1e-17 (fp32
+    // resolution), the same 1e-24 for a zero field (exact identity step), and two FMNMX per thread-step cheaper
+    p2 = fma_(bx, bx, fma_(by, by, fma_(bz, bz, (T)1e-24f)));
+#if MRPHY_HALF_ANGLE
+    if (POL == TRIG_PRECISE && HALF_OK) {
+      RotCoef<T> r = rot_coef_half<T>(p2);
+#ifndef MRPHY_HALF_NOFALLBACK   /* modelling builds only (profiles/model_all.py): the common path without the branch */
+      if (any_gt(p2, (typename Scalar<T>::type)MRPHY_HALF_P2MAX)) r = rot_coef_reduced<T, POL>(p2);
+#endif
+      return r;
+    }
+#endif
+  } else {
+    p2 = fma_(bx, bx, fma_(by, by, bz * bz));
+    p2 = max_(p2, (T)1e-24f);
+  }
+  return rot_coef_reduced<T, POL>(p2);
 }
 
 // field of one step from the staged waveform sample (rx[c], ry[c], gx, gy, gz)
@@ -458,16 +544,18 @@ MRPHY_HD void apply_bwd(const SpinConst<T, NC>& k, const RotCoef<T>& r, T bx, T 
   T wx = fms_(by, gz, bz * gy);
   T wy = fms_(bz, gx, bx * gz);
   T wz = fms_(bx, gy, by * gx);
-  // F = a (m0 x h~) - d (Q h~ + P m0) - [ (m~ - a m0).wb - 2 d P Q ] rs^2 b
-  T nx = fnma_(r.a, px, tx), ny = fnma_(r.a, py, ty), nz = fnma_(r.a, pz, tz);
-  T C = fma_(nx, wx, fma_(ny, wy, nz * wz));
-  C = fma_((T)(-2.0f) * kp, Q, C) * r.rs2;
-  T cx = fms_(py, gz, pz * gy);
-  T cy = fms_(pz, gx, px * gz);
-  T cz = fms_(px, gy, py * gx);
-  Fx = fnma_(C, bx, fms_(r.a, cx, fma_(kq, gx, kp * px)));
-  Fy = fnma_(C, by, fms_(r.a, cy, fma_(kq, gy, kp * py)));
-  Fz = fnma_(C, bz, fms_(r.a, cz, fma_(kq, gz, kp * pz)));
+  // F = -dL/db.  With R = exp(-[b]x) the differential of the rotation is dR = -[J db]x R, J = a I + e b b^T + d [b]x the
+  // left Jacobian of SO(3) in b-form (e = (1 - a)/|b|^2), so -dL/db = J (m~ x h~); and with b x (m~ x h~) = P m~ - Q h~,
+  // b.(m~ x h~) = -m~.wb:
+  //     F = a (m~ x h~) + d (P m~ - Q h~) - e (m~.wb) b
+  // (same value as the reference's closed form, sims.py:204-261, which is written in the pre-rotation state)
+  T E = fnma_(r.a, r.rs2, r.rs2) * fma_(tx, wx, fma_(ty, wy, tz * wz));
+  T cx = fms_(ty, gz, tz * gy);
+  T cy = fms_(tz, gx, tx * gz);
+  T cz = fms_(tx, gy, ty * gx);
+  Fx = fnma_(E, bx, fnma_(kq, gx, fma_(kp, tx, r.a * cx)));
+  Fy = fnma_(E, by, fnma_(kq, gy, fma_(kp, ty, r.a * cy)));
+  Fz = fnma_(E, bz, fnma_(kq, gz, fma_(kp, tz, r.a * cz)));
   // h0 = c*h~ + kp*b + a*wb
   hx = fma_(r.a, wx, fma_(kp, bx, r.c * gx));
   hy = fma_(r.a, wy, fma_(kp, by, r.c * gy));
@@ -477,7 +565,7 @@ MRPHY_HD void apply_bwd(const SpinConst<T, NC>& k, const RotCoef<T>& r, T bx, T 
 template <typename T, int POL, bool RELAX, int NC>
 MRPHY_HD void step_bwd(const SpinConst<T, NC>& k, T bx, T by, T bz, T& mx, T& my, T& mz, T& hx, T& hy, T& hz,
                        T& Fx, T& Fy, T& Fz) {
-  const RotCoef<T> r = rot_coef<T, POL>(bx, by, bz);
+  const RotCoef<T> r = rot_coef<T, POL, MRPHY_HALF_BWD != 0>(bx, by, bz);
   apply_bwd<T, RELAX, NC>(k, r, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
 }
 

@@ -689,12 +689,38 @@ def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -
     return K
 
 
+TRIG_POLICIES = ('precise', 'mixed', 'fast', 'strict')
+_policy_override = None
+
+
+def set_trig_policy(name: Optional[str]) -> None:
+    """Select the fp32 arithmetic policy for this process (None: back to MRPHY_B200_TRIG / the default)."""
+    global _policy_override
+    assert name is None or name in TRIG_POLICIES, f'policy must be one of {TRIG_POLICIES}'
+    _policy_override = name
+
+
+def trig_policy() -> str:
+    """fp32 arithmetic policy (ignored for fp64 tensors): `set_trig_policy`, else MRPHY_B200_TRIG, else 'mixed'.
+
+    precise  rotation coefficients from half-angle polynomials on the FMA pipe (|b| <= 2 pi; Cody-Waite reduction +
+             Newton-refined rsqrt beyond), forward and adjoint: M at 0.7-0.9x the reference's own fp32 error.
+    mixed    (default) the same forward -- M is bit-identical to 'precise' -- and MUFU.SIN/COS/RSQ in the adjoint kernel:
+             rf/gr gradients 1-4e-5 relative instead of 0.5-1e-5 (the reference's own fp32: 1.5-5e-5; tolerance 1e-4).
+    fast     MUFU trigonometry everywhere: ~2x the reference's fp32 error on M at nT ~ 1000.
+    strict   fp32 tensors in and out, fp64 arithmetic inside (the fp64 kernels): M within 1e-5 -- in fact 1e-6 -- of the
+             reference's fp64 result at every nT, which no fp32 evaluation of this recurrence, the reference's own included,
+             achieves beyond nT ~ 500; costs ~2.7x the time."""
+    pol = _policy_override or os.environ.get('MRPHY_B200_TRIG', 'mixed')
+    if pol not in TRIG_POLICIES:
+        raise ValueError(f'MRPHY_B200_TRIG={pol!r}: expected one of {TRIG_POLICIES}')
+    return pol
+
+
 def default_flags() -> int:
-    """fp32 trigonometry policy.  Default 'precise' (Newton-refined rsqrt + polynomial sincos on the FMA pipe):
-    on the reference's own fixtures it is ~0.6x the reference's fp32 error, whereas raw MUFU.SIN/COS
-    ('fast', MRPHY_B200_TRIG=fast) doubles it at nT~1000.  Ignored for fp64."""
-    pol = os.environ.get('MRPHY_B200_TRIG', 'precise')
-    if pol == 'mixed':      # precise forward (M as in 'precise'), MUFU trigonometry in the adjoint kernel only
+    """C-ABI flags of the current `trig_policy` ('strict' is handled above the ABI: it runs the fp64 kernels)."""
+    pol = trig_policy()
+    if pol == 'mixed':
         return _cabi.FLAG_TRIG_PRECISE | _cabi.FLAG_TRIG_FAST_BWD
     return 0 if pol == 'fast' else _cabi.FLAG_TRIG_PRECISE
 
@@ -711,6 +737,12 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
     dtype, dev = M_.dtype, M_.device
     if dtype not in _F:
         raise TypeError(f'mrphy (B200): M must be float32 or float64, got {dtype}')
+    if dtype == torch.float32 and flags is None and trig_policy() == 'strict':
+        # fp32 tensors in and out, fp64 arithmetic: the casts are differentiable torch copies either side of the fp64 op
+        up = lambda x: None if x is None else x.to(torch.float64)
+        Mo = fused_applypulse(up(M_), up(rf), up(gr), up(loc_), Δf_=up(Δf_), b1Map_=up(b1Map_), T1_=up(T1_), T2_=up(T2_),
+                              γ_=γ_, dt=dt, ckpt=ckpt)
+        return Mo.to(torch.float32)
     assert (T1_ is None) == (T2_ is None)      # both or neither (sims.py:68)
     N, nM = loc_.shape[0], loc_.shape[1]
     assert M_.shape == (N, nM, 3) and loc_.shape == (N, nM, 3)
@@ -725,6 +757,8 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
         if b1.ndim == 3:
             b1 = b1[..., None]
         nC = rf.shape[3] if rf.ndim == 4 else 1
+        if nC == 1 and b1.shape[3] > 1:          # one rf for every coil: sum_c b1_c * rf = (sum_c b1_c) * rf
+            b1 = b1.sum(dim=3, keepdim=True)
         assert b1.shape[2] == 2 and b1.shape[3] in (1, nC), 'b1Map and rf disagree on nCoils'
         # a single-coil b1Map with multi-coil rf broadcasts over coils, as upstream (beffective.py:153-165)
         b1 = _inner_contig(b1.expand(N, nM, 2, nC) if tuple(b1.shape) != (N, nM, 2, nC) else b1, 2)

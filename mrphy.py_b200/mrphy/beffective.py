@@ -161,8 +161,10 @@ class _RfGr2Beff(torch.autograd.Function):
         b1f = None
         if b1Map is not None:
             nC = rf.shape[3] if rf.ndim == 4 else 1
-            b1n = b1Map if b1Map.ndim == len(Nd) + 3 else b1Map[..., None]          # (N|1,*Nd|1,2,nC)
-            assert b1n.shape[-1] == nC, 'b1Map and rf disagree on nCoils'
+            b1n = b1Map if b1Map.ndim == len(Nd) + 3 else b1Map[..., None]          # (N|1,*Nd|1,2,nC|1)
+            # a single-coil b1Map broadcasts over the coils of rf, as upstream (beffective.py:153-165); the opposite
+            # case (multi-coil b1Map, rf without coils) is reduced to one coil by `rfgr2beff` below
+            assert b1n.shape[-1] in (1, nC), 'b1Map and rf disagree on nCoils'
             b1f = _ops._inner_contig(b1n.expand((N,) + Nd + (2, nC)).reshape(N, nM, 2, nC), 2)
         out = _ops.rfgr2beff_cuda(rf, gr, locf, dff, b1f, gf)
         ctx.save_for_backward(rf, gr, locf, dff, b1f, gf)
@@ -218,4 +220,8 @@ def rfgr2beff(
     _ops._require_cuda(rf)
     dev = rf.device
     cast = lambda x: None if x is None else _working(x.to(dev), rf)
-    return _RfGr2Beff.apply(rf, cast(gr), cast(loc), cast(Δf), cast(b1Map), _ops.on_device(γ, dev))
+    b1Map = cast(b1Map)
+    if b1Map is not None and b1Map.ndim == loc.ndim + 1 and b1Map.shape[-1] > 1 and (rf.ndim == 3 or rf.shape[3] == 1):
+        # the same rf drives every coil: sum_c b1_c * rf = (sum_c b1_c) * rf  (upstream's broadcast, beffective.py:158-165)
+        b1Map = b1Map.sum(dim=-1, keepdim=True)
+    return _RfGr2Beff.apply(rf, cast(gr), cast(loc), cast(Δf), b1Map, _ops.on_device(γ, dev))

@@ -59,7 +59,9 @@ class BlochSim(Function):
         saved = (Mo, ckpt, B, gf, dtf) + ((T1f, T2f) if T1 is not None else ())
         ctx.save_for_backward(*saved)
         ctx.NNd = NNd
-        return Mo.reshape(NNd + (3,))
+        # a private copy is what backward reconstructs the states from: the caller may edit the returned tensor in place
+        # (upstream returns a clone too, sims.py:128)
+        return Mo.clone().reshape(NNd + (3,))
 
     @staticmethod
     def backward(ctx, grad_Mo: Tensor) -> Tuple[Optional[Tensor], Optional[Tensor], None, None, None, None]:
@@ -104,6 +106,8 @@ def blochsim(
     assert ((T1 is None) == (T2 is None))            # sims.py:311
     if T1 is not None:
         T1, T2 = (x.reshape(x.shape + (ndim - x.ndim) * (1,)) for x in (T1, T2))
+    if Mi.dtype == torch.float32 and _ops.trig_policy() == 'strict':     # fp32 in and out, fp64 arithmetic
+        return BlochSim.apply(Mi.double(), Beff.double(), T1, T2, γ, dt).float()
     return BlochSim.apply(Mi, Beff, T1, T2, γ, dt)
 
 
@@ -121,7 +125,9 @@ class FreePrec(Function):
         N, Nd, dev = Mi.shape[0], tuple(Mi.shape[1:-1]), Mi.device
         args = (_ops.on_device(dur, dev).reshape(-1), _flat_param(T1, N, Nd, dev), _flat_param(T2, N, Nd, dev),
                 _flat_param(Δf, N, Nd, dev))
-        ctx.args, ctx.shape = args, Mi.shape
+        ctx.has = [x is not None for x in args]
+        ctx.save_for_backward(*[x for x in args if x is not None])     # version-checked, unlike attributes on ctx
+        ctx.shape = Mi.shape
         M = _ops._inner_contig(Mi.reshape(N, -1, 3), 1)
         return _ops.freeprec_cuda(M, *args, False).reshape(Mi.shape)
 
@@ -129,8 +135,10 @@ class FreePrec(Function):
     def backward(ctx, grad_Mo: Tensor):
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
+        saved = list(ctx.saved_tensors)
+        args = [saved.pop(0) if h else None for h in ctx.has]
         g = _ops._inner_contig(grad_Mo.reshape(ctx.shape[0], -1, 3), 1)
-        return _ops.freeprec_cuda(g, *ctx.args, True).reshape(ctx.shape), None, None, None, None
+        return _ops.freeprec_cuda(g, *args, True).reshape(ctx.shape), None, None, None, None
 
 
 def freeprec(

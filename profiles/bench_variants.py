@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-only comparison of tuning variants of the fused kernels (C2 / C3, fp32), one subprocess per variant.
 
-    python profiles/bench_variants.py name[:lib.so][:ENV=V,ENV=V] ...  [--workloads c2,c3] [--trig precise,fast]
+    python profiles/bench_variants.py name[:lib.so][:ENV=V,ENV=V] ...  [--workloads c2,c3] [--trig precise,mixed,fast]
 
 Each variant is a library built with `python mrphy.py_b200/build.py -D... --out=profiles/variants/x.so` and/or a set of
 MRPHY_B200_* environment switches.  Prints per variant: forward / backward kernel ms (CUDA events inside the C ABI, best and
@@ -69,8 +69,7 @@ def main():
                     env['MRPHY_B200_LIB'] = os.path.join(ROOT, parts[1])
                 if len(parts) > 2 and parts[2]:
                     env.update(dict(kv.split('=', 1) for kv in parts[2].split(',')))
-                if trig == 'fast':
-                    env['MRPHY_B200_TRIG'] = 'fast'
+                env['MRPHY_B200_TRIG'] = trig
                 outp = os.path.join(ROOT, 'gpurun_out', f'variant_{name}_{wl}_{trig}.npz')
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), '--worker', wl, outp], env=env,
                                    capture_output=True, text=True)

@@ -109,16 +109,20 @@ def test_f32_formulation_noise_floor(lib, golden, pol):
 
 @pytest.mark.parametrize('pol', [0, 1])
 def test_packed_f2_path_equals_scalar_path(lib, golden, pol):
-    """The two-spins-per-thread formulation (FFMA2 on the device) is the same arithmetic as the scalar one."""
+    """The two-spins-per-thread formulation (FFMA2 on the device) is the same arithmetic as the scalar one.  The only
+    difference: a step with |b| > 2 pi sends BOTH spins of a pair through the reduce-by-pi coefficients (one branch per
+    f2), so pairs that contain such a step differ from the scalar path by rounding."""
     g = golden('bench8')
     g = dict(g, in_w=2 * (g['Mo_f64'] - np.array([0., 1., 0.])))
     a = run(lib, 'f32', pol, g, 64)
     b = run(lib, 'f32x2', pol, g, 64)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-    assert rel(b[2], a[2]) < 1e-6 and rel(b[3], a[3]) < 1e-6
+    same = np.all(a[0] == b[0], axis=1) & np.all(a[1] == b[1], axis=1)
+    assert same.mean() > (0.9 if pol == 1 else 0.9999), same.mean()
+    assert np.abs(a[0] - b[0]).max() < 5e-6 and rel(b[1], a[1]) < 2e-5
+    assert rel(b[2], a[2]) < 2e-6 and rel(b[3], a[3]) < 2e-6
     g2 = golden('rand_norelax')
     a, b = run(lib, 'f32', pol, g2, 16), run(lib, 'f32x2', pol, g2, 16)
-    assert np.array_equal(a[0][:32], b[0][:32]) and np.array_equal(a[1][:32], b[1][:32])
+    assert np.abs(a[0][:32] - b[0][:32]).max() < 5e-6 and np.abs(a[1][:32] - b[1][:32]).max() < 5e-6 * np.abs(a[1]).max()
 
 
 def test_kat3_through_formulation(lib, golden):
