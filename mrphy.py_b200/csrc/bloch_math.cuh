@@ -314,7 +314,8 @@ template <> struct Fn<f2, TRIG_PRECISE> {
 // NC is the number of transmit coils held in registers (template); NC==1 covers "no b1Map"
 // (coils pre-summed by the pack kernel, cbr=g, cbi=0).
 template <typename T, int NC> struct SpinConst {
-  T cbr[NC], cbi[NC];   // g*Re(b1), g*Im(b1)          g = 2*pi*gamma*dt  (sims.py:62)
+  T cbr[NC], cbi[NC];   // g*Re(b1), g*Im(b1)          g = 2*pi*gamma*dt  (sims.py:62);  NC == 1: g*|b1|, 0 (spin frame)
+  T fc, fs;             // NC == 1: cos, sin of arg(b1): the spin's own transverse frame (make_consts); else 1, 0
   T glx, gly, glz;      // g*loc                        (beffective.py:137)
   T gbz0;               // g*df/gamma = 2*pi*dt*df      (beffective.py:142)
   T e1, e2;             // E1-1, E2-1 (expm1, full relative precision); 0 when no relaxation
@@ -328,10 +329,27 @@ template <typename T, int NC>
 MRPHY_HD void make_consts(SpinConst<T, NC>& k, double gamma, double dt, bool relax, double T1, double T2, double df,
                           T lx, T ly, T lz, const T* b1r, const T* b1i) {
   const double g = 6.283185307179586476925286766559 * gamma * dt;
+  k.fc = (T)1;
+  k.fs = (T)0;
+  if (NC == 1) {
+    // One transmit channel: simulate in the spin's OWN transverse frame, the lab frame turned about z by arg(b1).  There
+    // the sensitivity is real, (Bx + i By) = |b1| (rx + i ry): 2 multiplies per step instead of 4 multiply-adds for the
+    // field, and 2 instead of 4 for the chain rule to rf in the adjoint.  A fixed rotation about z commutes with Bz and
+    // with the relaxation, so only Mi / dL/dMo enter the frame (to_frame) and Mo / dL/dMi leave it (from_frame).
+    const double br = b1r ? (double)b1r[0] : 1.0, bi = b1i ? (double)b1i[0] : 0.0;
+    const double mag = sqrt(br * br + bi * bi);
+    k.cbr[0] = (T)(g * mag);
+    k.cbi[0] = (T)0;
+    if (mag > 0.0) {
+      k.fc = (T)(br / mag);
+      k.fs = (T)(bi / mag);
+    }
+  } else {
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    k.cbr[c] = (T)(g * (b1r ? (double)b1r[c] : 1.0));
-    k.cbi[c] = (T)(g * (b1i ? (double)b1i[c] : 0.0));
+    for (int c = 0; c < NC; ++c) {
+      k.cbr[c] = (T)(g * (b1r ? (double)b1r[c] : 1.0));
+      k.cbi[c] = (T)(g * (b1i ? (double)b1i[c] : 0.0));
+    }
   }
   k.glx = (T)(g * (double)lx);
   k.gly = (T)(g * (double)ly);
@@ -357,79 +375,56 @@ MRPHY_HD SpinConst<f2, NC> pack2(const SpinConst<float, NC>& a, const SpinConst<
   SpinConst<f2, NC> k;
 #pragma unroll
   for (int c = 0; c < NC; ++c) { k.cbr[c] = f2(a.cbr[c], b.cbr[c]); k.cbi[c] = f2(a.cbi[c], b.cbi[c]); }
+  k.fc = f2(a.fc, b.fc); k.fs = f2(a.fs, b.fs);
   k.glx = f2(a.glx, b.glx); k.gly = f2(a.gly, b.gly); k.glz = f2(a.glz, b.glz); k.gbz0 = f2(a.gbz0, b.gbz0);
   k.e1 = f2(a.e1, b.e1); k.e2 = f2(a.e2, b.e2); k.iE1 = f2(a.iE1, b.iE1); k.iE2 = f2(a.iE2, b.iE2); k.e1i = f2(a.e1i, b.e1i);
   return k;
 }
 
 // Rotation coefficients shared by forward and backward.
-template <typename T> struct RotCoef { T c, a, d, rs2; };
+template <typename T> struct RotCoef { T c, a, d, ne; };   // cos, sin/phi, (1 - cos)/phi^2, -(1 - sin/phi)/phi^2 (adjoint only)
 
 // fp32 "precise", common case |b| <= 2 pi: the rotation only needs a = sin(phi)/phi and d = (1 - cos(phi))/phi^2, both
 // EVEN entire functions of phi, i.e. functions of p2 = |b|^2 -- so neither the angle nor 1/phi is ever formed.  With the
 // half angle h = phi/2:  a = sinc(h) cos(h),  d = sinc(h)^2 / 2, and sinc(h), cos(h) are 7-term polynomials in p2 on
 // phi <= 2 pi (h <= pi: terms <= 1.7, no cancellation trouble).  Against MUFU.RSQ + Newton + Cody-Waite reduction + two
 // polynomials + sign fix-ups this is 12 FMAs with immediate coefficients and 3 multiplies: 21 FP32-pipe operations and 2
-// MUFU fewer per spin-step, at the same error (profiles/fit_halfangle.py: angle rms 4e-8, radius rms 1e-7, means 1e-8
-// on the bench distribution; the reduce-by-pi path: 8e-8, 1e-7, 8e-9).  Leading coefficients are exactly 1, so there is
-// no systematic scale (radius) error.  A step with |b| > MRPHY_HALF_PHIMAX (1.3e-5 of the spin-steps of the bench
-// distributions) takes the reduce-by-pi path below: one rarely taken branch per step.
+// MUFU fewer per spin-step, at the same error (profiles/fit_halfangle.py: angle rms 4e-8, radius rms 1e-7, means < 1e-8
+// on the bench distribution; the reduce-by-pi path: 8e-8, 1e-7, 8e-9; measured on the simulation, profiles/
+// host_accuracy.py: rms |dM| 0.9x, max 0.9x those of the reduce-by-pi path).  Leading coefficients are exactly 1, so
+// there is no systematic scale (radius) error.  A warp with a step of |b|^2 > MRPHY_HALF_P2MAX (2.7e-4 of the warp-steps
+// of the bench distributions, 1.3e-5 of the spin-steps) takes the reduce-by-pi path: one vote and a predicated-off call.
 #ifndef MRPHY_HALF_ANGLE
 #define MRPHY_HALF_ANGLE 1
+#endif
+#ifndef MRPHY_VOTE_MASK
+#define MRPHY_VOTE_MASK __activemask()   /* kernels whose loops run with all 32 lanes define it as 0xffffffffu before including this file */
 #endif
 #define MRPHY_HALF_P2MAX 40.0f   /* (2 pi * 1.0066)^2; the polynomials are fitted on [0, (2 pi * 1.02)^2] */
 MRPHY_HD bool any_gt(float a, float lim) { return a > lim; }
 MRPHY_HD bool any_gt(double a, double lim) { return a > lim; }
 MRPHY_HD bool any_gt(f2 a, float lim) { return fmaxf(a.v.x, a.v.y) > lim; }
-MRPHY_HD float rcp_(float x) {
-#if defined(__CUDA_ARCH__)
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // MUFU.RCP, 1 ulp: only scales the (1 - a)/|b|^2 term of the adjoint
-  return r;
-#else
-  return 1.0f / x;
-#endif
-}
-MRPHY_HD f2 rcp_(f2 x) { return f2(rcp_(x.v.x), rcp_(x.v.y)); }
 template <typename V> MRPHY_HD RotCoef<V> rot_coef_half(V p2) {
-#ifndef MRPHY_HALF_SET
-#define MRPHY_HALF_SET 0
-#endif
-#if MRPHY_HALF_SET == 2
-  V A = fma_(p2, V(-7.486010352e-17f), V(4.369235483e-14f));
-  A = fma_(A, p2, V(-2.472151477e-11f));
-  A = fma_(A, p2, V(1.077164669e-08f));
-  A = fma_(A, p2, V(-3.100295771e-06f));
-  A = fma_(A, p2, V(5.208339426e-04f));
-  A = fma_(A, p2, V(-4.166666791e-02f));
-#else
-  V A = fma_(p2, V(3.280267225e-14f), V(-2.409831189e-11f));
-  A = fma_(A, p2, V(1.075399236e-08f));
-  A = fma_(A, p2, V(-3.100041567e-06f));
-  A = fma_(A, p2, V(5.208322546e-04f));
-  A = fma_(A, p2, V(-4.166666418e-02f));
-#endif
-  A = fma_(A, p2, V(1.0f));                       // sinc(phi/2)
-#if MRPHY_HALF_SET == 0
-  V C = fma_(p2, V(4.191810202e-13f), V(-2.642699393e-10f));
-  C = fma_(C, p2, V(9.675193269e-08f));
-  C = fma_(C, p2, V(-2.169963955e-05f));
-  C = fma_(C, p2, V(2.604155801e-03f));
-  C = fma_(C, p2, V(-1.249999776e-01f));
-#else
-  V C = fma_(p2, V(-5.813414228e-16f), V(5.015682964e-13f));
-  C = fma_(C, p2, V(-2.688312073e-10f));
-  C = fma_(C, p2, V(9.687599345e-08f));
-  C = fma_(C, p2, V(-2.170134212e-05f));
-  C = fma_(C, p2, V(2.604166511e-03f));
-  C = fma_(C, p2, V(-1.250000000e-01f));
-#endif
-  C = fma_(C, p2, V(1.0f));                       // cos(phi/2)
+  // A = sinc(phi/2) = 1 + p2 PA(p2),  C = cos(phi/2) = 1 + p2 PC(p2)   (profiles/fit_halfangle.py, coefficients rounded
+  // to fp32 one at a time with the remaining ones refitted, so the means of the angle and radius errors stay < 1e-8)
+  V PA = fma_(p2, V(3.280267225e-14f), V(-2.409831189e-11f));
+  PA = fma_(PA, p2, V(1.075399236e-08f));
+  PA = fma_(PA, p2, V(-3.100041567e-06f));
+  PA = fma_(PA, p2, V(5.208322546e-04f));
+  PA = fma_(PA, p2, V(-4.166666418e-02f));
+  const V A = fma_(PA, p2, V(1.0f));
+  V PC = fma_(p2, V(4.191810202e-13f), V(-2.642699393e-10f));
+  PC = fma_(PC, p2, V(9.675193269e-08f));
+  PC = fma_(PC, p2, V(-2.169963955e-05f));
+  PC = fma_(PC, p2, V(2.604155801e-03f));
+  PC = fma_(PC, p2, V(-1.249999776e-01f));
+  const V C = fma_(PC, p2, V(1.0f));
   RotCoef<V> r;
   r.a = A * C;
   r.d = (A * V(0.5f)) * A;
   r.c = fnma_(p2, r.d, V(1.0f));
-  r.rs2 = rcp_(p2);                               // backward only (dead code in the forward)
+  // -(1 - a)/p2 without a division: 1 - A C = -p2 (PA + PC A)                     (adjoint only; dead code in the forward)
+  r.ne = fma_(PC, A, PA);
   return r;
 }
 
@@ -443,14 +438,33 @@ MRPHY_HD RotCoef<T> rot_coef_reduced(T p2) {
   RotCoef<T> r;
   r.c = c;
   r.a = s * rs;
-  r.rs2 = rs * rs;
-  r.d = fnma_(c, r.rs2, r.rs2);   // (1 - cos) / phi^2
+  const T rs2 = rs * rs;
+  r.d = fnma_(c, rs2, rs2);     // (1 - cos) / phi^2
+  r.ne = fms_(r.a, rs2, rs2);   // -(1 - sin/phi) / phi^2
   return r;
 }
 
 #ifndef MRPHY_HALF_BWD
 #define MRPHY_HALF_BWD 1
 #endif
+// the rare |b| > 2 pi path as a real call: the common path then carries one predicated-off CALL instead of a taken
+// branch around ~40 inlined instructions per step (-DMRPHY_HALF_INLINE_SLOW=1 inlines it again)
+#ifndef MRPHY_HALF_INLINE_SLOW
+#define MRPHY_HALF_INLINE_SLOW 0
+#endif
+#if defined(__CUDACC__) && !MRPHY_HALF_INLINE_SLOW
+template <typename T, int POL>
+__device__ __noinline__ RotCoef<T> rot_coef_reduced_call(T p2) { return rot_coef_reduced<T, POL>(p2); }
+#endif
+template <typename T, int POL>
+MRPHY_HD void rot_coef_slow(T p2, RotCoef<T>& r) {
+#if defined(__CUDA_ARCH__) && !MRPHY_HALF_INLINE_SLOW
+  r = rot_coef_reduced_call<T, POL>(p2);
+#else
+  r = rot_coef_reduced<T, POL>(p2);
+#endif
+}
+
 template <typename T, int POL, bool HALF_OK = true>
 MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
   T p2;
@@ -462,7 +476,13 @@ MRPHY_HD RotCoef<T> rot_coef(T bx, T by, T bz) {
     if (POL == TRIG_PRECISE && HALF_OK) {
       RotCoef<T> r = rot_coef_half<T>(p2);
 #ifndef MRPHY_HALF_NOFALLBACK   /* modelling builds only (profiles/model_all.py): the common path without the branch */
+      // the vote makes the branch warp-uniform: no divergence bookkeeping (BSSY/BSYNC) on the common path, and the
+      // reduce-by-pi coefficients are valid for every lane, so the whole warp may take them
+#if defined(__CUDA_ARCH__) && !defined(MRPHY_HALF_LANE_BRANCH)
+      if (__builtin_expect(__any_sync(MRPHY_VOTE_MASK, any_gt(p2, (typename Scalar<T>::type)MRPHY_HALF_P2MAX)), 0)) rot_coef_slow<T, POL>(p2, r);
+#else
       if (any_gt(p2, (typename Scalar<T>::type)MRPHY_HALF_P2MAX)) r = rot_coef_reduced<T, POL>(p2);
+#endif
 #endif
       return r;
     }
@@ -479,8 +499,10 @@ template <typename T, int NC>
 MRPHY_HD void field(const SpinConst<T, NC>& k, const T* rx, const T* ry, T gx, T gy, T gz, T& bx, T& by, T& bz) {
   bx = k.cbr[0] * rx[0];
   by = k.cbr[0] * ry[0];
-  bx = fnma_(k.cbi[0], ry[0], bx);
-  by = fma_(k.cbi[0], rx[0], by);
+  if (NC > 1) {
+    bx = fnma_(k.cbi[0], ry[0], bx);
+    by = fma_(k.cbi[0], rx[0], by);
+  }
 #pragma unroll
   for (int c = 1; c < NC; ++c) {
     bx = fma_(k.cbr[c], rx[c], bx);
@@ -491,9 +513,32 @@ MRPHY_HD void field(const SpinConst<T, NC>& k, const T* rx, const T* ry, T gx, T
   bz = fma_(k.glx, gx, fma_(k.gly, gy, fma_(k.glz, gz, k.gbz0)));
 }
 
+// lab frame <-> the spin's own transverse frame (NC == 1, see make_consts): v' = Rz(-arg b1) v, v = Rz(+arg b1) v'
+template <typename T, int NC> MRPHY_HD void to_frame(const SpinConst<T, NC>& k, T& x, T& y) {
+  if (NC == 1) {
+    const T x1 = fma_(k.fs, y, k.fc * x), y1 = fnma_(k.fs, x, k.fc * y);
+    x = x1; y = y1;
+  }
+}
+template <typename T, int NC> MRPHY_HD void from_frame(const SpinConst<T, NC>& k, T& x, T& y) {
+  if (NC == 1) {
+    const T x1 = fnma_(k.fs, y, k.fc * x), y1 = fma_(k.fs, x, k.fc * y);
+    x = x1; y = y1;
+  }
+}
+// chain rule of the field to the rf sample of coil q: (d/drx, d/dry) contributions of one spin, F = -dL/db
+template <typename T, int NC> MRPHY_HD void rf_chain(const SpinConst<T, NC>& k, int q, T Fx, T Fy, T& gx, T& gy) {
+  if (NC == 1) {
+    gx = k.cbr[0] * Fx;
+    gy = k.cbr[0] * Fy;
+  } else {
+    gx = fma_(k.cbr[q], Fx, k.cbi[q] * Fy);
+    gy = fnma_(k.cbi[q], Fx, k.cbr[q] * Fy);
+  }
+}
+
 // ---- forward step -------------------------------------------------------------------------
-// apply_fwd: the recurrent part (needs the previous state); rot_coef above is the part that only needs
-// the waveform, which the time-packed kernels evaluate for two consecutive steps in one f2.
+// apply_fwd: the recurrent part (needs the previous state); rot_coef above is the part that only needs the waveform.
 template <typename T, bool RELAX>
 MRPHY_HD void apply_fwd(const RotCoef<T>& r, T bx, T by, T bz, T e1, T e2, T& mx, T& my, T& mz) {
   T kk = r.d * fma_(bx, mx, fma_(by, my, bz * mz));
@@ -549,13 +594,13 @@ MRPHY_HD void apply_bwd(const SpinConst<T, NC>& k, const RotCoef<T>& r, T bx, T 
   // b.(m~ x h~) = -m~.wb:
   //     F = a (m~ x h~) + d (P m~ - Q h~) - e (m~.wb) b
   // (same value as the reference's closed form, sims.py:204-261, which is written in the pre-rotation state)
-  T E = fnma_(r.a, r.rs2, r.rs2) * fma_(tx, wx, fma_(ty, wy, tz * wz));
+  T E = r.ne * fma_(tx, wx, fma_(ty, wy, tz * wz));   // -e (m~.wb)
   T cx = fms_(ty, gz, tz * gy);
   T cy = fms_(tz, gx, tx * gz);
   T cz = fms_(tx, gy, ty * gx);
-  Fx = fnma_(E, bx, fnma_(kq, gx, fma_(kp, tx, r.a * cx)));
-  Fy = fnma_(E, by, fnma_(kq, gy, fma_(kp, ty, r.a * cy)));
-  Fz = fnma_(E, bz, fnma_(kq, gz, fma_(kp, tz, r.a * cz)));
+  Fx = fma_(E, bx, fnma_(kq, gx, fma_(kp, tx, r.a * cx)));
+  Fy = fma_(E, by, fnma_(kq, gy, fma_(kp, ty, r.a * cy)));
+  Fz = fma_(E, bz, fnma_(kq, gz, fma_(kp, tz, r.a * cz)));
   // h0 = c*h~ + kp*b + a*wb
   hx = fma_(r.a, wx, fma_(kp, bx, r.c * gx));
   hy = fma_(r.a, wy, fma_(kp, by, r.c * gy));
@@ -567,22 +612,6 @@ MRPHY_HD void step_bwd(const SpinConst<T, NC>& k, T bx, T by, T bz, T& mx, T& my
                        T& Fx, T& Fy, T& Fz) {
   const RotCoef<T> r = rot_coef<T, POL, MRPHY_HALF_BWD != 0>(bx, by, bz);
   apply_bwd<T, RELAX, NC>(k, r, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-}
-
-// ---- time-packed helpers: two consecutive time steps of ONE spin in an f2 ---------------------
-// The field and the rotation coefficients of a step depend only on the waveform, not on the state, so
-// steps (t, t+1) are evaluated together with packed arithmetic; per-spin constants enter as broadcast
-// scalars (FFMA2 ".F32" operand form, free).
-MRPHY_HD void field_tp(const SpinConst<float, 1>& k, f2 rx, f2 ry, f2 gx, f2 gy, f2 gz, f2& bx, f2& by, f2& bz) {
-  bx = fma_(f2(k.cbr[0]), rx, f2(-k.cbi[0]) * ry);
-  by = fma_(f2(k.cbr[0]), ry, f2(k.cbi[0]) * rx);
-  bz = fma_(f2(k.glx), gx, fma_(f2(k.gly), gy, fma_(f2(k.glz), gz, f2(k.gbz0))));
-}
-MRPHY_HD RotCoef<float> lane_x(const RotCoef<f2>& r) {
-  RotCoef<float> o; o.c = r.c.v.x; o.a = r.a.v.x; o.d = r.d.v.x; o.rs2 = r.rs2.v.x; return o;
-}
-MRPHY_HD RotCoef<float> lane_y(const RotCoef<f2>& r) {
-  RotCoef<float> o; o.c = r.c.v.y; o.a = r.a.v.y; o.d = r.d.v.y; o.rs2 = r.rs2.v.y; return o;
 }
 
 }  // namespace mrphy

@@ -6,7 +6,6 @@
 // Kernels in this file
 //   pack_waveform_kernel      rf (N,2,nT[,nC]), gr (N,3,nT) -> wave[N][chunk][W][TCP]  (W = 2*NC+3)
 //   fused_fwd_kernel<T,..>    one spin, or two spins packed in an f2 (FFMA2), per thread; checkpoint every K steps
-//   fused_*_tp_kernel         time-packed fp32 variant (one spin per thread, two steps' coefficients per f2)
 //   fused_bwd_kernel<T,..>    time-reversed state reconstruction + adjoint + spin reduction (only the gradient rows
 //                             asked for: ROWS); tiles owned through SM-aware virtual CTA ids (SCHED_*)
 //   grad_finalize_kernel<T>   deterministic sum of the per-CTA partials, reference layout out (grad_finalize.cuh)
@@ -25,6 +24,7 @@
 
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
+#define MRPHY_VOTE_MASK 0xffffffffu   /* every loop of the fused kernels runs with all lanes of the warp (padding lanes compute too) */
 #include "bloch_math.cuh"
 #include "ptx_helpers.cuh"
 #include "grad_finalize.cuh"
@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       load_consts_v<T, V, NC, PK, RELAX>(a, n, idx, lx, ly, lz, k);
     }
     load_vec3_tile<T, V, PK, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idx, scr, mx, my, mz);
+    to_frame(k, mx, my);   // single coil: the spin's own transverse frame (bloch_math.cuh: make_consts); checkpoints stay in it
     for (int c = 0; c < nChunks; ++c, ++it) {
       if (tid == 0 && it + 1 < total) {   // prefetch the next chunk (possibly chunk 0 of the next tile)
         const int cn = (c + 1 == nChunks) ? 0 : c + 1;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       }
       __syncthreads();   // everyone is done with wbuf[it&1] before it is refilled
     }
+    from_frame(k, mx, my);
     if (ok[0]) {
       T* op = a.Mo + ((size_t)n * nM + idx[0]) * 3;
       op[0] = getq<0>(mx); op[1] = getq<0>(my); op[2] = getq<0>(mz);
@@ -458,6 +460,8 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
     }
     load_vec3_tile<T, V, PK, BLKT>(a.Mo + (size_t)n * nM * 3, 3, tile, nM, idx, scr, mx, my, mz);
     load_vec3_tile<T, V, PK, BLKT>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, tile, nM, idx, scr, hx, hy, hz);
+    to_frame(k, mx, my);   // Mo and dL/dMo enter the spin's transverse frame, dL/dMi leaves it (single coil)
+    to_frame(k, hx, hy);
     {   // padding lanes carry a zero adjoint: they add nothing to the spin sums
       const T z0 = ok[0] ? (T)1 : (T)0, z1 = ok[PK - 1] ? (T)1 : (T)0;
       const V zm = mkv(z0, z1, (V*)nullptr);
@@ -491,8 +495,10 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         if constexpr (WANT_RF) {
 #pragma unroll
           for (int q = 0; q < NC; ++q) {
-            red[warp][q][row][lane] = hsum(fma_(k.cbr[q], Fx, k.cbi[q] * Fy));
-            red[warp][NC + q][row][lane] = hsum(fnma_(k.cbi[q], Fx, k.cbr[q] * Fy));
+            V gx_, gy_;
+            rf_chain<V, NC>(k, q, Fx, Fy, gx_, gy_);
+            red[warp][q][row][lane] = hsum(gx_);
+            red[warp][NC + q][row][lane] = hsum(gy_);
           }
         }
         if constexpr (WANT_GR) {
@@ -550,6 +556,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
       }
     }
     if (need_gmi) {
+      from_frame(k, hx, hy);
       if (ok[0]) {
         T* op = a.gMi + ((size_t)n * nM + idx[0]) * 3;
         op[0] = getq<0>(hx); op[1] = getq<0>(hy); op[2] = getq<0>(hz);
@@ -588,226 +595,6 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
   if (tid == 0 && blockIdx.x < 8192 && n == 0) g_cta_trace[blockIdx.x][2] = gtime();
 #endif
 }
-
-// ------------------------------------------------------------------------------------------
-// Time-packed variants (fp32, single coil): ONE spin per thread -- so twice the resident warps of the
-// spin-packed kernels for the same register file -- but the state-independent half of every step
-// (field, |b|, rsqrt, sincos, rotation coefficients) is evaluated for two consecutive time steps in
-// one f2 (FFMA2).  Only the short recurrent part (apply_fwd / apply_bwd) runs once per step in scalar.
-template <int POL, bool RELAX, int BLKT>
-__global__ void __launch_bounds__(BLKT) fused_fwd_tp_kernel(const KArgs<float> a) {
-  constexpr int W = 5;
-  __shared__ __align__(128) float wbuf[2][W * TCMAX];
-  __shared__ __align__(16) float scr[3 * BLKT];
-  __shared__ __align__(8) uint64_t full[2];
-  const int tid = threadIdx.x, n = blockIdx.y;
-  const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
-  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(float));
-  const float* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
-  const int tiles = (nM + BLKT - 1) / BLKT;
-  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
-  if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (tid == 0 && total > 0) {
-    mbar_arrive_expect_tx(&full[0], chunk_bytes);
-    bulk_g2s(wbuf[0], wave_n, chunk_bytes, &full[0]);
-  }
-  uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    SpinConst<float, 1> k;
-    const int i = tile * BLKT + tid;
-    const bool ok = i < nM;
-    const int idx = ok ? i : nM - 1;
-    const int idxv[1] = {idx};
-    float mx, my, mz;
-    {
-      float lx, ly, lz;
-      load_vec3_tile<float, float, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idxv, scr, lx, ly, lz);
-      load_spin<float, 1, RELAX>(a, n, idx, lx, ly, lz, k);
-    }
-    load_vec3_tile<float, float, 1, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idxv, scr, mx, my, mz);
-    for (int c = 0; c < nChunks; ++c, ++it) {
-      if (tid == 0 && it + 1 < total) {
-        const int cn = (c + 1 == nChunks) ? 0 : c + 1;
-        const uint32_t sn = (it + 1) & 1;
-        mbar_arrive_expect_tx(&full[sn], chunk_bytes);
-        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
-      }
-      mbar_wait(&full[it & 1], (it >> 1) & 1);
-      const float* wb = wbuf[it & 1];
-      const int ns = min(K, nT - c * K);
-      auto two_steps = [&](f2 rx, f2 ry, f2 gx, f2 gy, f2 gz) {   // .x = step t, .y = step t+1
-        f2 bx, by, bz;
-        field_tp(k, rx, ry, gx, gy, gz, bx, by, bz);
-        const RotCoef<f2> r = rot_coef<f2, POL>(bx, by, bz);
-        apply_fwd<float, RELAX>(lane_x(r), bx.v.x, by.v.x, bz.v.x, k.e1, k.e2, mx, my, mz);
-        apply_fwd<float, RELAX>(lane_y(r), bx.v.y, by.v.y, bz.v.y, k.e1, k.e2, mx, my, mz);
-      };
-      int j = 0;
-      for (; j + 4 <= ns; j += 4) {
-        float wv[W][4];
-#pragma unroll
-        for (int w = 0; w < W; ++w) load4(wb + w * TCP + j, wv[w]);
-        two_steps(f2(wv[0][0], wv[0][1]), f2(wv[1][0], wv[1][1]), f2(wv[2][0], wv[2][1]), f2(wv[3][0], wv[3][1]),
-                  f2(wv[4][0], wv[4][1]));
-        two_steps(f2(wv[0][2], wv[0][3]), f2(wv[1][2], wv[1][3]), f2(wv[2][2], wv[2][3]), f2(wv[3][2], wv[3][3]),
-                  f2(wv[4][2], wv[4][3]));
-      }
-      for (; j < ns; ++j) {
-        float bx, by, bz;
-        const float rx = wb[j], ry = wb[TCP + j];
-        field<float, 1>(k, &rx, &ry, wb[2 * TCP + j], wb[3 * TCP + j], wb[4 * TCP + j], bx, by, bz);
-        step_fwd<float, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
-      }
-      if (c + 1 < nChunks && ok) {
-        float* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
-        cp[idx] = mx; cp[(size_t)nM + idx] = my; cp[2 * (size_t)nM + idx] = mz;
-      }
-      __syncthreads();
-    }
-    if (ok) {
-      float* op = a.Mo + ((size_t)n * nM + idx) * 3;
-      op[0] = mx; op[1] = my; op[2] = mz;
-    }
-  }
-}
-
-template <int POL, bool RELAX, int BLKT>
-__global__ void __launch_bounds__(BLKT) fused_bwd_tp_kernel(const KArgs<float> a, const int need_gmi) {
-  using L = BwdSmem<float, 1, BLKT>;
-  constexpr int W = L::W, TR = L::TR, NW = L::NW;
-  static_assert(TR % 4 == 0, "time-packed backward expects 4-step groups");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float(*wbuf)[W * TCMAX] = reinterpret_cast<float(*)[W * TCMAX]>(smem_raw + L::wbuf);
-  float(*red)[W][TR][32] = reinterpret_cast<float(*)[W][TR][32]>(smem_raw + L::red);
-  float(*cta)[W][TR] = reinterpret_cast<float(*)[W][TR]>(smem_raw + L::cta);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::bar);
-  __shared__ __align__(16) float scr[3 * BLKT];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.y;
-  const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
-  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(float));
-  const float* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
-  const int tiles = (nM + BLKT - 1) / BLKT;
-  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
-  float* part = a.partials + ((size_t)n * a.P + blockIdx.x) * W * (size_t)nT;
-  if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (tid == 0 && total > 0) {
-    mbar_arrive_expect_tx(&full[0], chunk_bytes);
-    bulk_g2s(wbuf[0], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[0]);
-  }
-  if (my_tiles == 0) {
-    for (int e = tid; e < W * nT; e += BLKT) part[e] = 0.f;
-    return;
-  }
-  uint32_t it = 0, red_par = 0;
-  bool first = true;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, first = false) {
-    SpinConst<float, 1> k;
-    const int i = tile * BLKT + tid;
-    const bool ok = i < nM;
-    const int idx = ok ? i : nM - 1;
-    const int idxv[1] = {idx};
-    float mx, my, mz, hx, hy, hz;
-    {
-      float lx, ly, lz;
-      load_vec3_tile<float, float, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idxv, scr, lx, ly, lz);
-      load_spin<float, 1, RELAX>(a, n, idx, lx, ly, lz, k);
-    }
-    load_vec3_tile<float, float, 1, BLKT>(a.Mo + (size_t)n * nM * 3, 3, tile, nM, idxv, scr, mx, my, mz);
-    load_vec3_tile<float, float, 1, BLKT>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, tile, nM, idxv, scr, hx, hy, hz);
-    if (!ok) hx = hy = hz = 0.f;
-    auto emit = [&](float Fx, float Fy, float Fz, int row) {
-      red[warp][0][row][lane] = fmaf(k.cbr[0], Fx, k.cbi[0] * Fy);
-      red[warp][1][row][lane] = fmaf(-k.cbi[0], Fx, k.cbr[0] * Fy);
-      red[warp][2][row][lane] = k.glx * Fz;
-      red[warp][3][row][lane] = k.gly * Fz;
-      red[warp][4][row][lane] = k.glz * Fz;
-    };
-    for (int c = nChunks - 1; c >= 0; --c, ++it) {
-      if (tid == 0 && it + 1 < total) {
-        const int cn = (c == 0) ? nChunks - 1 : c - 1;
-        const uint32_t sn = (it + 1) & 1;
-        mbar_arrive_expect_tx(&full[sn], chunk_bytes);
-        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
-      }
-      float kx = mx, ky = my, kz = mz;
-      if (c > 0) {   // prefetch the checkpoint this chunk ends on
-        const float* cp = a.ckpt + ((size_t)n * (nChunks - 1) + (c - 1)) * 3 * (size_t)nM;
-        kx = cp[idx]; ky = cp[(size_t)nM + idx]; kz = cp[2 * (size_t)nM + idx];
-      }
-      mbar_wait(&full[it & 1], (it >> 1) & 1);
-      const float* wb = wbuf[it & 1];
-      const int ns = min(K, nT - c * K);
-      // .x = step t (row_lo), .y = step t+1 (row_lo+1); time runs backwards: .y first
-      auto two_steps = [&](f2 rx, f2 ry, f2 gx, f2 gy, f2 gz, int row_lo) {
-        f2 bx, by, bz;
-        field_tp(k, rx, ry, gx, gy, gz, bx, by, bz);
-        const RotCoef<f2> r = rot_coef<f2, POL>(bx, by, bz);
-        float Fx, Fy, Fz;
-        apply_bwd<float, RELAX, 1>(k, lane_y(r), bx.v.y, by.v.y, bz.v.y, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-        emit(Fx, Fy, Fz, row_lo + 1);
-        apply_bwd<float, RELAX, 1>(k, lane_x(r), bx.v.x, by.v.x, bz.v.x, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-        emit(Fx, Fy, Fz, row_lo);
-      };
-      for (int j1 = ns; j1 > 0;) {
-        const int j0 = ((j1 - 1) / TR) * TR;
-        if (j1 - j0 == TR) {
-#pragma unroll 1
-          for (int jj = TR - 4; jj >= 0; jj -= 4) {
-            float wv[W][4];
-#pragma unroll
-            for (int w = 0; w < W; ++w) load4(wb + w * TCP + j0 + jj, wv[w]);
-            two_steps(f2(wv[0][2], wv[0][3]), f2(wv[1][2], wv[1][3]), f2(wv[2][2], wv[2][3]), f2(wv[3][2], wv[3][3]),
-                      f2(wv[4][2], wv[4][3]), jj + 2);
-            two_steps(f2(wv[0][0], wv[0][1]), f2(wv[1][0], wv[1][1]), f2(wv[2][0], wv[2][1]), f2(wv[3][0], wv[3][1]),
-                      f2(wv[4][0], wv[4][1]), jj);
-          }
-        } else {
-          for (int j = j1 - 1; j >= j0; --j) {
-            float bx, by, bz, Fx, Fy, Fz;
-            const float rx = wb[j], ry = wb[TCP + j];
-            field<float, 1>(k, &rx, &ry, wb[2 * TCP + j], wb[3 * TCP + j], wb[4 * TCP + j], bx, by, bz);
-            step_bwd<float, POL, RELAX, 1>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-            emit(Fx, Fy, Fz, j - j0);
-          }
-        }
-        __syncwarp();
-        float(*ctab)[W][TR] = cta + (size_t)(red_par & 1) * NW;
-        warp_tile_reduce<float, W, TR>(red[warp], lane, ctab[warp]);
-        __syncthreads();
-        for (int e = tid; e < W * TR; e += BLKT) {
-          const int w = e / TR, r = e % TR;
-          if (j0 + r < j1) {
-            float sum = ctab[0][w][r];
-#pragma unroll
-            for (int q = 1; q < NW; ++q) sum += ctab[q][w][r];
-            float* dst = part + (size_t)w * nT + (c * K + j0 + r);
-            if (first) *dst = sum; else atomicAdd(dst, sum);
-          }
-        }
-        ++red_par;
-        j1 = j0;
-      }
-      if (c > 0) { mx = kx; my = ky; mz = kz; }
-    }
-    if (need_gmi && ok) {
-      float* op = a.gMi + ((size_t)n * nM + idx) * 3;
-      op[0] = hx; op[1] = hy; op[2] = hz;
-    }
-  }
-}
-
 
 }  // namespace mrphy
 
@@ -920,10 +707,14 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   p->K = a->K;
   p->TCP = (a->K + 3) & ~3;
   p->nChunks = (a->nT + a->K - 1) / a->K;
-  // fp32 single-coil fast paths (FFMA2): 2 = two spins per thread (default, fastest measured); 3 = time-packed,
-  // one spin per thread; MRPHY_B200_PACK=1 forces the scalar kernels that also serve fp64 and multi-coil
+  // fp32 single coil: two spins per thread, packed FFMA2 arithmetic.  fp64 and multi-coil: one spin per thread (scalar
+  // kernels); a build with -DMRPHY_FP32_SCALAR also carries the fp32 single-coil scalar kernels (MRPHY_B200_PACK=1)
+#ifdef MRPHY_FP32_SCALAR
   const int want = env_int("MRPHY_B200_PACK", 2);
-  p->PK = (a->dtype == MRPHY_F32 && p->NC == 1 && (want == 2 || want == 3)) ? want : 1;
+#else
+  const int want = 2;
+#endif
+  p->PK = (a->dtype == MRPHY_F32 && p->NC == 1 && want == 2) ? 2 : 1;
   p->BLKT = p->PK == 2 ? 64 : 128;
   p->tiles = (a->nM + p->BLKT * (p->PK == 2 ? 2 : 1) - 1) / (p->BLKT * (p->PK == 2 ? 2 : 1));
   const int sms = need_device ? sm_count_cached() : 148;
@@ -1085,38 +876,9 @@ int launch_any(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStr
              : launch_fwd_s<T, POL, RELAX, NC, PK, BLKT>(k, p, st);
 }
 
-template <int POL, bool RELAX, int BLKT>
-int launch_tp(bool bwd, KArgs<float> k, const Plan& p, int need_gmi, cudaStream_t st) {
-  int occ = 0;
-  if (bwd) {
-    constexpr size_t smem = BwdSmem<float, 1, BLKT>::bytes;
-    auto kern = fused_bwd_tp_kernel<POL, RELAX, BLKT>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, smem));
-    k.P = pick_ctas(p, k.N, occ);
-    g_last_P = k.P;
-    timing_begin(st);
-    kern<<<dim3(k.P, k.N), BLKT, smem, st>>>(k, need_gmi);
-    timing_end(st);
-  } else {
-    auto kern = fused_fwd_tp_kernel<POL, RELAX, BLKT>;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLKT, 0));
-    k.P = pick_ctas(p, k.N, occ);
-    timing_begin(st);
-    kern<<<dim3(k.P, k.N), BLKT, 0, st>>>(k);
-    timing_end(st);
-  }
-  ++g_launches;
-  CK(cudaGetLastError());
-  return MRPHY_OK;
-}
-
 template <typename T, int POL, bool RELAX>
 int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
   if constexpr (sizeof(T) == 4) {
-#ifndef MRPHY_ONLY_PK2
-    if (p.PK == 3) return launch_tp<POL, RELAX, 128>(bwd, k, p, need_gmi, st);
-#endif
     if (p.PK == 2) {
       if (!bwd) return launch_fwd_s<T, POL, RELAX, 1, 2, 64>(k, p, st);
       if (p.rows == 1) return launch_bwd_s<T, POL, RELAX, 1, 2, MRPHY_BWD_BLKT, 1>(k, p, need_gmi, st);   // dL/drf only
@@ -1128,7 +890,12 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
   return fail(MRPHY_ERR_ARG, "built with MRPHY_ONLY_PK2%s");
 #else
   switch (p.NC) {
-    case 1: return launch_any<T, POL, RELAX, 1, 1, 128>(bwd, k, p, need_gmi, st);
+    case 1:
+#ifndef MRPHY_FP32_SCALAR
+      if constexpr (sizeof(T) == 4) return fail(MRPHY_ERR_ARG, "internal: fp32 single-coil scalar kernels not built%s");
+      else
+#endif
+      return launch_any<T, POL, RELAX, 1, 1, 128>(bwd, k, p, need_gmi, st);
     case 2: return launch_any<T, POL, RELAX, 2, 1, 128>(bwd, k, p, need_gmi, st);
     case 4: return launch_any<T, POL, RELAX, 4, 1, 128>(bwd, k, p, need_gmi, st);
     case 8: return launch_any<T, POL, RELAX, 8, 1, 128>(bwd, k, p, need_gmi, st);

@@ -161,8 +161,9 @@ def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flag
 
 def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
                        df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
-                       gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """-> (gMi (N,nM,3) or empty, grf like rf or empty (FLAG_SKIP_GRF), ggr (N,3,nT) or empty (FLAG_SKIP_GGR))."""
+                       gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
+    """-> (gMi (N,nM,3) or empty, flat): flat = [dL/drf like rf (absent with FLAG_SKIP_GRF) | dL/dgr (N,3,nT) (absent with
+    FLAG_SKIP_GGR) | GRAD_TAIL spare elements, zero]; `split_wave_grads` cuts the views."""
     L = _cabi.lib()
     a = _cabi.FusedArgs()
     _fill_common(a, None, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
@@ -170,8 +171,13 @@ def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor
     need_gmi = bool(flags & _cabi.FLAG_NEED_GMI)
     gMi = torch.empty((a.N, a.nM, 3) if need_gmi else (0,), **kw)
     want_rf, want_gr = not flags & _cabi.FLAG_SKIP_GRF, not flags & _cabi.FLAG_SKIP_GGR
-    grf = torch.empty(rf.shape if want_rf else (0,), **kw)
-    ggr = torch.empty((a.N, 3, a.nT) if want_gr else (0,), **kw)
+    # ONE flat buffer [dL/drf | dL/dgr | GRAD_TAIL spare elements]: both gradients are views of it, so a sharded run sums
+    # them over ranks with a single in-place all-reduce of the buffer (mrphy.parallel), the spare tail carrying the loss
+    n_rf, n_gr = (rf.numel() if want_rf else 0), (a.N * 3 * a.nT if want_gr else 0)
+    flat = torch.empty(n_rf + n_gr + GRAD_TAIL, **kw)
+    flat[n_rf + n_gr:].zero_()
+    grf = flat[:n_rf].view(rf.shape) if want_rf else flat[:0]
+    ggr = flat[n_rf:n_rf + n_gr].view(a.N, 3, a.nT) if want_gr else flat[:0]
     partials = torch.empty(L.mrphy_fused_partial_elems(a), **kw)
     a.Mo, a.ckpt, a.wave = Mo.data_ptr(), ckpt.data_ptr(), wave.data_ptr()
     a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
@@ -180,13 +186,23 @@ def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor
     with torch.cuda.device(Mo.device):
         _cabi.check(L.mrphy_blochsim_fused_bwd(a, 1, _stream()), 'blochsim_fused_bwd')
     _cabi.count_launches()
-    return gMi, grf, ggr
+    return gMi, flat
 
 
 def _fake_blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
-    return (Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)),
-            Mo.new_empty((0,) if flags & _cabi.FLAG_SKIP_GRF else rf.shape),
-            Mo.new_empty((0,) if flags & _cabi.FLAG_SKIP_GGR else (rf.shape[0], 3, rf.shape[2])))
+    n = (0 if flags & _cabi.FLAG_SKIP_GRF else rf.numel()) + (0 if flags & _cabi.FLAG_SKIP_GGR else rf.shape[0] * 3 * rf.shape[2])
+    return Mo.new_empty(Mo.shape if flags & _cabi.FLAG_NEED_GMI else (0,)), Mo.new_empty((n + GRAD_TAIL,))
+
+
+GRAD_TAIL = 4      # spare elements behind the waveform gradients (16-byte granule); [0] is where `parallel` puts the loss
+
+
+def split_wave_grads(flat: Tensor, rf: Tensor, flags: int):
+    """(dL/drf, dL/dgr) as views of the backward's flat buffer (None where skipped)."""
+    N, nT = rf.shape[0], rf.shape[2]
+    n_rf = 0 if flags & _cabi.FLAG_SKIP_GRF else rf.numel()
+    n_gr = 0 if flags & _cabi.FLAG_SKIP_GGR else N * 3 * nT
+    return (flat[:n_rf].view(rf.shape) if n_rf else None), (flat[n_rf:n_rf + n_gr].view(N, 3, nT) if n_gr else None)
 
 
 def _fused_setup(ctx, inputs, output):
@@ -211,8 +227,9 @@ def _fused_backward(ctx, gMo, _gckpt, _gwave):
     # only the gradients autograd asks for: the rows of the spin reduction of the others are not even formed
     flags = ctx.flags | (_cabi.FLAG_NEED_GMI if need[0] else 0) | (0 if need[1] else _cabi.FLAG_SKIP_GRF) | \
         (0 if need[2] else _cabi.FLAG_SKIP_GGR)
-    gMi, grf, ggr = blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags)
-    return (gMi if need[0] else None, grf if need[1] else None, ggr if need[2] else None) + (None,) * 9
+    gMi, flat = blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags)
+    grf, ggr = split_wave_grads(flat, rf, flags)
+    return (gMi if need[0] else None, grf, ggr) + (None,) * 9
 
 
 
@@ -580,7 +597,7 @@ def _mask_backward(ctx, g):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -701,17 +718,20 @@ def set_trig_policy(name: Optional[str]) -> None:
 
 
 def trig_policy() -> str:
-    """fp32 arithmetic policy (ignored for fp64 tensors): `set_trig_policy`, else MRPHY_B200_TRIG, else 'mixed'.
+    """fp32 arithmetic policy (ignored for fp64 tensors): `set_trig_policy`, else MRPHY_B200_TRIG, else 'precise'.
 
-    precise  rotation coefficients from half-angle polynomials on the FMA pipe (|b| <= 2 pi; Cody-Waite reduction +
-             Newton-refined rsqrt beyond), forward and adjoint: M at 0.7-0.9x the reference's own fp32 error.
-    mixed    (default) the same forward -- M is bit-identical to 'precise' -- and MUFU.SIN/COS/RSQ in the adjoint kernel:
-             rf/gr gradients 1-4e-5 relative instead of 0.5-1e-5 (the reference's own fp32: 1.5-5e-5; tolerance 1e-4).
-    fast     MUFU trigonometry everywhere: ~2x the reference's fp32 error on M at nT ~ 1000.
-    strict   fp32 tensors in and out, fp64 arithmetic inside (the fp64 kernels): M within 1e-5 -- in fact 1e-6 -- of the
+    precise  (default) rotation coefficients from half-angle polynomials on the FMA pipe (|b| <= 2 pi; Cody-Waite reduction
+             + Newton-refined rsqrt beyond), forward and adjoint.  Measured at full size against the fp64 oracle (B200):
+             M 0.7-0.8x the reference algorithm's own fp32 error, rf/gr gradients 4e-6 (nT=1000) ... 1e-5 (nT=2000)
+             relative -- the reference's own fp32 gradients: 2e-5 ... 5e-5; north_star tolerance 1e-4.
+    mixed    the same forward -- M is bit-identical to 'precise' -- and MUFU.SIN/COS/RSQ in the adjoint kernel (~6 % faster):
+             the MUFU bias makes the gradient error grow with nT, 4.5e-5 at nT=1000, 8.6e-5 at nT=2000: fine for short
+             pulses, outside 1e-4 beyond nT ~ 2000, hence opt-in.
+    fast     MUFU trigonometry everywhere: ~1.5-2x the reference's fp32 error on M, gradients 5e-5 ... 1.3e-4.
+    strict   fp32 tensors in and out, fp64 arithmetic inside (the fp64 kernels): M within 1e-5 -- in fact 3e-8 -- of the
              reference's fp64 result at every nT, which no fp32 evaluation of this recurrence, the reference's own included,
              achieves beyond nT ~ 500; costs ~2.7x the time."""
-    pol = _policy_override or os.environ.get('MRPHY_B200_TRIG', 'mixed')
+    pol = _policy_override or os.environ.get('MRPHY_B200_TRIG', 'precise')
     if pol not in TRIG_POLICIES:
         raise ValueError(f'MRPHY_B200_TRIG={pol!r}: expected one of {TRIG_POLICIES}')
     return pol

@@ -16,7 +16,7 @@ from torch import Tensor
 
 from mrphy import mobjs
 
-__all__ = ['shard_range', 'shard_spins', 'allreduce_waveform_grads']
+__all__ = ['shard_range', 'shard_spins', 'allreduce_waveform_grads', 'flat_wave_grads']
 
 
 def shard_range(nM: int, rank: int, world: int) -> Tuple[int, int]:
@@ -46,10 +46,42 @@ def shard_spins(obj, rank: int, world: int, *, loc_: Optional[Tensor] = None, Δ
     return local, {'loc_': cut(loc_).contiguous(), 'Δf_': cut(Δf_), 'b1Map_': cut(b1Map_)}
 
 
+def flat_wave_grads(rf: Tensor, gr: Tensor) -> Optional[Tensor]:
+    """The fused backward writes ``rf.grad`` and ``gr.grad`` into ONE buffer ``[rf.grad | gr.grad | GRAD_TAIL spare]``
+    (``mrphy._ops``); autograd hands both views to the leaves unchanged.  Returns that buffer as a 1-D tensor, or None
+    when the gradients are separate tensors (accumulated over several backward calls, produced by other operators...)."""
+    from mrphy import _ops
+    a, b = rf.grad, gr.grad
+    if a is None or b is None or a.dtype != b.dtype or not (a.is_contiguous() and b.is_contiguous()):
+        return None
+    sa = a.untyped_storage()
+    if sa.data_ptr() != b.untyped_storage().data_ptr() or b.storage_offset() != a.storage_offset() + a.numel():
+        return None
+    n = a.numel() + b.numel() + _ops.GRAD_TAIL
+    if (a.storage_offset() + n) * a.element_size() > sa.nbytes():
+        return None
+    return torch.empty(0, dtype=a.dtype, device=a.device).set_(sa, a.storage_offset(), (n,), (1,))
+
+
 def allreduce_waveform_grads(rf: Tensor, gr: Tensor, *extras: Tensor, group=None) -> None:
-    """Sum ``rf.grad``, ``gr.grad`` (and any extra tensors, e.g. the scalar loss) over ranks, in place,
-    with ONE all-reduce on a flat buffer."""
+    """Sum ``rf.grad``, ``gr.grad`` (and any extra tensors, e.g. the scalar loss) over ranks, in place, with ONE
+    all-reduce.  After a fused backward the gradients already live in one flat buffer: the extras (up to GRAD_TAIL
+    elements) ride in its spare tail and the collective runs in place on it -- no gather, no scatter; captured into a
+    CUDA graph with the step it costs no launch of its own.  Otherwise the parts are concatenated and copied back."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    from mrphy import _ops
+    flat = flat_wave_grads(rf, gr)
+    if flat is not None and sum(e.numel() for e in extras) <= _ops.GRAD_TAIL:
+        off = flat.numel() - _ops.GRAD_TAIL
+        slots = []
+        for e in extras:
+            slots.append(flat[off:off + e.numel()])
+            slots[-1].copy_(e.reshape(-1))
+            off += e.numel()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        for e, sl in zip(extras, slots):
+            e.copy_(sl.reshape(e.shape))
         return
     parts = [rf.grad, gr.grad, *extras]
     flat = torch.cat([p.reshape(-1) for p in parts])

@@ -9,7 +9,7 @@ g = torch.Generator().manual_seed(0)
 U = lambda *s, dt=torch.float32: (torch.rand(s, generator=g, dtype=torch.float64) * 2 - 1).to(dt).to(dev)
 for dt in (torch.float32, torch.float64):
     for pack in ('1', '2', '3'):
-        os.environ['MRPHY_B200_PACK'] = pack
+        os.environ['MRPHY_B200_PACK'] = pack   # only honoured by -DMRPHY_FP32_SCALAR builds
         for (N, nM, nT, nC) in ((2, 131, 70, 1), (1, 65, 33, 3), (1, 200, 129, 0)):
             rf = U(N, 2, nT, nC, dt=dt) if nC else U(N, 2, nT, dt=dt)
             rf.requires_grad_(True)

@@ -20,6 +20,7 @@ static void run(int nM, int nT, int K, const T* M0, const T* rf /*[2][nT]*/, con
     make_consts<T, 1>(k, gamma[i], dt, RELAX, RELAX ? T1[i] : 1.0, RELAX ? T2[i] : 1.0, df ? df[i] : 0.0,
                       loc[3 * i], loc[3 * i + 1], loc[3 * i + 2], &br, &bi);
     T mx = M0[3 * i], my = M0[3 * i + 1], mz = M0[3 * i + 2];
+    to_frame(k, mx, my);
     std::vector<T> ck;
     for (int t = 0; t < nT; ++t) {
       if (t > 0 && t % K == 0) { ck.push_back(mx); ck.push_back(my); ck.push_back(mz); }
@@ -27,14 +28,17 @@ static void run(int nM, int nT, int K, const T* M0, const T* rf /*[2][nT]*/, con
       field<T, 1>(k, &rf[t], &rf[nT + t], gr[t], gr[nT + t], gr[2 * nT + t], bx, by, bz);
       step_fwd<T, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
     }
-    Mo[3 * i] = mx; Mo[3 * i + 1] = my; Mo[3 * i + 2] = mz;
+    { T ox = mx, oy = my; from_frame(k, ox, oy); Mo[3 * i] = ox; Mo[3 * i + 1] = oy; Mo[3 * i + 2] = mz; }
     T hx = gMo[3 * i], hy = gMo[3 * i + 1], hz = gMo[3 * i + 2];
+    to_frame(k, hx, hy);
     for (int t = nT - 1; t >= 0; --t) {
       T bx, by, bz, Fx, Fy, Fz;
       field<T, 1>(k, &rf[t], &rf[nT + t], gr[t], gr[nT + t], gr[2 * nT + t], bx, by, bz);
       step_bwd<T, POL, RELAX, 1>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-      grf[t] -= (double)(k.cbr[0] * Fx + k.cbi[0] * Fy);
-      grf[nT + t] -= (double)(k.cbr[0] * Fy - k.cbi[0] * Fx);
+      T rgx, rgy;
+      rf_chain(k, 0, Fx, Fy, rgx, rgy);
+      grf[t] -= (double)rgx;
+      grf[nT + t] -= (double)rgy;
       ggr[t] -= (double)(k.glx * Fz);
       ggr[nT + t] -= (double)(k.gly * Fz);
       ggr[2 * nT + t] -= (double)(k.glz * Fz);
@@ -46,6 +50,7 @@ static void run(int nM, int nT, int K, const T* M0, const T* rf /*[2][nT]*/, con
         mx = ck[3 * c]; my = ck[3 * c + 1]; mz = ck[3 * c + 2];
       }
     }
+    from_frame(k, hx, hy);
     gM0[3 * i] = hx; gM0[3 * i + 1] = hy; gM0[3 * i + 2] = hz;
   }
   *resync_err = maxerr;
@@ -68,6 +73,7 @@ static void run2(int nM, int nT, int K, const float* M0, const float* rf, const 
     }
     const SpinConst<f2, 1> k = pack2<1>(ks[0], ks[1]);
     f2 mx(M0[3 * i], M0[3 * i + 3]), my(M0[3 * i + 1], M0[3 * i + 4]), mz(M0[3 * i + 2], M0[3 * i + 5]);
+    to_frame(k, mx, my);
     std::vector<f2> ck;
     for (int t = 0; t < nT; ++t) {
       if (t > 0 && t % K == 0) { ck.push_back(mx); ck.push_back(my); ck.push_back(mz); }
@@ -75,15 +81,22 @@ static void run2(int nM, int nT, int K, const float* M0, const float* rf, const 
       field<f2, 1>(k, &rx, &ry, f2(gr[t]), f2(gr[nT + t]), f2(gr[2 * nT + t]), bx, by, bz);
       step_fwd<f2, POL, RELAX>(bx, by, bz, k.e1, k.e2, mx, my, mz);
     }
-    Mo[3 * i] = mx.v.x; Mo[3 * i + 1] = my.v.x; Mo[3 * i + 2] = mz.v.x;
-    Mo[3 * i + 3] = mx.v.y; Mo[3 * i + 4] = my.v.y; Mo[3 * i + 5] = mz.v.y;
+    {
+      f2 ox = mx, oy = my;
+      from_frame(k, ox, oy);
+      Mo[3 * i] = ox.v.x; Mo[3 * i + 1] = oy.v.x; Mo[3 * i + 2] = mz.v.x;
+      Mo[3 * i + 3] = ox.v.y; Mo[3 * i + 4] = oy.v.y; Mo[3 * i + 5] = mz.v.y;
+    }
     f2 hx(gMo[3 * i], gMo[3 * i + 3]), hy(gMo[3 * i + 1], gMo[3 * i + 4]), hz(gMo[3 * i + 2], gMo[3 * i + 5]);
+    to_frame(k, hx, hy);
     for (int t = nT - 1; t >= 0; --t) {
       f2 bx, by, bz, Fx, Fy, Fz, rx(rf[t]), ry(rf[nT + t]);
       field<f2, 1>(k, &rx, &ry, f2(gr[t]), f2(gr[nT + t]), f2(gr[2 * nT + t]), bx, by, bz);
       step_bwd<f2, POL, RELAX, 1>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
-      grf[t] -= (double)hsum(fma_(k.cbr[0], Fx, k.cbi[0] * Fy));
-      grf[nT + t] -= (double)hsum(fnma_(k.cbi[0], Fx, k.cbr[0] * Fy));
+      f2 rgx, rgy;
+      rf_chain(k, 0, Fx, Fy, rgx, rgy);
+      grf[t] -= (double)hsum(rgx);
+      grf[nT + t] -= (double)hsum(rgy);
       ggr[t] -= (double)hsum(k.glx * Fz);
       ggr[nT + t] -= (double)hsum(k.gly * Fz);
       ggr[2 * nT + t] -= (double)hsum(k.glz * Fz);
@@ -94,6 +107,7 @@ static void run2(int nM, int nT, int K, const float* M0, const float* rf, const 
         mx = ck[3 * c]; my = ck[3 * c + 1]; mz = ck[3 * c + 2];
       }
     }
+    from_frame(k, hx, hy);
     gM0[3 * i] = hx.v.x; gM0[3 * i + 1] = hy.v.x; gM0[3 * i + 2] = hz.v.x;
     gM0[3 * i + 3] = hx.v.y; gM0[3 * i + 4] = hy.v.y; gM0[3 * i + 5] = hz.v.y;
   }
