@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MRPHY_ABI_VERSION 2
+#define MRPHY_ABI_VERSION 3
 
 enum mrphy_dtype { MRPHY_F32 = 0, MRPHY_F64 = 1 };
 
@@ -222,6 +222,23 @@ typedef struct mrphy_reparam_args {
 } mrphy_reparam_args;
 int mrphy_design_waveform(const mrphy_reparam_args* a, void* cuda_stream);
 
+/* Amplitude limits of the design loop, replacing utils.rfclamp (utils.py:217-236) and utils.sclamp
+ * (utils.py:278-293) and their autograd, one launch each way:
+ *   kind 1  rf (N,2,nT,nC):  out = rf * min((rfmax[n,c] - eps) / |rf|, 1),  |rf| over the xy axis
+ *   kind 2  s  (N,3,nT):     out = min(max(s, -smax[n,x]), smax[n,x])
+ * adjoint != 0: from g = dL/dout write gx = dL/dx -- inside the limit g; kind 1 outside: (lim/|rf|) (g - (g.rf) rf/|rf|^2)
+ * (the radial part is cut); kind 2 outside: 0, exactly on the limit g/2 (torch's maximum/minimum tie rule).        */
+typedef struct mrphy_clamp_args {
+  int32_t dtype, adjoint;
+  int32_t kind, N, nT, nC;              /* nC: trailing coil dimension of rf (1 when absent; kind 2: 1)                 */
+  const void* x;                        /* rf (N,2,nT,nC) | s (N,3,nT), contiguous                                      */
+  const void* lim; int64_t lim_sn, lim_sc;   /* rfmax: element (n,c) at lim[n*sn + c*sc]; smax: (n,x) likewise           */
+  double eps;                           /* kind 1 only                                                                  */
+  const void* g;                        /* adjoint in, like x                                                           */
+  void* out;                            /* forward: clamped x; adjoint: dL/dx                                           */
+} mrphy_clamp_args;
+int mrphy_clamp_waveform(const mrphy_clamp_args* a, void* cuda_stream);
+
 /* Mask gather of the spin axis (mobjs.SpinArray.extract / .embed, mobjs.py:512-553) as ONE pass over the output:
  *   out[n, j, :] = idx[j] >= 0 ? in[n, idx[j], :] : NaN        j in [0, nOut), `inner` trailing elements per spin
  * extract: idx = row-major positions of the mask's True entries (nOut = nM, nIn = prod(Nd));
@@ -239,7 +256,8 @@ int mrphy_mask_copy(const mrphy_mask_args* a, void* cuda_stream);
 
 /* sizeof() of the argument structs as this library was compiled, for bindings to check their mirror of the layout:
  * which = 0 mrphy_param, 1 mrphy_fused_args, 2 mrphy_beff_args, 3 mrphy_rfgr2beff_args, 4 mrphy_beff2ab_args,
- * 5 mrphy_beff2uphi_args, 6 mrphy_freeprec_args, 7 mrphy_reparam_args, 8 mrphy_mask_args; 0 for any other value. */
+ * 5 mrphy_beff2uphi_args, 6 mrphy_freeprec_args, 7 mrphy_reparam_args, 8 mrphy_mask_args, 9 mrphy_clamp_args; 0 for any
+ * other value. */
 size_t mrphy_sizeof_args(int which);
 
 /* Number of kernel launches the last forward / backward call on this thread issued. */

@@ -447,6 +447,7 @@ extern "C" size_t mrphy_sizeof_args(int which) {
     case 6: return sizeof(mrphy_freeprec_args);
     case 7: return sizeof(mrphy_reparam_args);
     case 8: return sizeof(mrphy_mask_args);
+    case 9: return sizeof(mrphy_clamp_args);
   }
   return 0;
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('MRPHY_B200_LIB') or os.path.join(os.path.dirname(_HER
 MRPHY_F32, MRPHY_F64 = 0, 1
 FLAG_TRIG_PRECISE, FLAG_NEED_GMI, FLAG_RF_COIL_DIM, FLAG_NEED_GBEFF, FLAG_TRIG_FAST_BWD = 1, 2, 4, 8, 16
 FLAG_SKIP_GRF, FLAG_SKIP_GGR = 32, 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 
@@ -109,6 +109,14 @@ class MaskArgs(ctypes.Structure):
     ]
 
 
+class ClampArgs(ctypes.Structure):
+    _fields_ = [
+        ('dtype', c_i32), ('adjoint', c_i32), ('kind', c_i32), ('N', c_i32), ('nT', c_i32), ('nC', c_i32),
+        ('x', c_vp), ('lim', c_vp), ('lim_sn', c_i64), ('lim_sc', c_i64), ('eps', ctypes.c_double),
+        ('g', c_vp), ('out', c_vp),
+    ]
+
+
 EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mrphy_b200.h declares
     'mrphy_abi_version': (ctypes.c_int, []),
     'mrphy_last_error': (ctypes.c_char_p, []),
@@ -135,6 +143,7 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_freeprec': (ctypes.c_int, [ctypes.POINTER(FreePrecArgs), c_vp]),
     'mrphy_design_waveform': (ctypes.c_int, [ctypes.POINTER(ReparamArgs), c_vp]),
     'mrphy_mask_copy': (ctypes.c_int, [ctypes.POINTER(MaskArgs), c_vp]),
+    'mrphy_clamp_waveform': (ctypes.c_int, [ctypes.POINTER(ClampArgs), c_vp]),
 }
 
 _lib = None
@@ -161,7 +170,7 @@ def lib():
                     raise RuntimeError(f'mrphy (B200): ABI version mismatch: library {L.mrphy_abi_version()} '
                                        f'!= binding {ABI_VERSION}; rebuild with mrphy.py_b200/build.py')
                 mirrors = (Param, FusedArgs, BeffArgs, RfGr2BeffArgs, Beff2abArgs, Beff2uphiArgs, FreePrecArgs, ReparamArgs,
-                           MaskArgs)
+                           MaskArgs, ClampArgs)
                 for which, cls in enumerate(mirrors):
                     if L.mrphy_sizeof_args(which) != ctypes.sizeof(cls):
                         raise RuntimeError(f'mrphy (B200): layout of {cls.__name__} ({ctypes.sizeof(cls)} B) differs from '

@@ -562,6 +562,45 @@ def _design_backward(ctx, grf, ggr):
     return (grho if rf_kind else None, gtheta if rf_kind else None, None, gts if gr_kind else None, None, None, None, None)
 
 
+def _clamp_call(x: Tensor, lim: Tensor, eps: float, kind: int, g: Optional[Tensor]) -> Tensor:
+    L = _cabi.lib()
+    a = _cabi.ClampArgs()
+    a.dtype = _cabi.MRPHY_F64 if x.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.adjoint, a.kind, a.N, a.nT = int(g is not None), kind, x.shape[0], x.shape[2]
+    a.nC = x.shape[3] if (kind == 1 and x.ndim == 4) else 1
+    v = lim.expand((x.shape[0], a.nC if kind == 1 else 3))            # (N|1, nC|1 or 3|1) -> strides, 0 where broadcast
+    a.x, a.lim, a.lim_sn, a.lim_sc, a.eps = x.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), float(eps)
+    out = torch.empty_like(x)
+    a.out = out.data_ptr()
+    if g is not None:
+        a.g = g.data_ptr()
+    with torch.cuda.device(x.device):
+        _cabi.check(L.mrphy_clamp_waveform(a, _stream()), 'clamp_waveform')
+    _cabi.count_launches()
+    return out
+
+
+def _impl_clamp_waveform(x: Tensor, lim: Tensor, eps: float, kind: int) -> Tensor:
+    """kind 1: utils.rfclamp of rf (N,2,nT[,nC]) at rfmax `lim` (N|1, nC|1) - eps; kind 2: utils.sclamp of s (N,3,nT) at
+    `lim` (N|1, 3|1).  x contiguous."""
+    return _clamp_call(x, lim, eps, kind, None)
+
+
+def _impl_clamp_waveform_bwd(g: Tensor, x: Tensor, lim: Tensor, eps: float, kind: int) -> Tensor:
+    return _clamp_call(x, lim, eps, kind, g)
+
+
+def _clamp_setup(ctx, inputs, output):
+    x, lim, eps, kind = inputs
+    ctx.save_for_backward(x, lim)
+    ctx.eps, ctx.kind = eps, kind
+
+
+def _clamp_backward(ctx, g):
+    x, lim = ctx.saved_tensors
+    return clamp_waveform_bwd_cuda(g.contiguous(), x, lim, ctx.eps, ctx.kind), None, None, None
+
+
 def _impl_mask_copy(v: Tensor, idx: Tensor, inv: Tensor, fill_zero: bool) -> Tensor:
     """v (N,nIn,inner) contiguous, idx (nOut,) int64 -> out[n,j] = v[n,idx[j]], rows with idx[j] < 0 are NaN (or 0).
     ``inv`` (nIn,) is the inverse map; only the backward uses it."""
@@ -597,7 +636,7 @@ def _mask_backward(ctx, g):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor', 'clamp_waveform': '(Tensor x, Tensor lim, float eps, int kind) -> Tensor', 'clamp_waveform_bwd': '(Tensor g, Tensor x, Tensor lim, float eps, int kind) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -621,9 +660,12 @@ freeprec_cuda = _register('freeprec', _impl_freeprec, _fake_freeprec)
 design_waveform_cuda = _register('design_waveform', _impl_design_waveform, _fake_design_waveform)
 design_waveform_bwd_cuda = _register('design_waveform_bwd', _impl_design_waveform_bwd, _fake_design_waveform_bwd)
 mask_copy_cuda = _register('mask_copy', _impl_mask_copy, _fake_mask_copy)
+clamp_waveform_cuda = _register('clamp_waveform', _impl_clamp_waveform, lambda x, lim, eps, kind: x.new_empty(x.shape))
+clamp_waveform_bwd_cuda = _register('clamp_waveform_bwd', _impl_clamp_waveform_bwd, lambda g, x, lim, eps, kind: x.new_empty(x.shape))
 torch.library.register_autograd('mrphy_b200::blochsim_fused_fwd', _fused_backward, setup_context=_fused_setup, lib=_LIB)
 torch.library.register_autograd('mrphy_b200::design_waveform', _design_backward, setup_context=_design_setup, lib=_LIB)
 torch.library.register_autograd('mrphy_b200::mask_copy', _mask_backward, setup_context=_mask_setup, lib=_LIB)
+torch.library.register_autograd('mrphy_b200::clamp_waveform', _clamp_backward, setup_context=_clamp_setup, lib=_LIB)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -758,10 +800,14 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
     if dtype not in _F:
         raise TypeError(f'mrphy (B200): M must be float32 or float64, got {dtype}')
     if dtype == torch.float32 and flags is None and trig_policy() == 'strict':
-        # fp32 tensors in and out, fp64 arithmetic: the casts are differentiable torch copies either side of the fp64 op
+        # fp32 tensors in and out, fp64 arithmetic: the casts are differentiable torch copies either side of the fp64 op.
+        # The checkpoint interval is taken from the caller's own tensors (cached per object: no host read per call, which
+        # the fresh fp64 copies would force -- and which would invalidate a CUDA-graph capture).
+        mv = lambda x: None if x is None else (on_device(x, dev) if x.dtype in _F else on_device(x, dev, dtype))
+        K = int(ckpt) if ckpt is not None else pick_ckpt_interval(mv(dt), mv(T1_), mv(T2_))
         up = lambda x: None if x is None else x.to(torch.float64)
         Mo = fused_applypulse(up(M_), up(rf), up(gr), up(loc_), Δf_=up(Δf_), b1Map_=up(b1Map_), T1_=up(T1_), T2_=up(T2_),
-                              γ_=γ_, dt=dt, ckpt=ckpt)
+                              γ_=γ_, dt=dt, ckpt=K)
         return Mo.to(torch.float32)
     assert (T1_ is None) == (T2_ is None)      # both or neither (sims.py:68)
     N, nM = loc_.shape[0], loc_.shape[1]

@@ -164,16 +164,21 @@ class Pulse(_Obj):
         here = lambda t: None if t is None else t.to(device=self.device)
         return beffective.rfgr2beff(self.rf, self.gr, here(loc), Δf=here(Δf), b1Map=here(b1Map), γ=here(γ))
 
-    def interpT(self, dt: Tensor, *, kind: str = 'linear') -> 'Pulse':
+    def interpT(self, dt: Tensor, *, kind: str = 'linear', differentiable: bool = False) -> 'Pulse':
         r"""Resample to the (single, global) dwell time ``dt``; ``kind`` as in ``scipy.interpolate.interp1d``.
 
         Samples sit at the END of their interval and a zero sample is implied at t=0.  The new length is
         ``t_end // dt_new`` in Python floats, exactly as upstream (mobjs.py:211-212): nT=10 at 4 µs -> 2 µs gives
-        19 samples.  The result carries no autograd history and default limits.  ``kind='linear'`` is evaluated
-        on the pulse's device; other kinds take the scipy host round trip.
+        19 samples.  ``kind='linear'`` is evaluated on the pulse's device with NO device->host read: the dwell times are
+        taken from the host values the tensors were made from (a CUDA ``dt`` of unknown origin costs one read, cached per
+        tensor), so a multi-scale design loop stays free of host synchronisation.  Other kinds take the scipy host round
+        trip like upstream.  By default the result carries no autograd history (as upstream); with
+        ``differentiable=True`` (linear kind) gradients flow from the resampled ``rf``/``gr`` back to this pulse's.
+        The result has default limits.
         """
         assert self.dt.numel() == 1 and dt.numel() == 1
-        old, new = self.dt.item(), dt.item()
+        host = lambda t: _ops._cached_max(t) if t.is_cuda else float(t.reshape(-1)[0])
+        old, new = host(self.dt), host(dt)
         if old == new:
             return copy.deepcopy(self)
         nT = self.shape[2]
@@ -183,14 +188,17 @@ class Pulse(_Obj):
         if kind == 'linear':
             right = np.clip(np.searchsorted(knots, query, side='left'), 1, nT)
             frac = (query - knots[right - 1]) / (knots[right] - knots[right - 1])
-            right_t = torch.as_tensor(right, device=self.device)
+            right_t = torch.as_tensor(right).to(self.device, non_blocking=True)
+            frac_t = torch.as_tensor(frac).to(self.device, non_blocking=True)
 
             def resample(x):
-                padded = torch.cat((torch.zeros_like(x[:, :, :1]), x.detach()), dim=2).double()
-                w = torch.as_tensor(frac, device=x.device).reshape((1, 1, -1) + (1,) * (x.ndim - 3))
+                x = x if differentiable else x.detach()
+                padded = torch.cat((torch.zeros_like(x[:, :, :1]), x), dim=2).double()
+                w = frac_t.reshape((1, 1, -1) + (1,) * (x.ndim - 3))
                 lo, hi = padded.index_select(2, right_t - 1), padded.index_select(2, right_t)
                 return (lo + (hi - lo) * w).to(**kw)
         else:
+            assert not differentiable, 'only the linear kind is differentiable'
             from scipy import interpolate
 
             def resample(x):
@@ -198,7 +206,9 @@ class Pulse(_Obj):
                 f = interpolate.interp1d(knots, padded, axis=2, kind=kind, copy=False, assume_sorted=True)
                 return tensor(f(query), **kw)
 
-        return Pulse(resample(self.rf), resample(self.gr), dt=dt, desc=f"{self.desc} + interpT\'ed: dt = {new}", **kw)
+        # dt goes in as the host value: the new pulse's dwell time is then known without a device read as well
+        return Pulse(resample(self.rf), resample(self.gr), dt=tensor(new, dtype=torch.float64),
+                     desc=f"{self.desc} + interpT\'ed: dt = {new}", **kw)
 
 
 # ======================================================================================================
@@ -413,6 +423,53 @@ class SpinArray(_Obj):
             self.M_ = M_
         return self.embed(M_) if doEmbed else M_
 
+    def applysequence(
+        self,
+        events,
+        *,
+        loc: OptT = None,
+        loc_: OptT = None,
+        Δf: OptT = None,
+        Δf_: OptT = None,
+        b1Map: OptT = None,
+        b1Map_: OptT = None,
+        doEmbed: bool = False,
+        doRelax: bool = True,
+        doUpdate: bool = False,
+    ) -> Tensor:
+        r"""A whole sequence -- pulses and free-precession gaps in order -- without returning to the objects between stages.
+
+        ``events`` is an iterable of :class:`Pulse` (simulated like :meth:`applypulse`) and durations (``Tensor`` `()`⊻`(N⊻1,)`
+        or float, seconds; free precession like :meth:`freeprec`).  Equivalent to chaining the two methods with
+        ``doUpdate=True`` (mobjs.py:394-450, 555-592), but the magnetisation stays a compact device tensor from the first
+        kernel to the last -- no embed / extract / attribute coercion per stage, no host synchronisation -- and the result is
+        differentiable w.r.t. every pulse's ``rf`` / ``gr`` and ``M_``.  The chain is CUDA-graph capturable as a whole
+        (``mrphy.graphs.capture``): one replay per sequence.  Arguments and flags as in :meth:`applypulse`.
+        """
+        assert (loc_ is None) != (loc is None)
+        loc_ = loc_ if loc is None else self.extract(loc)
+        Δf_ = _one_of(Δf, Δf_, self.extract)
+        b1Map_ = _one_of(b1Map, b1Map_, self.extract)
+        T1_, T2_ = (self.T1_, self.T2_) if doRelax else (None, None)
+        geometry_grad = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (loc_, Δf_, b1Map_, self.γ_))
+        M_ = self.M_
+        for ev in events:
+            if isinstance(ev, Pulse):
+                p = ev.to(device=self.device, dtype=self.dtype)
+                if geometry_grad:
+                    beff_ = p.beff(loc_, γ=self.γ_, Δf=Δf_, b1Map=b1Map_)
+                    M_ = sims.blochsim(M_, beff_, T1=T1_, T2=T2_, γ=self.γ_, dt=p.dt)
+                else:
+                    M_ = _ops.fused_applypulse(M_, p.rf, p.gr, loc_, Δf_=Δf_, b1Map_=b1Map_, T1_=T1_, T2_=T2_, γ_=self.γ_,
+                                               dt=p.dt)
+            else:
+                dur = ev if isinstance(ev, Tensor) else tensor(float(ev), dtype=torch.float64)
+                M_ = sims.freeprec(M_, _ops.on_device(dur, self.device), T1=T1_, T2=T2_, Δf=Δf_)
+        if doUpdate:
+            self.M_ = M_
+        return self.embed(M_) if doEmbed else M_
+
     def pulse2beff(
         self,
         pulse: Pulse,
@@ -548,6 +605,13 @@ class SpinCube(SpinArray):
         b1Map_ = _one_of(b1Map, b1Map_, self.extract)
         return self.spinarray.applypulse(pulse, loc_=self.loc_, Δf_=self.Δf_, b1Map_=b1Map_, doEmbed=doEmbed,
                                          doRelax=doRelax, doUpdate=doUpdate)
+
+    def applysequence(self, events, *, b1Map: OptT = None, b1Map_: OptT = None, doEmbed: bool = False, doRelax: bool = True,
+                      doUpdate: bool = False) -> Tensor:
+        r"""As :meth:`SpinArray.applysequence` with the cube's ``loc_`` and ``Δf_``."""
+        b1Map_ = _one_of(b1Map, b1Map_, self.extract)
+        return self.spinarray.applysequence(events, loc_=self.loc_, Δf_=self.Δf_, b1Map_=b1Map_, doEmbed=doEmbed,
+                                            doRelax=doRelax, doUpdate=doUpdate)
 
     def freeprec(self, dur: Tensor, *, doEmbed: bool = False, doRelax: bool = True, doUpdate: bool = False) -> Tensor:
         r"""As :meth:`SpinArray.freeprec` with the cube's ``Δf_``."""

@@ -20,6 +20,9 @@ Cases (see SURVEY.md section 8c for the reference tests they mirror):
   bench8    8^3 cube, BASELINE.md workload distributions, nT=1000, fp32 and fp64
   freeprec  tests/test_slowsims.py:100-122 + random case
   reparam   utils.tρθ2rf / lρθ2rf / ts2s / s2g with autograd gradients; SpinArray.embed / extract on a random mask
+  sequence  SpinCube applypulse -> freeprec -> applypulse chained through doUpdate, gradients w.r.t. both pulses
+  standalone beffective.beff2uϕ, rfgr2beff (every gradient: rf, gr, loc, Δf, b1Map, γ; broadcast b1Map cases), beff2ab with
+            gradients, utils.rfclamp / sclamp with gradients -- what tests/torch_ref.py is pinned to
 """
 import os
 import sys
@@ -385,8 +388,119 @@ def case_reparam():
     save('reparam', **out)
 
 
+def case_sequence():
+    """pulse -> free precession -> pulse on a masked SpinCube, chained through doUpdate exactly as a user of the
+    reference writes it (mobjs.py:841-896): forward values from that chain.  Upstream's BlochSim.backward cannot return
+    grad_Mi for the (N, nM)-expanded constants mobjs passes (sims.py:267 indexes them wrongly), so the gradients
+    w.r.t. both pulses' waveforms come from the same chain written with the reference's plain-autograd simulator
+    (rfgr2beff -> slowsims.blochsim, sims.freeprec), which reproduces the forward values."""
+    g = torch.Generator().manual_seed(31)
+    U = lambda *s: torch.rand(s, generator=g, dtype=f64) * 2 - 1
+    dkw = {'dtype': f64}
+    N, shape = 2, (2, 4, 3, 3)
+    mask = torch.rand((1,) + shape[1:], generator=g) > 0.3
+    fov, ofst = torch.tensor([[6., 5., 4.]], **dkw), torch.tensor([[0.5, 0., -0.5]], **dkw)
+    cube = mobjs.SpinCube(shape, fov, mask=mask, ofst=ofst, **dkw)
+    nM = cube.nM
+    cube.Δf_ = U(N, nM) * 150
+    cube.T1_ = 1 + 0.3 * U(N, nM)
+    cube.T2_ = 0.06 + 0.02 * U(N, nM)
+    b1 = torch.stack((1 + 0.1 * U(N, nM), 0.1 * U(N, nM)), dim=-1)
+    rf1, gr1 = (U(N, 2, 30) * 0.2).requires_grad_(True), (U(N, 3, 30) * 2).requires_grad_(True)
+    rf2, gr2 = (U(N, 2, 20) * 0.2).requires_grad_(True), (U(N, 3, 20) * 2).requires_grad_(True)
+    dt1, dt2 = torch.tensor(4e-6, **dkw), torch.tensor(8e-6, **dkw)
+    dur = torch.tensor([2e-3, 5e-3], **dkw)
+    M0 = cube.M_.clone()
+    with torch.no_grad():
+        p1 = mobjs.Pulse(rf=rf1.detach(), gr=gr1.detach(), dt=dt1, **dkw)
+        p2 = mobjs.Pulse(rf=rf2.detach(), gr=gr2.detach(), dt=dt2, **dkw)
+        cube.applypulse(p1, b1Map_=b1, doUpdate=True)
+        Ma = npy(cube.M_)
+        cube.freeprec(dur, doUpdate=True)
+        Mb = npy(cube.M_)
+        Mc = npy(cube.applypulse(p2, b1Map_=b1))
+    kw = dict(T1=cube.T1_, T2=cube.T2_, γ=cube.γ_)
+    m = slowsims.blochsim(M0, beffective.rfgr2beff(rf1, gr1, cube.loc_, Δf=cube.Δf_, b1Map=b1, γ=cube.γ_), dt=dt1, **kw)
+    m = sims.freeprec(m, dur, T1=cube.T1_, T2=cube.T2_, Δf=cube.Δf_)
+    m = slowsims.blochsim(m, beffective.rfgr2beff(rf2, gr2, cube.loc_, Δf=cube.Δf_, b1Map=b1, γ=cube.γ_), dt=dt2, **kw)
+    assert np.abs(npy(m) - Mc).max() < 1e-12
+    w = U(N, nM, 3)
+    grads = torch.autograd.grad((m * w).sum(), (rf1, gr1, rf2, gr2))
+    save('sequence', mask=npy(mask), fov=npy(fov), ofst=npy(ofst), df=npy(cube.Δf_), T1=npy(cube.T1_), T2=npy(cube.T2_),
+         b1=npy(b1), rf1=npy(rf1), gr1=npy(gr1), rf2=npy(rf2), gr2=npy(gr2), dur=npy(dur), M0=npy(M0), Ma=Ma, Mb=Mb, Mc=Mc,
+         w=npy(w), grf1=npy(grads[0]), ggr1=npy(grads[1]), grf2=npy(grads[2]), ggr2=npy(grads[3]))
+
+
+def case_standalone():
+    """Outputs AND autograd gradients of the reference's stand-alone operators on seeded inputs (fp64)."""
+    from mrphy import utils
+    g = torch.Generator().manual_seed(2024)
+    U = lambda *s: torch.rand(s, generator=g, dtype=f64) * 2 - 1
+    out = {}
+    # ---- beff2uϕ (beffective.py:18-37), including a zero-field spin
+    N, Nd = 2, (3, 4)
+    beff = (U(N, *Nd, 3) * 3)
+    beff[0, 0, 0] = 0
+    beff = beff.requires_grad_(True)
+    g2 = (2 * PI * 4257.6 * 4e-6 * (1 + 0.1 * U(N, *Nd))).requires_grad_(True)
+    wU, wP = U(N, *Nd, 3), U(N, *Nd)
+    Uo, Po = beffective.beff2uϕ(beff, g2)
+    gb, gg = torch.autograd.grad((Uo * wU).sum() + (Po * wP).sum(), (beff, g2))
+    out.update(uphi_beff=npy(beff), uphi_g=npy(g2), uphi_wU=npy(wU), uphi_wP=npy(wP), uphi_U=npy(Uo), uphi_Phi=npy(Po),
+               uphi_gbeff=npy(gb), uphi_gg=npy(gg))
+    # ---- rfgr2beff (beffective.py:107-168) with every gradient; coil-broadcast variants
+    nT = 9
+    for tag, Nd, rf_c, b1_c in (('mc', (7,), 2, 2), ('b1bc', (5,), 3, 1), ('rfbc', (6,), 0, 3), ('nob1', (3, 2, 2), 3, None),
+                                ('sc', (4,), 0, 0)):
+        rf = (U(N, 2, nT, rf_c) if rf_c else U(N, 2, nT)).requires_grad_(True)
+        gr = U(N, 3, nT).requires_grad_(True)
+        loc = (U(N, *Nd, 3) * 5).requires_grad_(True)
+        df = (U(N, *Nd) * 100).requires_grad_(True)
+        gam = (4257.6 * (1 + 0.1 * U(N, *Nd))).requires_grad_(True)
+        b1 = None if b1_c is None else (U(N, *Nd, 2, b1_c) if b1_c else U(N, *Nd, 2)).requires_grad_(True)
+        w = U(N, *Nd, nT, 3)
+        be = beffective.rfgr2beff(rf, gr, loc, Δf=df, b1Map=b1, γ=gam)
+        ins = [rf, gr, loc, df, gam] + ([b1] if b1 is not None else [])
+        gs = torch.autograd.grad((be * w).sum(), ins)
+        names = ['rf', 'gr', 'loc', 'df', 'gam'] + (['b1'] if b1 is not None else [])
+        out.update({f'b_{tag}_{k}': npy(v) for k, v in zip(names, ins)})
+        out.update({f'b_{tag}_g{k}': npy(v) for k, v in zip(names, gs)})
+        out.update({f'b_{tag}_w': npy(w), f'b_{tag}_beff': npy(be)})
+    # ---- beff2ab (beffective.py:40-104) with gradients wrt beff, E1, E2
+    nT = 17
+    bf = (U(N, 6, nT, 3) * 2).requires_grad_(True)
+    E1 = (0.95 + 0.04 * U(N, 6)).requires_grad_(True)
+    E2 = (0.9 + 0.05 * U(N, 6)).requires_grad_(True)
+    wA, wB = U(N, 6, 3, 3), U(N, 6, 3)
+    A, B = beffective.beff2ab(bf, E1=E1, E2=E2, γ=gH.to(f64), dt=torch.tensor(4e-6, dtype=f64))
+    gbf, gE1, gE2 = torch.autograd.grad((A * wA).sum() + (B * wB).sum(), (bf, E1, E2))
+    out.update(ab_beff=npy(bf), ab_E1=npy(E1), ab_E2=npy(E2), ab_wA=npy(wA), ab_wB=npy(wB), ab_A=npy(A), ab_B=npy(B),
+               ab_gbeff=npy(gbf), ab_gE1=npy(gE1), ab_gE2=npy(gE2))
+    # ---- utils.rfclamp / sclamp (utils.py:217-236, 278-293) with gradients
+    for tag, nC in (('sc', 0), ('mc', 3)):
+        rf = (U(N, 2, 40, nC) if nC else U(N, 2, 40)) * 0.3
+        rf = rf.requires_grad_(True)
+        rfmax = torch.rand((N, nC) if nC else (N,), generator=g, dtype=f64) * 0.2 + 0.1
+        wr = U(*rf.shape)
+        rc = utils.rfclamp(rf, rfmax)
+        grc, = torch.autograd.grad((rc * wr).sum(), (rf,))
+        out.update({f'cl_{tag}_rf': npy(rf), f'cl_{tag}_rfmax': npy(rfmax), f'cl_{tag}_w': npy(wr), f'cl_{tag}_out': npy(rc),
+                    f'cl_{tag}_grf': npy(grc)})
+    sl = (U(N, 3, 40) * 2e4).requires_grad_(True)
+    smax = torch.rand((N, 3), generator=g, dtype=f64) * 1e4 + 5e3
+    ws = U(N, 3, 40)
+    sc = utils.sclamp(sl, smax)
+    gsl, = torch.autograd.grad((sc * ws).sum(), (sl,))
+    out.update(cl_s=npy(sl), cl_smax=npy(smax), cl_ws=npy(ws), cl_sout=npy(sc), cl_gs=npy(gsl))
+    save('standalone', **out)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:                      # regenerate selected cases only: python make_golden.py standalone ...
+        for name in sys.argv[1:]:
+            globals()['case_' + name]()
+        sys.exit(0)
     case_kat3()
     case_sims512()
     case_cube27()
@@ -400,3 +514,5 @@ if __name__ == '__main__':
     case_bench8()
     case_freeprec()
     case_reparam()
+    case_standalone()
+    case_sequence()

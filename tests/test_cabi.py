@@ -44,7 +44,7 @@ def test_abi_version_and_struct_layout(cabi):
     assert ctypes.sizeof(cabi.BeffArgs) == 6 * 4 + 8 * 3 + 8 * 4 + 32 * 4 + 8 * 2 + 8 * 3 + 8 * 2
     # ... and the C side agrees with every ctypes mirror (the loader checks the same and refuses a mismatch)
     for which, cls in enumerate((cabi.Param, cabi.FusedArgs, cabi.BeffArgs, cabi.RfGr2BeffArgs, cabi.Beff2abArgs,
-                                 cabi.Beff2uphiArgs, cabi.FreePrecArgs, cabi.ReparamArgs, cabi.MaskArgs)):
+                                 cabi.Beff2uphiArgs, cabi.FreePrecArgs, cabi.ReparamArgs, cabi.MaskArgs, cabi.ClampArgs)):
         assert L.mrphy_sizeof_args(which) == ctypes.sizeof(cls), cls.__name__
     assert L.mrphy_sizeof_args(99) == 0
 

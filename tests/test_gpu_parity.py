@@ -514,6 +514,171 @@ def test_beff2uphi_kernel_and_adjoint(dev, dtype):
     assert mx(bt.grad, -2 * torch.nn.functional.normalize(bt.detach(), dim=-1)) < 1e-12
 
 
+def test_standalone_operators_against_reference_goldens(dev, golden):
+    """beff2uϕ, rfgr2beff (outputs and EVERY gradient: rf, gr, loc, Δf, b1Map, γ -- including a single-coil b1Map
+    broadcast over multi-coil rf and a multi-coil b1Map with rf without a coil dim, beffective.py:153-165) and beff2ab with
+    its gradients: the CUDA operators against outputs and autograd gradients of the UNMODIFIED reference
+    (tests/golden/standalone.npz)."""
+    from mrphy import beffective
+    g = golden('standalone')
+    near = lambda a, b, tol=1e-11: a.shape == tuple(np.shape(b)) and mx(a, b) <= tol * max(1.0, float(np.abs(b).max()))
+    G = lambda k, grad=True: T(g[k], dev, f64).requires_grad_(grad)
+    beff, gg = G('uphi_beff'), G('uphi_g')
+    U, P = beffective.beff2uϕ(beff, gg)
+    assert near(U, g['uphi_U']) and near(P, g['uphi_Phi'])
+    ((U * G('uphi_wU', False)).sum() + (P * G('uphi_wP', False)).sum()).backward()
+    assert near(beff.grad, g['uphi_gbeff']) and near(gg.grad, g['uphi_gg'])
+    for tag in ('mc', 'b1bc', 'rfbc', 'nob1', 'sc'):
+        t = {k: G(f'b_{tag}_{k}') for k in ('rf', 'gr', 'loc', 'df', 'gam', 'b1') if f'b_{tag}_{k}' in g}
+        be = beffective.rfgr2beff(t['rf'], t['gr'], t['loc'], Δf=t['df'], b1Map=t.get('b1'), γ=t['gam'])
+        assert near(be, g[f'b_{tag}_beff']), tag
+        (be * G(f'b_{tag}_w', False)).sum().backward()
+        for k, v in t.items():
+            assert near(v.grad, g[f'b_{tag}_g{k}']), (tag, k)
+    bf, E1, E2 = G('ab_beff'), G('ab_E1'), G('ab_E2')
+    A, B = beffective.beff2ab(bf, E1=E1, E2=E2, γ=tensor(4257.6, dtype=f64), dt=tensor(4e-6, dtype=f64))
+    assert near(A, g['ab_A']) and near(B, g['ab_B'])
+    ((A * G('ab_wA', False)).sum() + (B * G('ab_wB', False)).sum()).backward()
+    assert near(bf.grad, g['ab_gbeff'], 1e-9) and near(E1.grad, g['ab_gE1'], 1e-9) and near(E2.grad, g['ab_gE2'], 1e-9)
+
+
+def test_applypulse_with_broadcast_b1map_on_both_paths(dev, golden):
+    """A single-coil b1Map with multi-coil rf, and a multi-coil b1Map with rf without a coil dim, through the fused path
+    and (loc requiring grad) through the explicit-field path: both equal the reference chain's field + the oracle."""
+    from mrphy import mobjs
+    from oracle import bloch_oracle as orc
+    g = golden('standalone')
+    kw = {'dtype': f64, 'device': dev}
+    for tag in ('b1bc', 'rfbc'):
+        rf, gr, loc, b1 = (T(g[f'b_{tag}_{k}'], dev, f64) for k in ('rf', 'gr', 'loc', 'b1'))
+        N, nM = loc.shape[0], loc.shape[1]
+        # the oracle takes matching coil dims: spell the broadcast out (expanded b1Map / coil-summed b1Map)
+        rf_o = g[f'b_{tag}_rf'] if tag == 'b1bc' else g[f'b_{tag}_rf'][..., None]
+        b1_o = np.broadcast_to(g[f'b_{tag}_b1'], (N, nM, 2, 3)) if tag == 'b1bc' else g[f'b_{tag}_b1'].sum(-1, keepdims=True)
+        Mo_ref = orc.blochsim_fwd(tensor([0., 0., 1.]).expand(N, nM, 3),
+                                  orc.rfgr2beff(rf_o, g[f'b_{tag}_gr'], g[f'b_{tag}_loc'], b1=b1_o), 1.47, 0.07)
+        sp = mobjs.SpinArray((N, nM), **kw)
+        p = mobjs.Pulse(rf=rf, gr=gr, **kw)
+        M1 = sp.applypulse(p, loc_=loc, b1Map_=b1)
+        M2 = sp.applypulse(p, loc_=loc.clone().requires_grad_(True), b1Map_=b1)        # routes through rfgr2beff + blochsim
+        assert mx(M1, Mo_ref) < 1e-12 and mx(M2, Mo_ref) < 1e-12
+
+
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_rfclamp_sclamp_kernels_match_reference(dev, golden, dtype):
+    """utils.rfclamp / utils.sclamp on CUDA tensors (one launch each way, csrc/design_ops.cu: clamp_waveform_kernel)
+    against the unmodified reference's outputs and autograd gradients (tests/golden/standalone.npz)."""
+    from mrphy import utils, _cabi
+    g = golden('standalone')
+    tol = 1e-12 if dtype == f64 else 2e-6
+    near = lambda a, b: mx(a, b) <= tol * max(1.0, float(np.abs(b).max()))
+    for tag in ('sc', 'mc'):
+        rf = T(g[f'cl_{tag}_rf'], dev, dtype).requires_grad_(True)
+        n0 = _cabi.launch_counter
+        out = utils.rfclamp(rf, T(g[f'cl_{tag}_rfmax'], dev, dtype))
+        (out * T(g[f'cl_{tag}_w'], dev, dtype)).sum().backward()
+        assert _cabi.launch_counter - n0 == 2                       # one launch forward, one backward
+        assert out.dtype == dtype and near(out, g[f'cl_{tag}_out']) and near(rf.grad, g[f'cl_{tag}_grf'])
+        assert (np.abs(g[f'cl_{tag}_out'] - g[f'cl_{tag}_rf']) > 0).any()   # the fixture does clamp something
+    s = T(g['cl_s'], dev, dtype).requires_grad_(True)
+    out = utils.sclamp(s, T(g['cl_smax'], dev, dtype))
+    (out * T(g['cl_ws'], dev, dtype)).sum().backward()
+    assert near(out, g['cl_sout']) and near(s.grad, g['cl_gs'])
+    # scalar limits and the CPU expressions agree with the kernels
+    rf = T(g['cl_sc_rf'], dev, dtype)
+    assert mx(utils.rfclamp(rf, tensor(0.15)), utils.rfclamp(rf.cpu(), tensor(0.15))) <= tol
+    assert mx(utils.sclamp(s.detach(), tensor(9e3)), utils.sclamp(s.detach().cpu(), tensor(9e3))) == 0.0
+
+
+@pytest.mark.parametrize('dtype', [f64, f32])
+def test_applysequence_matches_chained_reference(dev, golden, dtype):
+    """pulse -> freeprec -> pulse on a masked SpinCube: `applysequence` against the unmodified reference
+    chained through doUpdate (forward, tests/golden/sequence.npz) and its autograd gradients w.r.t. both pulses; the same
+    values from chaining our own applypulse / freeprec; no host synchronisation; and the whole sequence + loss + backward
+    replayed from ONE CUDA graph reproduces the eager gradients bit for bit."""
+    from mrphy import mobjs, graphs
+    g = golden('sequence')
+    kw = {'dtype': dtype, 'device': dev}
+    tolM, tolG = (1e-12, 1e-9) if dtype == f64 else (1e-5, 1e-4)
+
+    def build():
+        cube = mobjs.SpinCube((2, 4, 3, 3), T(g['fov'], dev, dtype), mask=tensor(g['mask'], device=dev), ofst=T(g['ofst'], dev, dtype),
+                              Δf_=T(g['df'], dev, dtype), T1_=T(g['T1'], dev, dtype), T2_=T(g['T2'], dev, dtype), **kw)
+        p1 = mobjs.Pulse(rf=T(g['rf1'], dev, dtype).requires_grad_(True), gr=T(g['gr1'], dev, dtype).requires_grad_(True),
+                         dt=tensor(4e-6, dtype=f64), **kw)
+        p2 = mobjs.Pulse(rf=T(g['rf2'], dev, dtype).requires_grad_(True), gr=T(g['gr2'], dev, dtype).requires_grad_(True),
+                         dt=tensor(8e-6, dtype=f64), **kw)
+        return cube, p1, p2
+
+    cube, p1, p2 = build()
+    b1, dur, w = T(g['b1'], dev, dtype), T(g['dur'], dev, dtype), T(g['w'], dev, dtype)
+    cube.applysequence([p1, dur, p2], b1Map_=b1)      # first use reads min(T1, T2) once (cached per tensor afterwards)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode('error')           # from here on: no device->host read at all
+    try:
+        Mc = cube.applysequence([p1, dur, p2], b1Map_=b1)
+        (Mc * w).sum().backward()
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert mx(Mc, g['Mc']) < tolM
+    for got, key in ((p1.rf.grad, 'grf1'), (p1.gr.grad, 'ggr1'), (p2.rf.grad, 'grf2'), (p2.gr.grad, 'ggr2')):
+        assert rel(got, g[key]) < tolG, key
+    # chaining the object methods gives the same intermediate and final states
+    c2, q1, q2 = build()
+    c2.applypulse(q1, b1Map_=b1, doUpdate=True)
+    assert mx(c2.M_, g['Ma']) < tolM
+    c2.freeprec(dur, doUpdate=True)
+    assert mx(c2.M_, g['Mb']) < tolM
+    assert mx(c2.applypulse(q2, b1Map_=b1), Mc) == 0.0
+    # one CUDA graph for the whole sequence + loss + backward
+    eager = [x.grad.clone() for x in (p1.rf, p1.gr, p2.rf, p2.gr)]
+    del Mc
+    step = graphs.capture(lambda: (cube.applysequence([p1, dur, p2], b1Map_=b1) * w).sum().backward(),
+                          params=(p1.rf, p1.gr, p2.rf, p2.gr))
+    step.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b.grad) for a, b in zip(eager, (p1.rf, p1.gr, p2.rf, p2.gr)))
+
+
+def test_interpT_on_device_goldens_no_sync_and_gradient(dev, golden):
+    """Pulse.interpT (linear) on CUDA tensors: the reference's values (tests/test_mobjs.py:160-195 and fixtures from the
+    unmodified reference, incl. the float-// length quirk and the fp32 1999-vs-2000 case), NO device->host read, and
+    with differentiable=True the gradient of the resampling (against the oracle's numpy interpolation as a matrix)."""
+    from mrphy import mobjs, dt0
+    from oracle import bloch_oracle as orc
+    g = golden('interp')
+    kw = {'dtype': f64, 'device': dev}
+    p = mobjs.Pulse(rf=T(g['a_rf'], dev, f64), gr=T(g['a_gr'], dev, f64), dt=dt0, **kw)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode('error')
+    try:
+        q = p.interpT(dt=dt0 * 5)
+        q2 = mobjs.Pulse(rf=T(g['b_rf'], dev, f64), gr=T(g['b_gr'], dev, f64), dt=dt0, **kw).interpT(dt=tensor(2e-6, dtype=f64))
+        q2b = q2.interpT(dt=tensor(1e-6, dtype=f64))          # resampling a resampled pulse: its dt is host-known too
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert q.rf.is_cuda and q.rf.cpu().numpy() == pytest.approx(np.array([[[0.04, 0.09], [0.06, 0.01]]]), abs=1e-9)
+    assert q.gr.cpu().numpy() == pytest.approx(np.array([[[0.04, 0.09], [0.06, 0.01], [0.1, 0.1]]]), abs=1e-9)
+    assert q2.rf.shape[2] == 19 and mx(q2.rf, g['b_rf_new']) < 1e-12 and mx(q2.gr, g['b_gr_new']) < 1e-12
+    assert q2b.rf.shape[2] == int((19 * 2e-6) // 1e-6) and mx(q2b.rf, orc.interp_linear(g['b_rf_new'], 2e-6, 1e-6)) < 1e-12
+    p3f = mobjs.Pulse(rf=T(g['c_rf'], dev, f32), gr=T(g['c_gr'], dev, f32), dt=tensor(20e-6, dtype=f64), dtype=f32, device=dev)
+    q3f = p3f.interpT(dt=tensor(4e-6, dtype=f64))
+    assert q3f.rf.shape[2] == 199 and mx(q3f.rf, g['c32_rf_new']) < 1e-6 and mx(q3f.gr, g['c32_gr_new']) < 1e-6
+    # gradient: q = J x with J the (linear) interpolation matrix, so dL/dx = J^T w
+    rf = T(g['b_rf'], dev, f64).requires_grad_(True)
+    gr = T(g['b_gr'], dev, f64).requires_grad_(True)
+    pd = mobjs.Pulse(rf=rf, gr=gr, dt=dt0, **kw)
+    qd = pd.interpT(dt=tensor(2e-6, dtype=f64), differentiable=True)
+    assert not pd.interpT(dt=tensor(2e-6, dtype=f64)).rf.requires_grad and qd.rf.requires_grad
+    gen = torch.Generator().manual_seed(1)
+    w = torch.rand(qd.rf.shape, generator=gen, dtype=f64)
+    (qd.rf * w.to(dev)).sum().backward()
+    nT = rf.shape[2]
+    J = orc.interp_linear(np.eye(nT)[None], 4e-6, 2e-6)[0]                 # (nT, nT_new): column j = weights of sample j
+    want = np.einsum('tj,ncj->nct', J, w.numpy())
+    assert mx(rf.grad, want) < 1e-12 and gr.grad is None
+
+
 def test_multiscale_design_loop_through_public_api(dev):
     """The use the reference is built for (BASELINE config C3 in miniature): optimise a pulse through its
     re-parametrisation (utils.tρθ2rf / ts2s / s2g), refine it with Pulse.interpT on the device, keep optimising.
