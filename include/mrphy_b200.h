@@ -40,7 +40,8 @@ enum mrphy_status {
 };
 
 enum mrphy_flags {
-  MRPHY_TRIG_PRECISE = 1 << 0, /* fp32 only: Newton rsqrt + polynomial sincos instead of MUFU   */
+  MRPHY_TRIG_PRECISE = 1 << 0, /* fp32 only: rotation coefficients on the FMA pipe (half-angle polynomials in |b|^2 up to 2 pi, Newton
+                                  rsqrt + Cody-Waite reduced polynomial sincos beyond) instead of MUFU.SIN/COS/RSQ */
   MRPHY_NEED_GMI = 1 << 1,     /* backward: also write dL/dMi                                   */
   MRPHY_RF_COIL_DIM = 1 << 2,  /* rf (and its gradient) carry the trailing nCoils dimension     */
   MRPHY_NEED_GBEFF = 1 << 3,   /* explicit-field backward: also write dL/dBeff                  */

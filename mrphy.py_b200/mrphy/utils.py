@@ -181,10 +181,10 @@ def rf2tρθ(rf: Tensor, rfmax: Tensor) -> Tuple[Tensor, Tensor]:
 def rfclamp(rf: Tensor, rfmax: Tensor, *, eps: Number = 1e-7) -> Tensor:
     r"""Scale samples with \|rf\| above ``rfmax-eps`` back onto that radius (one CUDA launch, and one for its adjoint, on
     GPU tensors)."""
+    # (a limit of another dtype keeps the torch expression: upstream then forms rfmax - eps in THAT dtype)
     if rf.is_cuda and rf.dtype in _FLOATS and rf.ndim in (3, 4) and rf.shape[1] == 2 and rf.numel() > 0 and _frozen(rfmax) \
-            and os.environ.get('MRPHY_B200_REPARAM') != 'torch' and (rfmax.ndim == 0 or
-                                                                      (torch.result_type(rf, rfmax) == rf.dtype and
-                                                                       (rfmax.ndim == 2) == (rf.ndim == 4))):
+            and os.environ.get('MRPHY_B200_REPARAM') != 'torch' and rfmax.dtype == rf.dtype \
+            and (rfmax.ndim == 0 or (rfmax.ndim == 2) == (rf.ndim == 4)):
         r = _aux(rfmax, rf, rf.shape[0], rf.shape[3] if rf.ndim == 4 else 1)
         if r is not None:
             from mrphy import _ops
@@ -231,7 +231,7 @@ def tρθts2rfgr(tρ: Tensor, θ: Tensor, ts: Tensor, rfmax: Tensor, smax: Tenso
 def sclamp(s: Tensor, smax: Tensor) -> Tensor:
     r"""Clamp slew rate componentwise to ``±smax`` `(N,xyz)` (one CUDA launch, and one for its adjoint, on GPU tensors)."""
     if s.is_cuda and s.dtype in _FLOATS and s.ndim == 3 and s.shape[1] == 3 and s.numel() > 0 and _frozen(smax) \
-            and os.environ.get('MRPHY_B200_REPARAM') != 'torch':
+            and os.environ.get('MRPHY_B200_REPARAM') != 'torch' and smax.ndim <= 2:
         m = _aux(smax if smax.ndim != 1 else smax.reshape(1, -1), s, s.shape[0], 3)
         if m is not None:
             from mrphy import _ops

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (ncu --set full) into profiles/r1_ncu_summary.json entries.
+"""Summarise an .ncu-rep (ncu --set full) into profiles/r2_ncu_summary.json entries (MRPHY_NCU_SUMMARY overrides the file).
 
     python profiles/summarize_ncu.py gpurun_out/prof_final.ncu-rep final     # -> captures.final_fwd / final_bwd / ...
     python profiles/summarize_ncu.py --launches profiles/r1_launches_c2.csv   # -> launch_list_c2_default (shares)
@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, 'profiles', 'r1_ncu_summary.json')
+OUT = os.environ.get('MRPHY_NCU_SUMMARY') or os.path.join(ROOT, 'profiles', 'r2_ncu_summary.json')
 WANT = [
     'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
     'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
@@ -36,7 +36,8 @@ WANT = [
     'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
 ]
 TAGS = (('fused_bwd', 'bwd'), ('fused_fwd', 'fwd'), ('grad_finalize', 'finalize'), ('pack_waveform', 'pack'),
-        ('rfgr2beff_bwd', 'rfgr2beff_bwd'), ('rfgr2beff', 'rfgr2beff'), ('beff_v2', 'beff'))
+        ('rfgr2beff_bwd', 'rfgr2beff_bwd'), ('rfgr2beff', 'rfgr2beff'), ('beff_v3_kernel<float, 1, 1, 1>', 'beff_bwd'),
+        ('beff_v3_kernel<float, 1, 1, 0>', 'beff_fwd'), ('beff_v3', 'beff'), ('beff_v2', 'beff'))
 
 
 def num(x):
@@ -82,7 +83,7 @@ def launch_shares(path):
 if __name__ == '__main__':
     d = json.load(open(OUT)) if os.path.exists(OUT) else {'captures': {}}
     if sys.argv[1] == '--launches':
-        d['launch_list_c2_default'] = launch_shares(sys.argv[2])
+        d[sys.argv[3] if len(sys.argv) > 3 else 'launch_list_c2_default'] = launch_shares(sys.argv[2])
     else:
         d.setdefault('captures', {}).update(captures(sys.argv[1], sys.argv[2]))
     json.dump(d, open(OUT, 'w'), indent=1)

@@ -586,7 +586,8 @@ def test_rfclamp_sclamp_kernels_match_reference(dev, golden, dtype):
     assert near(out, g['cl_sout']) and near(s.grad, g['cl_gs'])
     # scalar limits and the CPU expressions agree with the kernels
     rf = T(g['cl_sc_rf'], dev, dtype)
-    assert mx(utils.rfclamp(rf, tensor(0.15)), utils.rfclamp(rf.cpu(), tensor(0.15))) <= tol
+    lim = tensor(0.15, dtype=dtype)
+    assert mx(utils.rfclamp(rf, lim), utils.rfclamp(rf.cpu(), lim)) <= tol
     assert mx(utils.sclamp(s.detach(), tensor(9e3)), utils.sclamp(s.detach().cpu(), tensor(9e3))) == 0.0
 
 
