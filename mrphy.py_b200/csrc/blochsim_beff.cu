@@ -13,7 +13,6 @@
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
 #include "bloch_math.cuh"
-#include "ptx_helpers.cuh"
 
 namespace mrphy {
 
@@ -165,7 +164,10 @@ __global__ void __launch_bounds__(EBLK) beff_bwd_kernel(const EArgs<T> a, const 
 //    flight while tile k is consumed, no registers staged;
 //  * each thread reads its own row with LDS.128 without bank conflicts (20*r mod 32 hits 8 distinct quads);
 //  * the backward overwrites the row in place with dL/dBeff and the warp streams it out with 16-byte stores.
-constexpr int ROWB = 192, PITCHB = 208, CHUNKS = ROWB / 16;   // 12 chunks of 16 B per row
+#ifndef MRPHY_BEFF_ROWB
+#define MRPHY_BEFF_ROWB 192
+#endif
+constexpr int ROWB = MRPHY_BEFF_ROWB, PITCHB = ROWB + 16, CHUNKS = ROWB / 16;   // 12 chunks of 16 B per row (pitch 13 x 16 B: odd)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
@@ -327,135 +329,6 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// v3 tile pipeline: the same per-warp tiles, but every lane moves ITS OWN row with ONE 1-D TMA bulk copy per tile
-// (cp.async.bulk global -> shared, 384 contiguous bytes = 32 fp32 steps, completion on a per-warp mbarrier) instead of the
-// warp issuing 12 16-byte cp.async per lane: HBM sees 384-byte bursts instead of 16-byte requests spread over 32 DRAM
-// pages, and no LSU instruction is spent on the copy.  The backward returns dL/dBeff the same way: each lane writes its
-// row in place and hands it to a bulk store (shared -> global); a lane only ever waits for its own store before the row
-// is refilled, so there is no cross-lane synchronisation besides the mbarrier phase.  Two stages per warp, 400-byte row
-// pitch (25 x 16 B: the LDS.128 of a quarter-warp hit 8 distinct bank groups).
-constexpr int ROWB3 = 384, PITCHB3 = ROWB3 + 16;
-
-template <typename T, int POL, bool RELAX, bool BWD>
-__global__ void __launch_bounds__(EBLK) beff_v3_kernel(const EArgs<T> a, const int need_gmi, const int need_gb) {
-  constexpr int TB = ROWB3 / (3 * (int)sizeof(T));     // steps per tile: 32 (fp32), 16 (fp64)
-  constexpr int PITCH = PITCHB3 / (int)sizeof(T);
-  constexpr uint32_t STEPB = 3 * (uint32_t)sizeof(T);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
-  unsigned char* buf0 = smem_raw + (size_t)warp * 2 * 32 * PITCHB3;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)EWARP * 2 * 32 * PITCHB3) + 2 * warp;
-  const int nM = a.nM, nT = a.nT, K = a.K;
-  const int i0 = (blockIdx.x * EWARP + warp) * 32;
-  if (i0 >= nM) return;
-  if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_barrier_init();
-  }
-  __syncwarp();
-  const bool ok = i0 + lane < nM;
-  const int i = ok ? i0 + lane : nM - 1;
-  SpinConst<T, 1> k;
-  T g;
-  load_consts<T, RELAX>(a, n, i, k, g);
-  T mx, my, mz, hx = 0, hy = 0, hz = 0;
-  if (BWD) {
-    const T* mp = a.Mo + ((size_t)n * nM + i) * 3;
-    mx = mp[0]; my = mp[1]; mz = mp[2];
-    const T* gp = a.gMo + (int64_t)n * a.gMo_sn + (int64_t)i * a.gMo_sm;
-    hx = gp[0]; hy = gp[1]; hz = gp[2];
-  } else {
-    const T* mp = a.Mi + (int64_t)n * a.Mi_sn + (int64_t)i * a.Mi_sm;
-    mx = mp[0]; my = mp[1]; mz = mp[2];
-  }
-  const T* Brow = a.B + (int64_t)n * a.B_sn + (int64_t)i * a.B_sm;          // this lane's row of the field
-  T* Grow = (BWD && need_gb) ? a.gB + ((size_t)n * nM + i) * (size_t)nT * 3 : nullptr;
-  const T ng = -g;
-  int next_ck = BWD ? ((nT - 1) / K) * K : K;
-  const int ntiles = (nT + TB - 1) / TB;
-  auto tile_t0 = [&](int q) { return (BWD ? ntiles - 1 - q : q) * TB; };
-  auto tile_len = [&](int q) { return min(TB, nT - tile_t0(q)); };
-  auto issue = [&](int q) {                  // every lane: its row of tile q into stage q & 1
-    const uint32_t bytes = (uint32_t)tile_len(q) * STEPB;
-    if (lane == 0) mbar_arrive_expect_tx(&bars[q & 1], 32u * bytes);
-    bulk_g2s(buf0 + (q & 1) * 32 * PITCHB3 + lane * PITCHB3, Brow + (int64_t)tile_t0(q) * 3, bytes, &bars[q & 1]);
-  };
-  issue(0);
-  for (int q = 0; q < ntiles; ++q) {
-    if (q + 1 < ntiles) {
-      if (BWD) bulk_wait_read<0>();          // this lane's store out of that stage (tile q-1) has read its row
-      issue(q + 1);
-    }
-    mbar_wait(&bars[q & 1], (uint32_t)(q >> 1) & 1u);
-    T* row = reinterpret_cast<T*>(buf0 + (q & 1) * 32 * PITCHB3) + lane * PITCH;
-    const int t0 = tile_t0(q), len = tile_len(q);
-    constexpr int GS = 16 / (int)sizeof(T);            // 4 (fp32) or 2 (fp64) steps per 48-byte group
-    constexpr int GV = 3 * GS;
-    if (!BWD) {
-      for (int j0 = 0; j0 < len; j0 += GS) {
-        T v[GV];
-        float4* v4 = reinterpret_cast<float4*>(v);
-        const float4* src = reinterpret_cast<const float4*>(row + 3 * j0);
-        v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
-#pragma unroll
-        for (int u = 0; u < GS; ++u) {
-          step_fwd<T, POL, RELAX>(g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], k.e1, k.e2, mx, my, mz);
-          const int t1 = t0 + j0 + u + 1;
-          if (t1 == next_ck) {
-            if (t1 < nT && ok) {
-              T* cp = a.ckpt + ((size_t)n * a.nCk + (t1 / K - 1)) * 3 * (size_t)nM;
-              cp[i] = mx; cp[(size_t)nM + i] = my; cp[2 * (size_t)nM + i] = mz;
-            }
-            next_ck += K;
-          }
-        }
-      }
-    } else {
-      for (int j0 = len - GS; j0 >= 0; j0 -= GS) {
-        T v[GV];
-        float4* v4 = reinterpret_cast<float4*>(v);
-        float4* src = reinterpret_cast<float4*>(row + 3 * j0);
-        v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
-#pragma unroll
-        for (int u = GS - 1; u >= 0; --u) {
-          T Fx, Fy, Fz;
-          step_bwd<T, POL, RELAX, 1>(k, g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], mx, my, mz, hx, hy, hz,
-                                     Fx, Fy, Fz);
-          v[3 * u] = ng * Fx;       // dL/dBeff = -2*pi*gamma*dt * F   (sims.py:194, 234-259)
-          v[3 * u + 1] = ng * Fy;
-          v[3 * u + 2] = ng * Fz;
-          const int t = t0 + j0 + u;
-          if (t == next_ck) {
-            if (t > 0) {
-              const T* cp = a.ckpt + ((size_t)n * a.nCk + (t / K - 1)) * 3 * (size_t)nM;
-              mx = cp[i]; my = cp[(size_t)nM + i]; mz = cp[2 * (size_t)nM + i];
-            }
-            next_ck -= K;
-          }
-        }
-        src[0] = v4[0]; src[1] = v4[1]; src[2] = v4[2];
-      }
-      if (Grow != nullptr && ok) {           // this lane's row leaves as one bulk store
-        fence_proxy_async_smem();
-        bulk_s2g(Grow + (int64_t)t0 * 3, row, (uint32_t)len * STEPB);
-      }
-      bulk_commit();
-    }
-    __syncwarp();   // every lane has passed this phase of the barrier before lane 0 re-arms it two tiles later
-  }
-  if (BWD) bulk_wait_read<0>();
-  if (!BWD && ok) {
-    T* op = a.Mo + ((size_t)n * nM + i) * 3;
-    op[0] = mx; op[1] = my; op[2] = mz;
-  }
-  if (BWD && need_gmi && ok) {
-    T* op = a.gMi + ((size_t)n * nM + i) * 3;
-    op[0] = hx; op[1] = hy; op[2] = hz;
-  }
-}
-
 }  // namespace mrphy
 
 using namespace mrphy;
@@ -502,26 +375,6 @@ template <typename T, int POL, bool RELAX>
 int launch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
   const EArgs<T> e = make_eargs<T>(a);
   dim3 grid((a->nM + EBLK - 1) / EBLK, a->N);
-  if (rows_aligned16<T>(a) && !getenv("MRPHY_B200_BEFF_V1") && !getenv("MRPHY_B200_BEFF_V2")) {   // TMA rows (v3)
-    constexpr size_t smem3 = (size_t)EWARP * 2 * 32 * PITCHB3 + (size_t)EWARP * 2 * sizeof(uint64_t);
-    const int gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0, gb = (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0;
-    if (bwd) {
-      auto kern = beff_v3_kernel<T, POL, RELAX, true>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      timing_begin(st);
-      kern<<<grid, EBLK, smem3, st>>>(e, gmi, gb);
-      timing_end(st);
-    } else {
-      auto kern = beff_v3_kernel<T, POL, RELAX, false>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      timing_begin(st);
-      kern<<<grid, EBLK, smem3, st>>>(e, 0, 0);
-      timing_end(st);
-    }
-    ++launch_count();
-    CK(cudaGetLastError());
-    return MRPHY_OK;
-  }
   if (rows_aligned16<T>(a) && !getenv("MRPHY_B200_BEFF_V1")) {   // cp.async double-buffered tiles
     constexpr size_t smem2 = (size_t)EWARP * 2 * 32 * PITCHB;
     const int gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0, gb = (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0;

@@ -32,6 +32,8 @@ _on_device = {}
 def _cast(value, device, dtype) -> Tensor:
     """Anything assignable -> tensor on (device, dtype)."""
     if not isinstance(value, Tensor):
+        if isinstance(value, (int, float)) and device.type == 'cuda':
+            return torch.full((), value, device=device, dtype=dtype)     # a fill kernel: no (synchronous) host->device copy
         return tensor(value, device=device, dtype=dtype)
     if device.type == 'cuda' and id(value) in _DEFAULTS:
         key = (id(value), device, dtype)
@@ -182,14 +184,17 @@ class Pulse(_Obj):
         if old == new:
             return copy.deepcopy(self)
         nT = self.shape[2]
-        knots = np.arange(0, nT + 1) * old
-        query = np.arange(1, knots[-1] // new + 1) * new
         kw = {'device': self.device, 'dtype': self.dtype}
+        n_new = int((nT * old) // new)                 # == len(np.arange(1, t_end // dt_new + 1)), mobjs.py:211-212
         if kind == 'linear':
-            right = np.clip(np.searchsorted(knots, query, side='left'), 1, nT)
-            frac = (query - knots[right - 1]) / (knots[right] - knots[right - 1])
-            right_t = torch.as_tensor(right).to(self.device, non_blocking=True)
-            frac_t = torch.as_tensor(frac).to(self.device, non_blocking=True)
+            # knots k*old and query points j*new, their bracketing and weights: the same IEEE double operations as upstream's
+            # numpy grid, evaluated on the pulse's device (nothing is uploaded, nothing is read back)
+            f8 = {'device': self.device, 'dtype': torch.float64}
+            knots_t = torch.arange(0, nT + 1, **f8) * old
+            query_t = torch.arange(1, n_new + 1, **f8) * new
+            right_t = torch.searchsorted(knots_t, query_t).clamp_(1, nT)
+            lo_t, hi_t = knots_t.index_select(0, right_t - 1), knots_t.index_select(0, right_t)
+            frac_t = (query_t - lo_t) / (hi_t - lo_t)
 
             def resample(x):
                 x = x if differentiable else x.detach()
@@ -200,6 +205,8 @@ class Pulse(_Obj):
         else:
             assert not differentiable, 'only the linear kind is differentiable'
             from scipy import interpolate
+            knots = np.arange(0, nT + 1) * old
+            query = np.arange(1, knots[-1] // new + 1) * new
 
             def resample(x):
                 padded = torch.cat((torch.zeros_like(x[:, :, :1]), x.detach()), dim=2).cpu().numpy()
@@ -207,7 +214,7 @@ class Pulse(_Obj):
                 return tensor(f(query), **kw)
 
         # dt goes in as the host value: the new pulse's dwell time is then known without a device read as well
-        return Pulse(resample(self.rf), resample(self.gr), dt=tensor(new, dtype=torch.float64),
+        return Pulse(resample(self.rf), resample(self.gr), dt=new,
                      desc=f"{self.desc} + interpT\'ed: dt = {new}", **kw)
 
 

@@ -641,6 +641,27 @@ def test_applysequence_matches_chained_reference(dev, golden, dtype):
     assert all(torch.equal(a, b.grad) for a, b in zip(eager, (p1.rf, p1.gr, p2.rf, p2.gr)))
 
 
+def test_integration_md_stub_runs(dev):
+    """The ctypes stub INTEGRATION.md section 2 shows a maintainer (struct mirrors + `BlochSim.forward` over
+    `mrphy_blochsim_beff_fwd`) is executed verbatim -- only the library path is filled in -- and reproduces the oracle."""
+    import re
+    from mrphy import _cabi
+    from oracle import bloch_oracle as orc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, 'INTEGRATION.md')).read()
+    sec = md[md.index('## 2.'):md.index('## 3.')]
+    code = re.search(r'```python\n(.*?)```', sec, flags=re.S).group(1)
+    assert "'.../libmrphy_b200.so'" in code
+    ns = {}
+    exec(code.replace("'.../libmrphy_b200.so'", repr(_cabi.LIB_PATH)), ns)
+    p = _random_problem(13, 2, 70, 45, 1, has_b1=True, relax=True)
+    beff = orc.rfgr2beff(p['rf'], p['gr'], p['loc'], df=p['df'], b1=p['b1'], gamma=p['gam'])
+    col = lambda x: x.to(dev).reshape(x.shape[0], -1)                      # (N|1, nM|1) as the stub's _param expects
+    Mo = ns['BlochSim'].apply(p['M0'].to(dev), beff.to(dev), col(p['T1']), col(p['T2']), col(p['gam']),
+                              p['dt'].to(dev).reshape(1, 1))
+    assert mx(Mo, orc.blochsim_fwd(p['M0'], beff, p['T1'], p['T2'], p['gam'], p['dt'])) < ATOL64
+
+
 def test_interpT_on_device_goldens_no_sync_and_gradient(dev, golden):
     """Pulse.interpT (linear) on CUDA tensors: the reference's values (tests/test_mobjs.py:160-195 and fixtures from the
     unmodified reference, incl. the float-// length quirk and the fp32 1999-vs-2000 case), NO device->host read, and
@@ -650,11 +671,12 @@ def test_interpT_on_device_goldens_no_sync_and_gradient(dev, golden):
     g = golden('interp')
     kw = {'dtype': f64, 'device': dev}
     p = mobjs.Pulse(rf=T(g['a_rf'], dev, f64), gr=T(g['a_gr'], dev, f64), dt=dt0, **kw)
+    p2 = mobjs.Pulse(rf=T(g['b_rf'], dev, f64), gr=T(g['b_gr'], dev, f64), dt=dt0, **kw)
     torch.cuda.synchronize()
-    torch.cuda.set_sync_debug_mode('error')
+    torch.cuda.set_sync_debug_mode('error')       # no device->host read and no synchronous host->device copy from here on
     try:
         q = p.interpT(dt=dt0 * 5)
-        q2 = mobjs.Pulse(rf=T(g['b_rf'], dev, f64), gr=T(g['b_gr'], dev, f64), dt=dt0, **kw).interpT(dt=tensor(2e-6, dtype=f64))
+        q2 = p2.interpT(dt=tensor(2e-6, dtype=f64))
         q2b = q2.interpT(dt=tensor(1e-6, dtype=f64))          # resampling a resampled pulse: its dt is host-known too
     finally:
         torch.cuda.set_sync_debug_mode('default')
