@@ -178,15 +178,19 @@ class Problem:
             lo, hi = parallel.shard_range(n ** 3, rank, world)
             host = dict(rf=glob['rf'], gr=glob['gr'], loc=glob['loc'][:, lo:hi].contiguous(), df=glob['df'][:, lo:hi].contiguous(),
                         b1=glob['b1'][:, lo:hi].contiguous(), M0=glob['M0'][:, lo:hi].contiguous())
-            self.glob = glob if rank == 0 else None
             del sp_g
         else:                             # weak: every rank owns an n^3 slab of an (n*world) x n x n cube
             host = synth(N, n, n, nT, dtype, x_off=rank * n, n_x_total=n * world, interp=itp)
-            self.glob = host if world == 1 else None
         self.host = host
         self.nM = host['loc'].shape[1]
         self.tgt = torch.tensor([0., 1., 0.], **kw)
-        self.sp, self.pulse, self.d = self.make_objects(host)
+        if scaling == 'strong':          # the objects the timed region runs on are the ones mrphy.parallel.shard_spins built
+            self.sp = sp
+            self.d = {'loc': skw['loc_'], 'df': skw['Δf_'], 'b1': skw['b1Map_']}
+            self.pulse = mobjs.Pulse(rf=glob['rf'].to(dev).requires_grad_(True), gr=glob['gr'].to(dev).requires_grad_(True), **kw)
+            assert self.sp.nM == self.nM and self.d['loc'].shape == (N, self.nM, 3)
+        else:
+            self.sp, self.pulse, self.d = self.make_objects(host)
         self.units_local = float(N) * self.nM * nT
 
     def make_objects(self, src, non_blocking=False):
@@ -381,9 +385,7 @@ def parity_block(P, dtype):
     fp64 and -- the reference algorithm's own fp32 floor -- in fp32, for the default policy and for 'strict'."""
     from mrphy import _ops
     from oracle import bloch_oracle as orc
-    g, nS = P.glob, 128
-    if g is None:
-        return None
+    g, nS = P.host, 128          # this rank's slab (the whole cube at N = 1)
     gen = torch.Generator().manual_seed(7)
     nM = g['loc'].shape[1]
     sub = torch.randperm(nM, generator=gen)[:nS]
@@ -398,7 +400,7 @@ def parity_block(P, dtype):
     ref32 = orc.applypulse_fwd_bwd(*oargs, **okw, dtype=torch.float32) if dtype == torch.float32 else None
     mx = lambda a, b: float((a.detach().cpu().double() - b.double()).abs().max())
     rel = lambda a, b: float((a.detach().cpu().double() - b.double()).norm() / b.double().norm())
-    out = {'subset': f'{nS} random spins of the workload, batch entry 0, oracle/bloch_oracle.py on CPU',
+    out = {'subset': f'{nS} random spins of rank 0\'s slab of the workload, batch entry 0, oracle/bloch_oracle.py on CPU',
            'oracle_seconds': None, 'north_star': 'M 1e-5 abs (fp32) / 1e-12 (fp64); rf/gr gradients 1e-4 relative'}
     if ref32 is not None:
         out['reference_algorithm_fp32_vs_fp64'] = {'max_abs_dM': mx(ref32['Mo'], ref['Mo']), 'grf_rel': rel(ref32['grf'], ref['grf']),

@@ -177,26 +177,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // warp-cooperative async copy of rows [i0, i0+32) x bytes [t0*3*sizeof(T), +nbytes) into `tile`
-template <typename T>
+template <typename T, int ROWS = 32>
 __device__ __forceinline__ void tile_load_async(const T* __restrict__ B, int64_t B_sm, int i0, int nM, int t0, int nbytes,
                                                 unsigned char* tile, int lane) {
   const int nch = nbytes >> 4;             // chunks per row in this tile (<= 12)
   const unsigned char* base = reinterpret_cast<const unsigned char*>(B + (int64_t)t0 * 3);
   const int64_t rowb = B_sm * (int64_t)sizeof(T);
-  if (nch == CHUNKS) {                     // full tile: compile-time divisor, 12 copies per lane
+  if (nch == CHUNKS) {                     // full tile: compile-time divisor, 12 copies per lane (per 32 rows)
 #pragma unroll
-    for (int k = 0; k < CHUNKS; ++k) {
+    for (int k = 0; k < CHUNKS * ROWS / 32; ++k) {
       const int q = k * 32 + lane, r = q / CHUNKS, c = q - r * CHUNKS;
       cp_async16(tile + r * PITCHB + c * 16, base + (int64_t)min(i0 + r, nM - 1) * rowb + c * 16);
     }
     return;
   }
-  for (int q = lane; q < 32 * nch; q += 32) {
+  for (int q = lane; q < ROWS * nch; q += 32) {
     const int r = q / nch, c = q - r * nch;
     cp_async16(tile + r * PITCHB + c * 16, base + (int64_t)min(i0 + r, nM - 1) * rowb + c * 16);
   }
 }
-template <typename T>
+template <typename T, int ROWS = 32>
 __device__ __forceinline__ void tile_store16(T* __restrict__ G, int64_t G_sm, int i0, int nM, int t0, int nbytes,
                                              const unsigned char* tile, int lane) {
   const int nch = nbytes >> 4;
@@ -204,7 +204,7 @@ __device__ __forceinline__ void tile_store16(T* __restrict__ G, int64_t G_sm, in
   const int64_t rowb = G_sm * (int64_t)sizeof(T);
   if (nch == CHUNKS) {
 #pragma unroll
-    for (int k = 0; k < CHUNKS; ++k) {
+    for (int k = 0; k < CHUNKS * ROWS / 32; ++k) {
       const int q = k * 32 + lane, r = q / CHUNKS, c = q - r * CHUNKS;
       if (i0 + r < nM)
         *reinterpret_cast<float4*>(base + (int64_t)(i0 + r) * rowb + c * 16) =
@@ -212,7 +212,7 @@ __device__ __forceinline__ void tile_store16(T* __restrict__ G, int64_t G_sm, in
     }
     return;
   }
-  for (int q = lane; q < 32 * nch; q += 32) {
+  for (int q = lane; q < ROWS * nch; q += 32) {
     const int r = q / nch, c = q - r * nch;
     if (i0 + r < nM)
       *reinterpret_cast<float4*>(base + (int64_t)(i0 + r) * rowb + c * 16) =
@@ -248,7 +248,20 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
   const T* Bn = a.B + (int64_t)n * a.B_sn;
   T* Gn = BWD ? a.gB + (size_t)n * nM * (size_t)nT * 3 : nullptr;
   const T ng = -g;
-  int next_ck = BWD ? ((nT - 1) / K) * K : K;   // next step index at which a checkpoint is read / written
+  // Checkpoints by a running counter instead of a test (and an integer division for the slot) at every step: `until` steps
+  // are left before the next checkpoint, whose slot pointer moves by one stride each time.  A 4-step group that contains
+  // no checkpoint (15 of 16 at K = 64) is a clean run of steps; the others take the per-step path.
+  const size_t ck_stride = 3 * (size_t)nM;
+  int until;                 // forward: steps until state after (slot+1)*K steps is stored; backward: steps until resync
+  T* ckp;                    // slot the next checkpoint is written to / read from (this spin's x entry)
+  if (!BWD) {
+    until = K;
+    ckp = a.ckpt + (size_t)n * a.nCk * ck_stride + i;
+  } else {
+    const int last = ((nT - 1) / K) * K;           // the backward resyncs when it has undone step `last`, `last - K`, ...
+    until = nT - last;
+    ckp = a.ckpt + ((size_t)n * a.nCk + (last / K - 1)) * ck_stride + i;     // only dereferenced when last > 0
+  }
   const int ntiles = (nT + TB - 1) / TB;
   auto tile_t0 = [&](int q) { return (BWD ? ntiles - 1 - q : q) * TB; };     // q-th tile in processing order
   auto tile_len = [&](int q) { return min(TB, nT - tile_t0(q)); };
@@ -276,16 +289,22 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
         float4* v4 = reinterpret_cast<float4*>(v);
         const float4* src = reinterpret_cast<const float4*>(row + 3 * j0);
         v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
+        if (until > GS) {
 #pragma unroll
-        for (int u = 0; u < GS; ++u) {
-          step_fwd<T, POL, RELAX>(g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], k.e1, k.e2, mx, my, mz);
-          const int t1 = t0 + j0 + u + 1;
-          if (t1 == next_ck) {
-            if (t1 < nT && ok) {
-              T* cp = a.ckpt + ((size_t)n * a.nCk + (t1 / K - 1)) * 3 * (size_t)nM;
-              cp[i] = mx; cp[(size_t)nM + i] = my; cp[2 * (size_t)nM + i] = mz;
+          for (int u = 0; u < GS; ++u)
+            step_fwd<T, POL, RELAX>(g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], k.e1, k.e2, mx, my, mz);
+          until -= GS;
+        } else {
+#pragma unroll
+          for (int u = 0; u < GS; ++u) {
+            step_fwd<T, POL, RELAX>(g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], k.e1, k.e2, mx, my, mz);
+            if (--until == 0) {
+              if (t0 + j0 + u + 1 < nT && ok) {
+                ckp[0] = mx; ckp[(size_t)nM] = my; ckp[2 * (size_t)nM] = mz;
+              }
+              ckp += ck_stride;
+              until = K;
             }
-            next_ck += K;
           }
         }
       }
@@ -295,21 +314,33 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
         float4* v4 = reinterpret_cast<float4*>(v);
         float4* src = reinterpret_cast<float4*>(row + 3 * j0);
         v4[0] = src[0]; v4[1] = src[1]; v4[2] = src[2];
+        if (until > GS) {
 #pragma unroll
-        for (int u = GS - 1; u >= 0; --u) {
-          T Fx, Fy, Fz;
-          step_bwd<T, POL, RELAX, 1>(k, g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], mx, my, mz, hx, hy, hz,
-                                     Fx, Fy, Fz);
-          v[3 * u] = ng * Fx;       // dL/dBeff = -2*pi*gamma*dt * F   (sims.py:194, 234-259)
-          v[3 * u + 1] = ng * Fy;
-          v[3 * u + 2] = ng * Fz;
-          const int t = t0 + j0 + u;
-          if (t == next_ck) {
-            if (t > 0) {
-              const T* cp = a.ckpt + ((size_t)n * a.nCk + (t / K - 1)) * 3 * (size_t)nM;
-              mx = cp[i]; my = cp[(size_t)nM + i]; mz = cp[2 * (size_t)nM + i];
+          for (int u = GS - 1; u >= 0; --u) {
+            T Fx, Fy, Fz;
+            step_bwd<T, POL, RELAX, 1>(k, g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], mx, my, mz, hx, hy, hz,
+                                       Fx, Fy, Fz);
+            v[3 * u] = ng * Fx;       // dL/dBeff = -2*pi*gamma*dt * F   (sims.py:194, 234-259)
+            v[3 * u + 1] = ng * Fy;
+            v[3 * u + 2] = ng * Fz;
+          }
+          until -= GS;
+        } else {
+#pragma unroll
+          for (int u = GS - 1; u >= 0; --u) {
+            T Fx, Fy, Fz;
+            step_bwd<T, POL, RELAX, 1>(k, g * v[3 * u], g * v[3 * u + 1], g * v[3 * u + 2], mx, my, mz, hx, hy, hz,
+                                       Fx, Fy, Fz);
+            v[3 * u] = ng * Fx;
+            v[3 * u + 1] = ng * Fy;
+            v[3 * u + 2] = ng * Fz;
+            if (--until == 0) {     // step t = t0 + j0 + u undone: the state is now the one after t steps
+              if (t0 + j0 + u > 0) {
+                mx = ckp[0]; my = ckp[(size_t)nM]; mz = ckp[2 * (size_t)nM];
+              }
+              ckp -= ck_stride;
+              until = K;
             }
-            next_ck -= K;
           }
         }
         src[0] = v4[0]; src[1] = v4[1]; src[2] = v4[2];

@@ -134,7 +134,9 @@ class Pulse(_Obj):
             assert t.ndim == 1
             if t.is_cuda and (not isinstance(value, Tensor) or (value.device.type == 'cpu' and not value.requires_grad)):
                 # the value is known here without a device->host read: the checkpoint policy wants max(dt) on the host
-                _ops.note_host_max(t, float(torch.as_tensor(value).to(self.dtype).max()))
+                # (a Python float enters as float64, not torch's default float32, before it is rounded to the pulse's dtype)
+                host = value if isinstance(value, Tensor) else torch.as_tensor(value, dtype=torch.float64)
+                _ops.note_host_max(t, float(host.to(self.dtype).max()))
         elif name == 'rfmax':
             if t.ndim == 0:
                 t = t.reshape(1)

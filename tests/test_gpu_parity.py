@@ -231,6 +231,27 @@ def test_explicit_beff_vs_oracle_and_fused(dev):
         assert rel(rf.grad, ref['grf']) < tolG and rel(gr.grad, ref['ggr']) < tolG
 
 
+@pytest.mark.parametrize('nM,nT', [(200, 152), (64, 16), (1, 4), (333, 1000)])
+def test_explicit_beff_aligned_rows_fp32(dev, nM, nT):
+    """fp32 explicit-field kernels on 16-byte-aligned rows (the cp.async tile pipeline): ragged spin counts (odd, < 32, not
+    a multiple of the CTA), partial last tiles, checkpoints that fall inside tiles; values and both gradients against the
+    fp64 oracle within the fp32 rule."""
+    from oracle import bloch_oracle as orc
+    from mrphy import sims
+    p = _random_problem(100 + nM, 2, nM, nT, 1, has_b1=True, relax=True, dtype=f32)
+    beff = orc.rfgr2beff(p['rf'], p['gr'], p['loc'], df=p['df'], b1=p['b1'], gamma=p['gam']).to(f32)
+    Mo64, gM64, gB64 = orc.blochsim_adj(p['M0'], beff, p['w'], T1=p['T1'], T2=p['T2'], gamma=p['gam'], dt=p['dt'])
+    Mo32, _, _ = orc.blochsim_adj(p['M0'].to(f32), beff, p['w'].to(f32), T1=p['T1'].to(f32), T2=p['T2'].to(f32),
+                                  gamma=p['gam'].to(f32), dt=p['dt'].to(f32), dtype=f32)
+    M0 = p['M0'].to(dev, f32).requires_grad_(True)
+    B = beff.to(dev).requires_grad_(True)
+    assert (B.stride(1) * 4) % 16 == 0
+    Mo = sims.blochsim(M0, B, T1=p['T1'].to(dev, f32), T2=p['T2'].to(dev, f32), γ=p['gam'].to(dev), dt=p['dt'].to(dev))
+    (Mo * p['w'].to(dev, f32)).sum().backward()
+    assert mx(Mo, Mo64) < _fp32_bound(Mo32, Mo64)
+    assert rel(B.grad, gB64) < RTOL_G32 and rel(M0.grad, gM64) < RTOL_G32
+
+
 def test_defaults_fp64_constants_with_fp32_state(dev):
     """sims.blochsim(Mi32, Beff32) with the float64 0-dim defaults γH, dt0 (output stays fp32)."""
     from mrphy import sims
