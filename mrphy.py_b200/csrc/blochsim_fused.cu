@@ -676,15 +676,23 @@ struct Plan {
 };
 
 int sm_count_cached() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-      cudaGetLastError();
-      sms = 148;   // B200; only used for grid sizing
-    }
+  // per device ordinal: a process may drive GPUs of different size, and the first call may come from any of them
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;   // B200; only used for grid sizing
   }
-  return sms;
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] <= 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      cudaGetLastError();
+      v = 148;
+    }
+    sms[dev] = v;
+  }
+  return sms[dev];
 }
 
 int env_int(const char* name, int dflt) {
@@ -736,7 +744,7 @@ int pick_ctas(const Plan& p, int N, int occ, bool sm_aware = false, int warps_pe
   // c is, so take all the resident slots the tiles can fill.
   if (sm_aware && N == 1 && !forced && p.tiles >= 2 * sms) {
     const int c = p.tiles / sms < occ ? p.tiles / sms : occ;
-    return sms * c;
+    if (sms * c <= p.Pmax) return sms * c;     // never more ids than the partial-sum workspace was sized for (MRPHY_B200_MAX_CTAS)
   }
   int best_P = 1, best_cost = 1 << 30;
   for (int c = occ; c >= (occ + 1) / 2; --c) {
@@ -848,6 +856,7 @@ int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   if (q.Pmax > q.tiles) q.Pmax = q.tiles;
   const bool sm_aware = env_int("MRPHY_B200_SCHED", 1) != 2;
   k.P = pick_ctas(q, k.N, occ, sm_aware, BLKT / 32);
+  if (k.P < 1 || k.P > p.Pmax) return fail(MRPHY_ERR_ARG, "internal: backward grid exceeds the partial-sum workspace%s");
   g_last_P = k.P;
   dim3 grid(k.P, k.N);
   // SM-aware tile ownership when the grid is exactly c CTAs on each SM of one batch entry (see SCHED_*)

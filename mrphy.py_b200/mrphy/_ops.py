@@ -178,7 +178,8 @@ def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor
     flat[n_rf + n_gr:].zero_()
     grf = flat[:n_rf].view(rf.shape) if want_rf else flat[:0]
     ggr = flat[n_rf:n_rf + n_gr].view(a.N, 3, a.nT) if want_gr else flat[:0]
-    partials = torch.empty(L.mrphy_fused_partial_elems(a), **kw)
+    with torch.cuda.device(Mo.device):        # the workspace is sized from THIS device's SM count
+        partials = torch.empty(L.mrphy_fused_partial_elems(a), **kw)
     a.Mo, a.ckpt, a.wave = Mo.data_ptr(), ckpt.data_ptr(), wave.data_ptr()
     a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
     a.gMi, a.grf, a.ggr, a.partials = (gMi.data_ptr() if need_gmi else None), (grf.data_ptr() if want_rf else None), \

@@ -205,6 +205,23 @@ def test_multi_tile_ctas_accumulate(dev, monkeypatch):
     assert rel(gM0, ref['gM0']) < RTOL_G64
 
 
+def test_cta_cap_below_sm_aware_grid(dev, monkeypatch):
+    """MRPHY_B200_MAX_CTAS below the SM-aware backward grid (one batch entry, >= 2 tiles per SM): the grid must stay
+    inside the partial-sum workspace that was sized from the cap (out-of-bounds partial sums otherwise)."""
+    from oracle import bloch_oracle as orc
+    p = _random_problem(78, 1, 80000, 24, 1, has_b1=True, relax=True, dtype=f32)
+    g = {('in_' + k): v.numpy() for k, v in p.items() if v is not None}
+    a = run_fused(g, dev, f32, p['w'].numpy())
+    monkeypatch.setenv('MRPHY_B200_MAX_CTAS', '200')
+    b = run_fused(g, dev, f32, p['w'].numpy())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert rel(b[2], a[2]) < 1e-5 and rel(b[3], a[3]) < 1e-5        # another partition of the spin sum: rounding only
+    sub = slice(0, 64)
+    ref = orc.applypulse_fwd_bwd(p['M0'][:, sub], p['rf'], p['gr'], p['loc'][:, sub], p['w'][:, sub], df=p['df'][:, sub],
+                                 b1=p['b1'][:, sub], T1=p['T1'][:, sub], T2=p['T2'][:, sub], gamma=p['gam'][:, sub], dt=p['dt'])
+    assert mx(b[0][:, sub], ref['Mo']) < ATOL32 and rel(b[1][:, sub], ref['gM0']) < RTOL_G32
+
+
 def test_explicit_beff_vs_oracle_and_fused(dev):
     from oracle import bloch_oracle as orc
     from mrphy import sims, beffective
