@@ -52,6 +52,31 @@ __device__ __forceinline__ unsigned smid() {
 template <typename T, int PK> struct Pack { typedef T type; };
 template <> struct Pack<float, 2> { typedef f2 type; };
 
+// Staged waveform layout of one chunk.  Up to 11 rows (44 bytes per step): row-major [W][TCP], a thread reads 4 steps of a row
+// with one broadcast 128-bit load.  More rows (8 / 16 coils, fp64 with >= 2 coils): step-major [TCP][WS], WS = W padded to 4, so
+// that the W samples of ONE step are ceil(W/4) 128-bit loads instead of W scalar ones.
+template <typename T, int W> struct WaveLayout {
+  static constexpr bool STEPMAJOR = W * sizeof(T) > 44;
+  static constexpr int WS = STEPMAJOR ? ((W + 3) & ~3) : W;
+};
+// the W samples of step j of the staged chunk `wb`
+template <typename T, int W>
+__device__ __forceinline__ void load_step(const T* wb, int TCP, int j, T (&sv)[W]) {
+  if constexpr (WaveLayout<T, W>::STEPMAJOR) {
+    constexpr int WS = WaveLayout<T, W>::WS;
+    T tmp[WS];
+    const float4* src = reinterpret_cast<const float4*>(wb + (size_t)j * WS);
+    float4* dst = reinterpret_cast<float4*>(tmp);
+#pragma unroll
+    for (int e = 0; e < WS * (int)sizeof(T) / 16; ++e) dst[e] = src[e];
+#pragma unroll
+    for (int w = 0; w < W; ++w) sv[w] = tmp[w];
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; ++w) sv[w] = wb[w * TCP + j];
+  }
+}
+
 // steps per gradient-reduction tile (a CTA barrier every TR steps): the per-warp transposition tile [W][TR][32] is
 // kept <= 10 KB; 11 KB with 4 coils (TR 8 instead of 4, still 4 CTAs per SM) and 20 KB with 8 and 16 coils
 // (fp32 TR 8 / 4; 2 CTAs per SM -- measured 1.3x / 1.5x faster than TR 4 / 2 at twice the occupancy)
@@ -73,13 +98,23 @@ constexpr int pick_tr(int W, int elem) {
 }
 
 // dynamic shared memory layout of the backward kernel
+// Single coil: the per-warp transposition tile holds the W = 5 weighted gradient terms of every (spin, step).
+// Multi-coil (WRED): it holds only F = -dL/db (3 values + pad per spin and step, one 128-bit store per step instead of
+// 2 NC + 3 scalar ones) and the per-spin weights (g*b1 of every coil, g*loc) sit beside it; they are applied in the reduce
+// phase, where a lane owns ONE time step and sums over its share of the warp's spins (warp_tile_reduce_weighted).
 template <typename T, int NC, int BLKT> struct BwdSmem {
   static constexpr int W = 2 * NC + 3;
   static constexpr int NW = BLKT / 32;
-  static constexpr int TR = pick_tr(W, (int)sizeof(T));
+  static constexpr bool WRED = NC > 1;
+  static constexpr int TR = WRED ? 64 / (int)sizeof(T) : pick_tr(W, (int)sizeof(T));   // WRED: 16 (fp32), 8 (fp64)
+  static constexpr int WP = (W + 3) & ~3;                                          // weights per spin, padded to 128-bit loads
+  static constexpr int E16 = (int)sizeof(T) / 4;                                   // one F entry in 16-byte units
+  static constexpr int P16 = TR * E16 + 1;                                         // per-spin pitch of the F tile (odd: conflict-free)
+  static constexpr size_t red_bytes = WRED ? (size_t)NW * 32 * (P16 * 16 + WP * sizeof(T)) : (size_t)NW * W * TR * 32 * sizeof(T);
   static constexpr size_t wbuf = 0;                                                // T[2][W*TCMAX]
-  static constexpr size_t red = (2 * W * TCMAX * sizeof(T) + 127) / 128 * 128;     // T[NW][W][TR][32]
-  static constexpr size_t cta = red + (size_t)NW * W * TR * 32 * sizeof(T);        // T[2][NW][W][TR] (double-buffered)
+  static constexpr int WS = WaveLayout<T, W>::WS;
+  static constexpr size_t red = (2 * WS * TCMAX * sizeof(T) + 127) / 128 * 128;    // T[NW][W][TR][32]  |  F tiles + weights
+  static constexpr size_t cta = (red + red_bytes + 15) / 16 * 16;                  // T[2][NW][W][TR] (double-buffered)
   static constexpr size_t bar = (cta + (size_t)2 * NW * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
   static constexpr size_t bytes = bar + 16;
 };
@@ -206,17 +241,18 @@ __device__ __forceinline__ void load_vec3_tile(const T* base, int64_t stride, in
 template <typename T>
 __global__ void pack_waveform_kernel(const T* __restrict__ rf, int64_t rf_sn, int64_t rf_sx, int64_t rf_st, int64_t rf_sc,
                                      const T* __restrict__ gr, int64_t gr_sn, int64_t gr_sx, int64_t gr_st, int nC,
-                                     int NC, int sum_coils, int nT, int K, int TCP, int nChunks, int64_t total,
-                                     T* __restrict__ wave) {
+                                     int NC, int sum_coils, int nT, int K, int TCP, int nChunks, int WS, int stepmajor,
+                                     int64_t total, T* __restrict__ wave) {
   const int W = 2 * NC + 3;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(e % TCP);
-    const int w = (int)((e / TCP) % W);
-    const int c = (int)((e / ((int64_t)TCP * W)) % nChunks);
-    const int n = (int)(e / ((int64_t)TCP * W * nChunks));
+    // row-major chunk [WS = W][TCP]  |  step-major chunk [TCP][WS]
+    const int j = stepmajor ? (int)((e / WS) % TCP) : (int)(e % TCP);
+    const int w = stepmajor ? (int)(e % WS) : (int)((e / TCP) % WS);
+    const int c = (int)((e / ((int64_t)TCP * WS)) % nChunks);
+    const int n = (int)(e / ((int64_t)TCP * WS * nChunks));
     const int t = c * K + j;
     T v = (T)0;
-    if (j < K && t < nT) {
+    if (j < K && t < nT && w < W) {
       if (w < 2 * NC) {
         const int x = w / NC, coil = w % NC;
         const T* p = rf + n * rf_sn + x * rf_sx + t * rf_st;
@@ -239,13 +275,14 @@ template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
 __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(const KArgs<T> a) {
   typedef typename Pack<T, PK>::type V;
   constexpr int W = 2 * NC + 3;
-  __shared__ __align__(128) T wbuf[2][W * TCMAX];
+  constexpr int WS = WaveLayout<T, W>::WS;
+  __shared__ __align__(128) T wbuf[2][WS * TCMAX];
   __shared__ __align__(16) T scr[3 * BLKT * PK];
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
-  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
-  const T* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
+  const uint32_t chunk_bytes = (uint32_t)(WS * TCP * sizeof(T));
+  const T* wave_n = a.wave + (size_t)n * nChunks * WS * TCP;
   const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);
   const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
@@ -283,7 +320,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
         const int cn = (c + 1 == nChunks) ? 0 : c + 1;
         const uint32_t sn = (it + 1) & 1;
         mbar_arrive_expect_tx(&full[sn], chunk_bytes);
-        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
+        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * WS * TCP, chunk_bytes, &full[sn]);
       }
       mbar_wait(&full[it & 1], (it >> 1) & 1);
       const T* wb = wbuf[it & 1];
@@ -297,7 +334,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       };
       int j = 0;
       // 4 steps per iteration with 128-bit broadcast loads, while the staged samples fit ~40 registers
-      constexpr bool VEC4 = W * sizeof(T) <= 44;
+      constexpr bool VEC4 = !WaveLayout<T, W>::STEPMAJOR;
       for (; VEC4 && j + 4 <= ns; j += 4) {
         T wv[W][4];
 #pragma unroll
@@ -312,8 +349,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       }
       for (; j < ns; ++j) {
         T s[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) s[w] = wb[w * TCP + j];
+        load_step<T, W>(wb, TCP, j, s);
         one_step(s);
       }
       if (c + 1 < nChunks) {   // checkpoint: state after (c+1)*K steps
@@ -378,6 +414,58 @@ __device__ __forceinline__ void warp_tile_reduce(const T (*tile)[TR][32], int la
   }
 }
 
+// Multi-coil column sums: `ft` is the warp's F tile [32 spins][P16 x 16 B] (entry r of spin s = Fx, Fy, Fz, pad of step r),
+// `wt` the per-spin weights [32][WP] = (g Re b1_c)_c, (g Im b1_c)_c, g loc.  Lane l owns step r = l % TR and the spins
+// [grp*SP, (grp+1)*SP), grp = l / TR: per spin one 128-bit load of F (consecutive lanes = consecutive entries), broadcast
+// 128-bit loads of the weights, 4 NC + 3 FMAs into W register accumulators; the 32/TR groups meet through shuffles.
+// No second pass over shared memory, no per-step chain rule in the time loop.
+template <typename T, int NC, int TR, int W0, int W1>
+__device__ __forceinline__ void warp_tile_reduce_weighted(const unsigned char* ft, const T* wt, int lane, T (*out)[TR]) {
+  constexpr int W = 2 * NC + 3, WP = (W + 3) & ~3, E16 = (int)sizeof(T) / 4, P16 = TR * E16 + 1, SP = TR;   // 32 / (32 / TR)
+  constexpr bool WANT_RF = W0 == 0, WANT_GR = W1 == W;
+  const int r = lane % TR, grp = lane / TR;
+  T acc[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) acc[w] = (T)0;
+#pragma unroll 2
+  for (int q = 0; q < SP; ++q) {
+    const int sp = grp * SP + q;
+    T f[4];
+    {
+      const float4* src = reinterpret_cast<const float4*>(ft + ((size_t)sp * P16 + (size_t)r * E16) * 16);
+      float4* dst = reinterpret_cast<float4*>(f);
+#pragma unroll
+      for (int e = 0; e < E16; ++e) dst[e] = src[e];
+    }
+    T wv[WP];
+    {
+      const float4* src = reinterpret_cast<const float4*>(wt + (size_t)sp * WP);
+      float4* dst = reinterpret_cast<float4*>(wv);
+#pragma unroll
+      for (int e = 0; e < WP * (int)sizeof(T) / 16; ++e) dst[e] = src[e];
+    }
+    if constexpr (WANT_RF) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        acc[c] = fma_(wv[c], f[0], fma_(wv[NC + c], f[1], acc[c]));
+        acc[NC + c] = fma_(wv[c], f[1], fnma_(wv[NC + c], f[0], acc[NC + c]));
+      }
+    }
+    if constexpr (WANT_GR) {
+      acc[2 * NC] = fma_(wv[2 * NC], f[2], acc[2 * NC]);
+      acc[2 * NC + 1] = fma_(wv[2 * NC + 1], f[2], acc[2 * NC + 1]);
+      acc[2 * NC + 2] = fma_(wv[2 * NC + 2], f[2], acc[2 * NC + 2]);
+    }
+  }
+#pragma unroll
+  for (int w = W0; w < W1; ++w) {
+    T sum = acc[w];
+#pragma unroll
+    for (int o = TR; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane < TR) out[w][r] = sum;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward
 // ROWS: which gradients the caller wants -- bit 0 dL/drf (rows [0, 2 NC)), bit 1 dL/dgr (rows [2 NC, W)); the other rows
@@ -390,15 +478,19 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
   constexpr bool WANT_RF = (ROWS & 1) != 0, WANT_GR = (ROWS & 2) != 0;
   constexpr int W0 = WANT_RF ? 0 : 2 * NC, W1 = WANT_GR ? W : 2 * NC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T(*wbuf)[W * TCMAX] = reinterpret_cast<T(*)[W * TCMAX]>(smem_raw + L::wbuf);
-  T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile
+  constexpr int WS = L::WS;
+  T(*wbuf)[WS * TCMAX] = reinterpret_cast<T(*)[WS * TCMAX]>(smem_raw + L::wbuf);
+  T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile (single coil)
+  constexpr bool WRED = L::WRED;
+  unsigned char* const ft = smem_raw + L::red + (size_t)(threadIdx.x >> 5) * 32 * L::P16 * 16;            // WRED: this warp's F tile
+  T* const wt = reinterpret_cast<T*>(smem_raw + L::red + (size_t)NW * 32 * L::P16 * 16) + (size_t)(threadIdx.x >> 5) * 32 * L::WP;
   T(*cta)[W][TR] = reinterpret_cast<T(*)[W][TR]>(smem_raw + L::cta);          // per-warp tile sums
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::bar);
   __shared__ __align__(16) T scr[3 * BLKT * PK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM;
-  const uint32_t chunk_bytes = (uint32_t)(W * TCP * sizeof(T));
-  const T* wave_n = a.wave + (size_t)n * nChunks * W * TCP;
+  const uint32_t chunk_bytes = (uint32_t)(WS * TCP * sizeof(T));
+  const T* wave_n = a.wave + (size_t)n * nChunks * WS * TCP;
   const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);
 #define NCTA ((int)gridDim.x)   /* constant-bank operand, not a register */
   __shared__ int s_vid, s_sweep;
@@ -439,7 +531,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
       for (int e = tid; e < W * nT; e += BLKT) part[e] = (T)0;
     } else if (tid == 0) {
       mbar_arrive_expect_tx(&full[it & 1], chunk_bytes);
-      bulk_g2s(wbuf[it & 1], wave_n + (size_t)(nChunks - 1) * W * TCP, chunk_bytes, &full[it & 1]);
+      bulk_g2s(wbuf[it & 1], wave_n + (size_t)(nChunks - 1) * WS * TCP, chunk_bytes, &full[it & 1]);
     }
   bool first = true;
   for (int tile = vid; tile < tiles; tile += NCTA, first = false) {
@@ -462,6 +554,15 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
     load_vec3_tile<T, V, PK, BLKT>(a.gMo + (int64_t)n * a.gMo_sn, a.gMo_sm, tile, nM, idx, scr, hx, hy, hz);
     to_frame(k, mx, my);   // Mo and dL/dMo enter the spin's transverse frame, dL/dMi leaves it (single coil)
     to_frame(k, hx, hy);
+    if constexpr (WRED) {   // this spin's weights for the reduce phase (the previous tile's last reduce ended with a CTA barrier)
+      T* wrow = wt + (size_t)lane * L::WP;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) { wrow[q] = lane0(k.cbr[q]); wrow[NC + q] = lane0(k.cbi[q]); }
+      wrow[2 * NC] = lane0(k.glx); wrow[2 * NC + 1] = lane0(k.gly); wrow[2 * NC + 2] = lane0(k.glz);
+#pragma unroll
+      for (int q = W; q < L::WP; ++q) wrow[q] = (T)0;
+      __syncwarp();
+    }
     {   // padding lanes carry a zero adjoint: they add nothing to the spin sums
       const T z0 = ok[0] ? (T)1 : (T)0, z1 = ok[PK - 1] ? (T)1 : (T)0;
       const V zm = mkv(z0, z1, (V*)nullptr);
@@ -472,7 +573,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         const int cn = (c == 0) ? nChunks - 1 : c - 1;
         const uint32_t sn = (it + 1) & 1;
         mbar_arrive_expect_tx(&full[sn], chunk_bytes);
-        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * W * TCP, chunk_bytes, &full[sn]);
+        bulk_g2s(wbuf[sn], wave_n + (size_t)cn * WS * TCP, chunk_bytes, &full[sn]);
       }
       // prefetch the checkpoint this chunk ends on (state after c*K steps) while we compute
       V kx = mx, ky = my, kz = mz;
@@ -492,6 +593,14 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         for (int q = 0; q < NC; ++q) { rx[q] = V(s[q]); ry[q] = V(s[NC + q]); }
         field<V, NC>(k, rx, ry, V(s[2 * NC]), V(s[2 * NC + 1]), V(s[2 * NC + 2]), bx, by, bz);
         step_bwd<V, POL, RELAX, NC>(k, bx, by, bz, mx, my, mz, hx, hy, hz, Fx, Fy, Fz);
+        if constexpr (WRED) {   // multi-coil: only F goes to the tile; the weights are applied in the reduce phase
+          T fv[4] = {lane0(Fx), lane0(Fy), lane0(Fz), (T)0};
+          float4* dst = reinterpret_cast<float4*>(ft + ((size_t)lane * L::P16 + (size_t)row * L::E16) * 16);
+          const float4* src = reinterpret_cast<const float4*>(fv);
+#pragma unroll
+          for (int e = 0; e < L::E16; ++e) dst[e] = src[e];
+          return;
+        }
         if constexpr (WANT_RF) {
 #pragma unroll
           for (int q = 0; q < NC; ++q) {
@@ -509,7 +618,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
       };
       for (int j1 = ns; j1 > 0;) {
         const int j0 = ((j1 - 1) / TR) * TR;   // tile [j0, j1), at most TR steps
-        constexpr bool VEC4 = W * sizeof(T) <= 44 && TR % 4 == 0;
+        constexpr bool VEC4 = !WaveLayout<T, W>::STEPMAJOR && TR % 4 == 0;
         if (VEC4 && j1 - j0 == TR) {
 #pragma unroll 1
           for (int jj = TR - 4; jj >= 0; jj -= 4) {
@@ -527,14 +636,14 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
         } else {
           for (int j = j1 - 1; j >= j0; --j) {
             T s[W];
-#pragma unroll
-            for (int w = 0; w < W; ++w) s[w] = wb[w * TCP + j];
+            load_step<T, W>(wb, TCP, j, s);
             one_step(s, j - j0);
           }
         }
         __syncwarp();
         T(*ctab)[W][TR] = cta + (size_t)(red_par & 1) * NW;   // this tile's half of the double buffer
-        warp_tile_reduce<T, W, TR, W0, W1>(red[warp], lane, ctab[warp]);
+        if constexpr (WRED) warp_tile_reduce_weighted<T, NC, TR, W0, W1>(ft, wt, lane, ctab[warp]);
+        else warp_tile_reduce<T, W, TR, W0, W1>(red[warp], lane, ctab[warp]);
         __syncthreads();   // the only CTA barrier per tile: `cta` alternates, `red` is re-written after it
         for (int e = tid; e < (W1 - W0) * TR; e += BLKT) {   // fixed-order combine of the warps
           const int w = W0 + e / TR, r = e % TR;
@@ -669,6 +778,7 @@ struct Plan {
   int PK;        // spins per thread (2 = packed f2 arithmetic, fp32 single-coil only)
   int BLKT;      // threads per CTA
   int K, TCP, nChunks, W;
+  int WS, stepmajor;   // staged waveform layout (WaveLayout): row-major [W][TCP] or step-major [TCP][WS]
   int sum_coils; // no b1Map
   int tiles;     // spin tiles per batch entry (BLKT*PK spins each)
   int Pmax;      // upper bound on CTAs per batch entry (sizes the partial-sum workspace)
@@ -712,6 +822,8 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   if (nc > 16) return fail(MRPHY_ERR_ARG, "more than 16 transmit coils with a b1Map are not supported%s");
   p->NC = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : nc <= 8 ? 8 : 16;
   p->W = 2 * p->NC + 3;
+  p->stepmajor = (size_t)p->W * (a->dtype == MRPHY_F64 ? 8 : 4) > 44;
+  p->WS = p->stepmajor ? ((p->W + 3) & ~3) : p->W;
   p->K = a->K;
   p->TCP = (a->K + 3) & ~3;
   p->nChunks = (a->nT + a->K - 1) / a->K;
@@ -774,7 +886,7 @@ extern "C" size_t mrphy_fused_ckpt_elems(const mrphy_fused_args* a) {
 extern "C" size_t mrphy_fused_wave_elems(const mrphy_fused_args* a) {
   Plan p;
   if (make_plan(a, &p, false) != MRPHY_OK) return 0;
-  return (size_t)a->N * p.nChunks * p.W * p.TCP;
+  return (size_t)a->N * p.nChunks * p.WS * p.TCP;
 }
 extern "C" size_t mrphy_fused_partial_elems(const mrphy_fused_args* a) {
   Plan p;
@@ -816,12 +928,12 @@ KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
 
 template <typename T>
 int launch_pack(const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
-  const int64_t total = (int64_t)a->N * p.nChunks * p.W * p.TCP;
+  const int64_t total = (int64_t)a->N * p.nChunks * p.WS * p.TCP;
   const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   const int64_t rf_sc = (a->flags & MRPHY_RF_COIL_DIM) ? a->rf_sc : 0;
   pack_waveform_kernel<T><<<grid, 256, 0, st>>>((const T*)a->rf, a->rf_sn, a->rf_sx, a->rf_st, rf_sc, (const T*)a->gr,
                                                 a->gr_sn, a->gr_sx, a->gr_st, a->nC, p.NC, p.sum_coils, a->nT, p.K,
-                                                p.TCP, p.nChunks, total, (T*)a->wave);
+                                                p.TCP, p.nChunks, p.WS, p.stepmajor, total, (T*)a->wave);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;

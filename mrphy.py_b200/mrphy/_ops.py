@@ -155,8 +155,10 @@ def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flag
     chunks = (nT + K - 1) // K
     nc = 1 if b1 is None else (rf.shape[3] if rf.ndim == 4 else 1)
     NC = next(c for c in (1, 2, 4, 8, 16) if nc <= c)           # coils held in registers (csrc: make_plan)
+    W = 2 * NC + 3
+    WS = (W + 3) // 4 * 4 if W * Mi.element_size() > 44 else W  # csrc: WaveLayout (step-major staging for many rows)
     return (Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * (chunks - 1) * 3 * nM, 1),)),
-            Mi.new_empty((N * chunks * (2 * NC + 3) * ((K + 3) // 4 * 4),)))
+            Mi.new_empty((N * chunks * WS * ((K + 3) // 4 * 4),)))
 
 
 def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
