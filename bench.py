@@ -539,7 +539,8 @@ def run_ours(args):
                 cap = json.load(f)['captures'].get(f'{args.workload}_{args.dtype}_bwd')
             if cap:
                 m = cap['metrics']
-                traffic = (m['dram__bytes_read.sum']['value'] + m['dram__bytes_write.sum']['value']) * 1e6
+                scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+                traffic = sum(m[k]['value'] * scale[m[k]['unit']] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
                 traffic_src = 'static: profiles/r2_ncu_summary.json (ncu --set full capture of this kernel on this workload), not measured in this run'
         except Exception:
             pass

@@ -354,15 +354,17 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(con
       }
       if (c + 1 < nChunks) {   // checkpoint: state after (c+1)*K steps
         T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
+        // streaming (evict-first) stores and, in the backward, loads: 12.7 GB of checkpoints at C5 pass through the 126-MB L2
+        // exactly once and must not push the L2-resident partial sums out (ncu: 1.8 GB of write-backs per launch otherwise)
         if (ok[0]) {
-          cp[idx[0]] = getq<0>(mx);
-          cp[(size_t)nM + idx[0]] = getq<0>(my);
-          cp[2 * (size_t)nM + idx[0]] = getq<0>(mz);
+          __stcs(cp + idx[0], getq<0>(mx));
+          __stcs(cp + (size_t)nM + idx[0], getq<0>(my));
+          __stcs(cp + 2 * (size_t)nM + idx[0], getq<0>(mz));
         }
         if (PK == 2 && ok[PK - 1]) {
-          cp[idx[PK - 1]] = getq<1>(mx);
-          cp[(size_t)nM + idx[PK - 1]] = getq<1>(my);
-          cp[2 * (size_t)nM + idx[PK - 1]] = getq<1>(mz);
+          __stcs(cp + idx[PK - 1], getq<1>(mx));
+          __stcs(cp + (size_t)nM + idx[PK - 1], getq<1>(my));
+          __stcs(cp + 2 * (size_t)nM + idx[PK - 1], getq<1>(mz));
         }
       }
       __syncthreads();   // everyone is done with wbuf[it&1] before it is refilled
@@ -579,9 +581,9 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
       V kx = mx, ky = my, kz = mz;
       if (c > 0) {
         const T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + (c - 1)) * 3 * (size_t)nM;
-        kx = mkv(cp[idx[0]], cp[idx[PK - 1]], (V*)nullptr);
-        ky = mkv(cp[(size_t)nM + idx[0]], cp[(size_t)nM + idx[PK - 1]], (V*)nullptr);
-        kz = mkv(cp[2 * (size_t)nM + idx[0]], cp[2 * (size_t)nM + idx[PK - 1]], (V*)nullptr);
+        kx = mkv(__ldcs(cp + idx[0]), __ldcs(cp + idx[PK - 1]), (V*)nullptr);
+        ky = mkv(__ldcs(cp + (size_t)nM + idx[0]), __ldcs(cp + (size_t)nM + idx[PK - 1]), (V*)nullptr);
+        kz = mkv(__ldcs(cp + 2 * (size_t)nM + idx[0]), __ldcs(cp + 2 * (size_t)nM + idx[PK - 1]), (V*)nullptr);
       }
       mbar_wait(&full[it & 1], (it >> 1) & 1);
       const T* wb = wbuf[it & 1];
