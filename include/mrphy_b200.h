@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MRPHY_ABI_VERSION 3
+#define MRPHY_ABI_VERSION 4
 
 enum mrphy_dtype { MRPHY_F32 = 0, MRPHY_F64 = 1 };
 
@@ -146,12 +146,19 @@ typedef struct mrphy_rfgr2beff_args {
   const void* gBeff;                                  /* adjoint in: dL/dBeff (N,nM,nT,3) contiguous */
   void* grf; void* ggr;                               /* adjoint out: dL/drf like rf (contiguous), dL/dgr (N,3,nT) */
   void* partials;                                     /* adjoint workspace, mrphy_rfgr2beff_partial_elems() */
+  void* gloc; void* gsz; void* gb1;                   /* per-spin adjoint out (mrphy_rfgr2beff_spin_grads), each may be NULL */
 } mrphy_rfgr2beff_args;
 int mrphy_rfgr2beff(const mrphy_rfgr2beff_args* a, void* cuda_stream);
 /* The spin sums of the autograd of rfgr2beff (upstream: bmm / expand / sum backward): dL/drf_c = sum_i conj(b1_c)*gBxy,
  * dL/dgr = sum_i loc*gBz -- one pass over dL/dBeff (12 B/spin.step read, fp32), two-stage and bitwise reproducible. */
 size_t mrphy_rfgr2beff_partial_elems(const mrphy_rfgr2beff_args* a);
 int mrphy_rfgr2beff_bwd(const mrphy_rfgr2beff_args* a, void* cuda_stream);
+/* The per-spin half of that autograd -- sums over TIME instead of over spins -- in the same single pass over dL/dBeff:
+ *   gloc (N,nM,3)     = sum_t gr[:,t] * gBz[t]                        (dL/dloc)
+ *   gsz  (N,nM)       = sum_t gBz[t]                                  (dL/ddf = gsz/gamma, dL/dgamma = -gsz*df/gamma^2: caller)
+ *   gb1  (N,nM,2,nC)  = sum_t (rx_c gBx + ry_c gBy,  rx_c gBy - ry_c gBx)   (dL/db1Map; nC = 1 when rf has no coil dim)
+ * contiguous outputs, any of them NULL = not wanted.  One warp per spin, lanes along time (384-byte coalesced reads).  */
+int mrphy_rfgr2beff_spin_grads(const mrphy_rfgr2beff_args* a, void* cuda_stream);
 
 /* Hargreaves A/B propagation, replacing beffective.beff2ab (beffective.py:40-104) and its autograd:
  * A (N,nM,3,3), B (N,nM,3) contiguous out; E1, E2 are the per-step relaxation FACTORS as upstream.

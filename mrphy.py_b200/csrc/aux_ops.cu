@@ -436,6 +436,71 @@ using namespace mrphy;
   if (!a) return fail(MRPHY_ERR_ARG, "null args%s")
 #define DTYPE_OK(a) ((a)->dtype == MRPHY_F32 || (a)->dtype == MRPHY_F64)
 
+// Per-spin gradients of rfgr2beff (autograd of beffective.py:137-167 w.r.t. loc, df, gamma, b1Map): reductions over TIME.
+// One warp per spin, lanes along time: every iteration reads 32 consecutive (gBx, gBy, gBz) = 384 contiguous bytes of the
+// spin's row; the waveform samples of those steps come from L1/L2 (every warp reads the same 20 KB).  3 + 1 + 2 NC running
+// sums per lane, combined with shuffles at the end.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) rfgr2beff_spin_grads_kernel(const mrphy_rfgr2beff_args a) {
+  const int lane = threadIdx.x & 31, n = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= a.nM) return;
+  const T* G = (const T*)a.gBeff + ((size_t)n * a.nM + (size_t)i) * (size_t)a.nT * 3;
+  const T* rf = (const T*)a.rf + (int64_t)n * a.rf_sn;
+  const T* gr = (const T*)a.gr + (int64_t)n * a.gr_sn;
+  const int64_t rf_sc = (a.flags & MRPHY_RF_COIL_DIM) ? a.rf_sc : 0;
+  const bool want_b1 = a.gb1 != nullptr, want_loc = a.gloc != nullptr;
+  T al[3] = {0, 0, 0}, az = 0, abr[NC], abi[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) abr[c] = abi[c] = (T)0;
+#pragma unroll 2
+  for (int t = lane; t < a.nT; t += 32) {
+    const T gx = G[3 * (size_t)t], gy = G[3 * (size_t)t + 1], gz = G[3 * (size_t)t + 2];
+    az += gz;
+    if (want_loc) {
+#pragma unroll
+      for (int x = 0; x < 3; ++x) al[x] = fma(gr[x * a.gr_sx + t * a.gr_st], gz, al[x]);
+    }
+    if (want_b1) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (c < a.nC) {
+          const T rx = rf[t * a.rf_st + c * rf_sc], ry = rf[a.rf_sx + t * a.rf_st + c * rf_sc];
+          abr[c] = fma(rx, gx, fma(ry, gy, abr[c]));
+          abi[c] = fma(rx, gy, fma(-ry, gx, abi[c]));
+        }
+      }
+    }
+  }
+  auto wsum = [&](T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  az = wsum(az);
+  const size_t s = (size_t)n * a.nM + (size_t)i;
+  if (a.gsz && lane == 0) ((T*)a.gsz)[s] = az;
+  if (want_loc) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const T v = wsum(al[x]);
+      if (lane == 0) ((T*)a.gloc)[s * 3 + x] = v;
+    }
+  }
+  if (want_b1) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < a.nC) {
+        const T vr = wsum(abr[c]), vi = wsum(abi[c]);
+        if (lane == 0) {
+          ((T*)a.gb1)[(s * 2) * a.nC + c] = vr;
+          ((T*)a.gb1)[(s * 2 + 1) * a.nC + c] = vi;
+        }
+      }
+    }
+  }
+}
+
 extern "C" size_t mrphy_sizeof_args(int which) {
   switch (which) {
     case 0: return sizeof(mrphy_param);
@@ -566,6 +631,34 @@ static int check_beff2ab(const mrphy_beff2ab_args* a, bool bwd) {
   if ((a->ckpt || bwd) && a->K < 1) return fail(MRPHY_ERR_ARG, "K must be >= 1%s");
   if (bwd && (!a->ckpt || !a->gA || !a->gB || !a->gBeff || !a->gP)) return fail(MRPHY_ERR_ARG, "ckpt, gA, gB, gBeff, gP are required%s");
   return MRPHY_OK;
+}
+
+namespace {
+template <typename T>
+int launch_spin_grads(const mrphy_rfgr2beff_args* a, cudaStream_t st) {
+  const int nc = (a->flags & MRPHY_RF_COIL_DIM) ? a->nC : 1;
+  dim3 grid((unsigned)((a->nM + 7) / 8), a->N);
+  if (nc <= 1) rfgr2beff_spin_grads_kernel<T, 1><<<grid, 256, 0, st>>>(*a);
+  else if (nc <= 2) rfgr2beff_spin_grads_kernel<T, 2><<<grid, 256, 0, st>>>(*a);
+  else if (nc <= 4) rfgr2beff_spin_grads_kernel<T, 4><<<grid, 256, 0, st>>>(*a);
+  else if (nc <= 8) rfgr2beff_spin_grads_kernel<T, 8><<<grid, 256, 0, st>>>(*a);
+  else rfgr2beff_spin_grads_kernel<T, 16><<<grid, 256, 0, st>>>(*a);
+  ++launch_count();
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+}  // namespace
+
+extern "C" int mrphy_rfgr2beff_spin_grads(const mrphy_rfgr2beff_args* a, void* cuda_stream) {
+  BEGIN_CALL();
+  if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
+  if (!DTYPE_OK(a) || a->N < 1 || a->nM < 1 || a->nT < 1 || a->nC < 1 || a->N > 65535)
+    return fail(MRPHY_ERR_ARG, "bad sizes or dtype%s");
+  if (!a->gBeff || !a->rf || !a->gr) return fail(MRPHY_ERR_ARG, "gBeff, rf and gr are required%s");
+  if (!a->gloc && !a->gsz && !a->gb1) return MRPHY_OK;
+  if (a->nC > 16) return fail(MRPHY_ERR_ARG, "more than 16 transmit coils are not supported%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return a->dtype == MRPHY_F64 ? launch_spin_grads<double>(a, st) : launch_spin_grads<float>(a, st);
 }
 
 extern "C" size_t mrphy_beff2ab_ckpt_elems(const mrphy_beff2ab_args* a) {

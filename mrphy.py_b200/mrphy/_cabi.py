@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('MRPHY_B200_LIB') or os.path.join(os.path.dirname(_HER
 MRPHY_F32, MRPHY_F64 = 0, 1
 FLAG_TRIG_PRECISE, FLAG_NEED_GMI, FLAG_RF_COIL_DIM, FLAG_NEED_GBEFF, FLAG_TRIG_FAST_BWD = 1, 2, 4, 8, 16
 FLAG_SKIP_GRF, FLAG_SKIP_GGR = 32, 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 
@@ -60,6 +60,7 @@ class RfGr2BeffArgs(ctypes.Structure):
         ('b1', c_vp), ('b1_sn', c_i64), ('b1_sm', c_i64),
         ('df', Param), ('gamma', Param),
         ('Beff', c_vp), ('gBeff', c_vp), ('grf', c_vp), ('ggr', c_vp), ('partials', c_vp),
+        ('gloc', c_vp), ('gsz', c_vp), ('gb1', c_vp),
     ]
 
 
@@ -136,6 +137,7 @@ EXPORTS = {   # name -> (restype, argtypes); tests check every symbol include/mr
     'mrphy_rfgr2beff': (ctypes.c_int, [ctypes.POINTER(RfGr2BeffArgs), c_vp]),
     'mrphy_rfgr2beff_partial_elems': (ctypes.c_size_t, [ctypes.POINTER(RfGr2BeffArgs)]),
     'mrphy_rfgr2beff_bwd': (ctypes.c_int, [ctypes.POINTER(RfGr2BeffArgs), c_vp]),
+    'mrphy_rfgr2beff_spin_grads': (ctypes.c_int, [ctypes.POINTER(RfGr2BeffArgs), c_vp]),
     'mrphy_beff2ab_ckpt_elems': (ctypes.c_size_t, [ctypes.POINTER(Beff2abArgs)]),
     'mrphy_beff2ab': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),
     'mrphy_beff2ab_bwd': (ctypes.c_int, [ctypes.POINTER(Beff2abArgs), c_vp]),

@@ -347,6 +347,41 @@ def _impl_rfgr2beff_bwd(gB: Tensor, rf: Tensor, gr: Tensor, loc: Tensor, b1: Opt
     return grf, ggr
 
 
+def _impl_rfgr2beff_spin_grads(gB: Tensor, rf: Tensor, gr: Tensor, want_loc: bool, want_b1: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """gB (N,nM,nT,3) contiguous -> (gloc (N,nM,3) = sum_t gr*gBz, gsz (N,nM) = sum_t gBz, gb1 (N,nM,2,nC)): the per-spin
+    (time-summed) half of rfgr2beff's chain rule in one pass over gB; unwanted outputs come back empty."""
+    L = _cabi.lib()
+    a = _cabi.RfGr2BeffArgs()
+    N, nM, nT = gB.shape[0], gB.shape[1], gB.shape[2]
+    nC = rf.shape[3] if rf.ndim == 4 else 1
+    a.dtype = _cabi.MRPHY_F64 if gB.dtype == torch.float64 else _cabi.MRPHY_F32
+    a.flags = _cabi.FLAG_RF_COIL_DIM if rf.ndim == 4 else 0
+    a.N, a.nM, a.nT, a.nC = N, nM, nT, nC
+    a.rf, a.rf_sn, a.rf_sx, a.rf_st = rf.data_ptr(), _bstride(rf, 0), rf.stride(1), rf.stride(2)
+    a.rf_sc = rf.stride(3) if rf.ndim == 4 else 0
+    a.gr, a.gr_sn, a.gr_sx, a.gr_st = gr.data_ptr(), _bstride(gr, 0), gr.stride(1), gr.stride(2)
+    kw = {'dtype': gB.dtype, 'device': gB.device}
+    gloc = torch.empty((N, nM, 3) if want_loc else (0,), **kw)
+    gsz = torch.empty((N, nM), **kw)
+    gb1 = torch.empty((N, nM, 2, nC) if want_b1 else (0,), **kw)
+    a.gBeff, a.gsz = gB.data_ptr(), gsz.data_ptr()
+    if want_loc:
+        a.gloc = gloc.data_ptr()
+    if want_b1:
+        a.gb1 = gb1.data_ptr()
+    with torch.cuda.device(gB.device):
+        _cabi.check(L.mrphy_rfgr2beff_spin_grads(a, _stream()), 'rfgr2beff_spin_grads')
+    _cabi.count_launches()
+    return gloc, gsz, gb1
+
+
+def _fake_rfgr2beff_spin_grads(gB, rf, gr, want_loc, want_b1):
+    N, nM = gB.shape[0], gB.shape[1]
+    nC = rf.shape[3] if rf.ndim == 4 else 1
+    return (gB.new_empty((N, nM, 3) if want_loc else (0,)), gB.new_empty((N, nM)),
+            gB.new_empty((N, nM, 2, nC) if want_b1 else (0,)))
+
+
 def _fake_rfgr2beff_bwd(gB, rf, gr, loc, b1):
     return rf.new_empty(rf.shape), gr.new_empty((loc.shape[0], 3, rf.shape[2]))
 
@@ -639,7 +674,7 @@ def _mask_backward(ctx, g):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor', 'clamp_waveform': '(Tensor x, Tensor lim, float eps, int kind) -> Tensor', 'clamp_waveform_bwd': '(Tensor g, Tensor x, Tensor lim, float eps, int kind) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'rfgr2beff_spin_grads': '(Tensor gB, Tensor rf, Tensor gr, bool want_loc, bool want_b1) -> (Tensor, Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor', 'clamp_waveform': '(Tensor x, Tensor lim, float eps, int kind) -> Tensor', 'clamp_waveform_bwd': '(Tensor g, Tensor x, Tensor lim, float eps, int kind) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -655,6 +690,7 @@ blochsim_beff_fwd = _register('blochsim_beff_fwd', _impl_blochsim_beff_fwd, _fak
 blochsim_beff_bwd = _register('blochsim_beff_bwd', _impl_blochsim_beff_bwd, _fake_blochsim_beff_bwd)
 rfgr2beff_cuda = _register('rfgr2beff', _impl_rfgr2beff, _fake_rfgr2beff)
 rfgr2beff_bwd_cuda = _register('rfgr2beff_bwd', _impl_rfgr2beff_bwd, _fake_rfgr2beff_bwd)
+rfgr2beff_spin_grads_cuda = _register('rfgr2beff_spin_grads', _impl_rfgr2beff_spin_grads, _fake_rfgr2beff_spin_grads)
 beff2ab_cuda = _register('beff2ab', _impl_beff2ab, _fake_beff2ab)
 beff2ab_bwd_cuda = _register('beff2ab_bwd', _impl_beff2ab_bwd, _fake_beff2ab_bwd)
 beff2uphi_cuda = _register('beff2uphi', _impl_beff2uphi, _fake_beff2uphi)

@@ -148,7 +148,8 @@ def beff2ab(
 
 class _RfGr2Beff(torch.autograd.Function):
     r"""CUDA field synthesis (one pass, 12 B/spin·step written) with the chain rule of beffective.py:137-167
-    written out: the reference gets these gradients from autograd through bmm / broadcast / stack."""
+    written out: the reference gets these gradients from autograd through bmm / broadcast / stack.  Backward: the sums
+    over spins (∂rf, ∂gr) and the sums over time (∂loc, ∂Δf, ∂b1Map, ∂γ) are ONE kernel each over the dense ∂L/∂Beff."""
 
     @staticmethod
     def forward(ctx, rf, gr, loc, Δf, b1Map, γ):
@@ -177,32 +178,32 @@ class _RfGr2Beff(torch.autograd.Function):
         rf, gr, loc, df, b1, γ = ctx.saved_tensors
         need, Nd = ctx.needs_input_grad, ctx.Nd
         N, nM = loc.shape[0], loc.shape[1]
-        gB = gB.reshape(N, nM, -1, 3)
-        gx, gy, gz = gB.unbind(-1)
+        gB = gB.reshape(N, nM, -1, 3).contiguous()
         out = [None] * 6
-        rf4 = rf if rf.ndim == 4 else rf[..., None]
         if need[0] or need[1]:       # the two sums over spins: one native pass over dL/dBeff
-            grf, ggr = _ops.rfgr2beff_bwd_cuda(gB.contiguous(), rf, gr, loc, b1)
+            grf, ggr = _ops.rfgr2beff_bwd_cuda(gB, rf, gr, loc, b1)
             out[0], out[1] = (grf if need[0] else None), (ggr if need[1] else None)
-        if need[2]:
-            out[2] = torch.einsum('nct,nmt->nmc', gr, gz).reshape(ctx.shapes[0])
-        gzs = gz.sum(-1).reshape((N,) + Nd) if (df is not None and (need[3] or need[5])) else None
-        γf = γ.expand(N, nM).reshape((N,) + Nd) if gzs is not None else None
-        if need[3] and df is not None:
-            out[3] = _reduce_to(gzs / γf, ctx.shapes[1])
-        if need[4] and b1 is not None:
-            rx, ry = rf4[:, 0], rf4[:, 1]                                              # (N,nT,nC)
-            gbr = torch.einsum('ntc,nmt->nmc', rx, gx) + torch.einsum('ntc,nmt->nmc', ry, gy)
-            gbi = torch.einsum('ntc,nmt->nmc', rx, gy) - torch.einsum('ntc,nmt->nmc', ry, gx)
-            gb = torch.stack((gbr, gbi), dim=2).reshape((N,) + Nd + (2, -1))          # (N,*Nd,2,nC)
-            shp = ctx.shapes[2]
-            if len(shp) == len(Nd) + 2:                                                # b1Map given without coil dim
-                out[4] = _reduce_to(gb[..., 0], shp, tail=1)
-            else:
-                out[4] = _reduce_to(gb, shp, tail=2)
-        if need[5] and df is not None:
-            dff = df.expand(N, nM).reshape((N,) + Nd)
-            out[5] = _reduce_to(-gzs * dff / (γf * γf), ctx.shapes[3])
+        want_loc, want_b1 = bool(need[2]), bool(need[4] and b1 is not None)
+        want_z = df is not None and (need[3] or need[5])
+        if want_loc or want_b1 or want_z:    # the sums over time (per-spin gradients): one more native pass
+            gloc, gsz, gb1 = _ops.rfgr2beff_spin_grads_cuda(gB, rf, gr, want_loc, want_b1)
+            if want_loc:
+                out[2] = gloc.reshape(ctx.shapes[0])
+            if want_z:
+                gzs = gsz.reshape((N,) + Nd)
+                γf = γ.expand(N, nM).reshape((N,) + Nd)
+                if need[3]:
+                    out[3] = _reduce_to(gzs / γf, ctx.shapes[1])
+                if need[5]:
+                    dff = df.expand(N, nM).reshape((N,) + Nd)
+                    out[5] = _reduce_to(-gzs * dff / (γf * γf), ctx.shapes[3])
+            if want_b1:
+                gb = gb1.reshape((N,) + Nd + (2, -1))                                      # (N,*Nd,2,nC)
+                shp = ctx.shapes[2]
+                if len(shp) == len(Nd) + 2:                                                # b1Map given without coil dim
+                    out[4] = _reduce_to(gb[..., 0], shp, tail=1)
+                else:
+                    out[4] = _reduce_to(gb, shp, tail=2)
         return tuple(out)
 
 
