@@ -171,9 +171,11 @@ def _random_problem(seed, N, nM, nT, nC, has_b1, relax, dtype=f64):
 
 
 @pytest.mark.parametrize('K', [1, 7, 16, 64])
-@pytest.mark.parametrize('shape', [(1, 130, 75, 1), (2, 300, 333, 2), (1, 1, 1, 0), (3, 129, 64, 4)])
+@pytest.mark.parametrize('shape', [(1, 130, 75, 1), (2, 300, 333, 2), (1, 1, 1, 0), (3, 129, 64, 4), (1, 200, 70, 8),
+                                   (2, 131, 33, 16), (1, 150, 41, 3)])
 def test_fused_vs_oracle_ragged(dev, K, shape):
-    """Ragged sizes (nM not a multiple of the CTA, nT not a multiple of K), nCoils 1/2/4, N>1."""
+    """Ragged sizes (nM not a multiple of the CTA, nT not a multiple of K), nCoils 1/2/3/4/8/16 (8 and 16: step-major staged
+    waveform; all multi-coil: weights applied in the reduce phase), N>1."""
     from oracle import bloch_oracle as orc
     N, nM, nT, nC = shape
     p = _random_problem(10 + nM, N, nM, nT, nC, has_b1=nC > 0, relax=True)
@@ -1160,7 +1162,7 @@ def test_gradient_rows_on_demand(dev, dtype):
     from mrphy import _ops
     gen = torch.Generator().manual_seed(9)
     U = lambda *s: (torch.rand(s, generator=gen, dtype=f64) * 2 - 1)
-    for N, nM, nT, nC in ((1, 148 * 4 * 256 + 77, 130, 0), (2, 300, 97, 2)):
+    for N, nM, nT, nC in ((1, 148 * 4 * 256 + 77, 130, 0), (2, 300, 97, 2), (1, 517, 70, 8)):
         rf = (U(N, 2, nT, nC) if nC else U(N, 2, nT)) * 0.1
         b1 = U(N, nM, 2, max(nC, 1)) * 0.1
         b1[:, :, 0] += 1
