@@ -167,6 +167,10 @@ __global__ void __launch_bounds__(EBLK) beff_bwd_kernel(const EArgs<T> a, const 
 #ifndef MRPHY_BEFF_ROWB
 #define MRPHY_BEFF_ROWB 192
 #endif
+#ifndef MRPHY_BEFF_NST
+#define MRPHY_BEFF_NST 2
+#endif
+constexpr int NST = MRPHY_BEFF_NST;   // tiles in the per-warp ring (NST - 1 in flight while one is consumed)
 constexpr int ROWB = MRPHY_BEFF_ROWB, PITCHB = ROWB + 16, CHUNKS = ROWB / 16;   // 12 chunks of 16 B per row (pitch 13 x 16 B: odd)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
   constexpr int PITCH = PITCHB / (int)sizeof(T);       // row pitch in elements
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = blockIdx.y;
-  unsigned char* buf0 = smem_raw + (size_t)warp * 2 * 32 * PITCHB;
+  unsigned char* buf0 = smem_raw + (size_t)warp * NST * 32 * PITCHB;
   const int nM = a.nM, nT = a.nT, K = a.K;
   const int i0 = (blockIdx.x * EWARP + warp) * 32;
   if (i0 >= nM) return;
@@ -265,18 +269,20 @@ __global__ void __launch_bounds__(EBLK) beff_v2_kernel(const EArgs<T> a, const i
   const int ntiles = (nT + TB - 1) / TB;
   auto tile_t0 = [&](int q) { return (BWD ? ntiles - 1 - q : q) * TB; };     // q-th tile in processing order
   auto tile_len = [&](int q) { return min(TB, nT - tile_t0(q)); };
-  tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(0), tile_len(0) * 3 * (int)sizeof(T), buf0, lane);
-  cp_async_commit();
+  // ring of NST tiles: NST - 1 loads in flight while one tile is consumed; every iteration commits exactly one group (an
+  // empty one past the end), so "all but the newest NST - 1 groups" is always "tile q has landed"
+#pragma unroll
+  for (int p = 0; p < NST - 1; ++p) {
+    if (p < ntiles) tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(p), tile_len(p) * 3 * (int)sizeof(T), buf0 + p * 32 * PITCHB, lane);
+    cp_async_commit();
+  }
   for (int q = 0; q < ntiles; ++q) {
-    unsigned char* cur = buf0 + (q & 1) * 32 * PITCHB;
-    if (q + 1 < ntiles) {
-      tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(q + 1), tile_len(q + 1) * 3 * (int)sizeof(T),
-                         buf0 + ((q + 1) & 1) * 32 * PITCHB, lane);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    unsigned char* cur = buf0 + (q % NST) * 32 * PITCHB;
+    if (q + NST - 1 < ntiles)
+      tile_load_async<T>(Bn, a.B_sm, i0, nM, tile_t0(q + NST - 1), tile_len(q + NST - 1) * 3 * (int)sizeof(T),
+                         buf0 + ((q + NST - 1) % NST) * 32 * PITCHB, lane);
+    cp_async_commit();
+    cp_async_wait<NST - 1>();
     __syncwarp();
     T* row = reinterpret_cast<T*>(cur) + lane * PITCH;
     const int t0 = tile_t0(q), len = tile_len(q);
@@ -407,7 +413,7 @@ int launch_e(bool bwd, const mrphy_beff_args* a, cudaStream_t st) {
   const EArgs<T> e = make_eargs<T>(a);
   dim3 grid((a->nM + EBLK - 1) / EBLK, a->N);
   if (rows_aligned16<T>(a) && !getenv("MRPHY_B200_BEFF_V1")) {   // cp.async double-buffered tiles
-    constexpr size_t smem2 = (size_t)EWARP * 2 * 32 * PITCHB;
+    constexpr size_t smem2 = (size_t)EWARP * NST * 32 * PITCHB;
     const int gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0, gb = (a->flags & MRPHY_NEED_GBEFF) ? 1 : 0;
     if (bwd) {
       auto kern = beff_v2_kernel<T, POL, RELAX, true>;
