@@ -1005,6 +1005,35 @@ def test_large_angle_steps_fp32(dev):
         assert mx(Mo64, ref['Mo']) < 1e-10
 
 
+def test_mixed_small_and_large_angle_tiles(dev):
+    """Spins sorted by radius and two batch entries with gradients 30x apart: spin tiles whose steps all stay inside the
+    half-angle polynomials' range, tiles that take the large-angle path on most steps, and tiles that mix both inside one
+    warp (phi from ~0 to ~25 rad per step), all in one launch; everything must track the fp64 oracle like the reference
+    algorithm run in fp32."""
+    from oracle import bloch_oracle as orc
+    p = _random_problem(77, 2, 3001, 130, 1, has_b1=True, relax=True, dtype=f32)
+    order = torch.argsort(p['loc'].norm(dim=-1), dim=1)
+    for k in ('loc', 'df', 'M0', 'gam', 'T1', 'T2', 'w', 'b1'):
+        idx = order.reshape(order.shape + (1,) * (p[k].dim() - 2)).expand_as(p[k])
+        p[k] = torch.gather(p[k], 1, idx)
+    p['loc'] = p['loc'] * torch.linspace(0.02, 1.0, 3001, dtype=f64)[None, :, None]
+    p['gr'] = p['gr'] * tensor([3.0, 0.1], dtype=f64)[:, None, None]
+    p['df'][1] *= 0.05
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'],
+                                 T2=p['T2'], gamma=p['gam'], dt=p['dt'])
+    p32 = {k: v.to(f32) for k, v in p.items()}
+    ref32 = orc.applypulse_fwd_bwd(p32['M0'], p32['rf'], p32['gr'], p32['loc'], p32['w'], df=p32['df'], b1=p32['b1'],
+                                   T1=p32['T1'], T2=p32['T2'], gamma=p32['gam'], dt=p32['dt'], dtype=f32)
+    g = {('in_' + k): v.numpy() for k, v in p.items()}
+    for K in (16, 64):
+        Mo, gM0, grf, ggr = run_fused(g, dev, f32, p['w'].numpy(), ckpt=K)
+        dM, floor = mx(Mo, ref['Mo']), mx(ref32['Mo'], ref['Mo'])
+        print(f'[mixed angle tiles K={K}] max|dM|={dM:.2e} (reference fp32 {floor:.2e}) grf {rel(grf, ref["grf"]):.2e} '
+              f'ggr {rel(ggr, ref["ggr"]):.2e} gM0 {rel(gM0, ref["gM0"]):.2e}')
+        assert dM < _fp32_bound(ref32['Mo'], ref['Mo'])
+        assert rel(grf, ref['grf']) < RTOL_G32 and rel(ggr, ref['ggr']) < RTOL_G32 and rel(gM0, ref['gM0']) < RTOL_G32
+
+
 # ---- SURVEY 8f-2 / f-4: re-parametrisation chain and mask plumbing as single launches -------------------------
 @pytest.mark.parametrize('tag', ['sc', 'mc'])
 @pytest.mark.parametrize('dtype', [f64, f32])
