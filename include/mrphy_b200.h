@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MRPHY_ABI_VERSION 4
+#define MRPHY_ABI_VERSION 5
 
 enum mrphy_dtype { MRPHY_F32 = 0, MRPHY_F64 = 1 };
 
@@ -229,6 +229,17 @@ typedef struct mrphy_reparam_args {
   void* grho; void* gtheta; void* gts;  /* adjoint out, like rho, theta, ts                                       */
 } mrphy_reparam_args;
 int mrphy_design_waveform(const mrphy_reparam_args* a, void* cuda_stream);
+
+/* mrphy_blochsim_fused_bwd with the adjoint of the re-parametrisation fused into its gradient epilogue: what
+ * autograd does upstream in two stages -- BlochSim.backward (sims.py:187-269) -> dL/drf, dL/dgr, then the backward of
+ * utils.t-rho-theta2rf / l-rho-theta2rf / ts2s / s2g (utils.py:114-131, 239-256, 293-330) -> dL/drho, dL/dtheta, dL/dts.
+ * `d` describes the chain that produced a->rf and/or a->gr: adjoint != 0, dtype / N / nT as in `a`, nC = trailing coil
+ * dimension of rf; rf_kind 0..2 and gr_kind 0..2 as in mrphy_design_waveform (0: that waveform is not re-parametrised);
+ * d->grf / d->ggr are ignored -- the tail reads a->grf / a->ggr, which are written as usual.  Same launches as
+ * mrphy_blochsim_fused_bwd: the last CTA of the epilogue to finish for a batch entry evaluates that entry's adjoint and
+ * writes d->grho, d->gtheta, d->gts.  a->partials as sized by mrphy_fused_partial_elems().                          */
+int mrphy_blochsim_fused_bwd_design(const mrphy_fused_args* a, int wave_is_packed, const mrphy_reparam_args* d,
+                                    void* cuda_stream);
 
 /* Amplitude limits of the design loop, replacing utils.rfclamp (utils.py:217-236) and utils.sclamp
  * (utils.py:278-293) and their autograd, one launch each way:

@@ -133,6 +133,7 @@ template <typename T> struct KArgs {
   T* partials;
   int* sched;          // SM-aware tile ownership of the backward (null: CTA b owns tiles b, b+P, ...), see SCHED_* below
   int n_sm, c_per_sm;
+  int* done;           // finished-CTA counters of grad_finalize_design_kernel, one per batch entry (null: no design tail); zeroed here
 };
 
 // Scheduling workspace of the backward kernel (ints, zeroed before every launch; lives behind the partial sums).
@@ -501,6 +502,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
     mbar_init(&full[1], 1);
     fence_barrier_init();
   }
+  if (a.done && blockIdx.x == 0 && tid == 0) a.done[n] = 0;   // for the epilogue that follows in stream order
   // which virtual id does this CTA serve first (see SCHED_*)
   int vid = blockIdx.x;
   if (a.sched && tid == 0) {
@@ -893,7 +895,8 @@ extern "C" size_t mrphy_fused_wave_elems(const mrphy_fused_args* a) {
 extern "C" size_t mrphy_fused_partial_elems(const mrphy_fused_args* a) {
   Plan p;
   if (make_plan(a, &p, true) != MRPHY_OK) return 0;
-  return (size_t)a->N * p.Pmax * p.W * (size_t)a->nT + (size_t)(SCHED_CLAIM + p.Pmax);   // + the scheduling ints
+  // + the scheduling ints + one finished-CTA counter per batch entry (design tail of the gradient epilogue)
+  return (size_t)a->N * p.Pmax * p.W * (size_t)a->nT + (size_t)(SCHED_CLAIM + p.Pmax) + (size_t)a->N;
 }
 
 namespace {
@@ -924,7 +927,7 @@ KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
   k.Mo = (T*)a->Mo; k.ckpt = (T*)a->ckpt; k.wave = (const T*)a->wave;
   k.gMo = (const T*)a->gMo; k.gMo_sn = a->gMo_sn; k.gMo_sm = a->gMo_sm;
   k.gMi = (T*)a->gMi; k.partials = (T*)a->partials;
-  k.sched = nullptr; k.n_sm = 0; k.c_per_sm = 0;
+  k.sched = nullptr; k.n_sm = 0; k.c_per_sm = 0; k.done = nullptr;
   return k;
 }
 
@@ -1029,8 +1032,9 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
 }
 
 template <typename T>
-int dispatch(bool bwd, const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
-  const KArgs<T> k = make_kargs<T>(a, p);
+int dispatch(bool bwd, const mrphy_fused_args* a, const Plan& p, cudaStream_t st, int* done = nullptr) {
+  KArgs<T> k = make_kargs<T>(a, p);
+  k.done = done;
   const bool relax = a->T1.ptr != nullptr;
   const bool precise = (a->flags & MRPHY_TRIG_PRECISE) != 0 && sizeof(T) == 4 && !(bwd && (a->flags & MRPHY_TRIG_FAST_BWD));
   const int need_gmi = (a->flags & MRPHY_NEED_GMI) ? 1 : 0;
@@ -1052,18 +1056,44 @@ int run_fwd(const mrphy_fused_args* a, cudaStream_t st) {
   return dispatch<T>(false, a, p, st);
 }
 
+// the re-parametrisation the design tail can take: adjoint of an rf half and/or a gradient half that ends in a gradient
+int check_design(const mrphy_fused_args* a, const mrphy_reparam_args* d) {
+  if (d->dtype != a->dtype || d->N != a->N || d->nT != a->nT || !d->adjoint)
+    return fail(MRPHY_ERR_ARG, "design: dtype, N, nT must match the simulation and adjoint must be set%s");
+  if (d->rf_kind < 0 || d->rf_kind > 2 || d->gr_kind < 0 || d->gr_kind > 2 || (d->rf_kind == 0 && d->gr_kind == 0))
+    return fail(MRPHY_ERR_ARG, "design: rf_kind 0..2, gr_kind 0..2 (ts -> s is not a gradient), not both 0%s");
+  if (d->rf_kind) {
+    if (a->flags & MRPHY_SKIP_GRF) return fail(MRPHY_ERR_ARG, "design: the rf half needs dL/drf (MRPHY_SKIP_GRF is set)%s");
+    if (d->nC != ((a->flags & MRPHY_RF_COIL_DIM) ? a->nC : 1)) return fail(MRPHY_ERR_ARG, "design: nC differs from rf's coil dimension%s");
+    if (!d->rho || !d->theta || !d->rfmax || !d->grho || !d->gtheta) return fail(MRPHY_ERR_ARG, "design: rho, theta, rfmax, grho, gtheta are required%s");
+  }
+  if (d->gr_kind) {
+    if (a->flags & MRPHY_SKIP_GGR) return fail(MRPHY_ERR_ARG, "design: the gradient half needs dL/dgr (MRPHY_SKIP_GGR is set)%s");
+    if (!d->ts || !d->gts || (d->gr_kind == 1 && !d->smax) || !d->dt.ptr) return fail(MRPHY_ERR_ARG, "design: ts, gts, dt (and smax for ts -> g) are required%s");
+  }
+  return MRPHY_OK;
+}
+
 template <typename T>
-int run_bwd(const mrphy_fused_args* a, int wave_is_packed, cudaStream_t st) {
+int run_bwd(const mrphy_fused_args* a, int wave_is_packed, const mrphy_reparam_args* d, cudaStream_t st) {
   Plan p;
   int rc = make_plan(a, &p, true);
   if (rc) return rc;
   if ((rc = check_common<T>(a, true))) return rc;
+  if (d && (rc = check_design(a, d))) return rc;
   if (!wave_is_packed && (rc = launch_pack<T>(a, p, st))) return rc;
-  if ((rc = dispatch<T>(true, a, p, st))) return rc;
+  // finished-CTA counters of the design tail: behind the scheduling ints, zeroed by the backward kernel itself
+  int* const done = d ? reinterpret_cast<int*>((T*)a->partials + (size_t)a->N * p.Pmax * p.W * (size_t)a->nT) + SCHED_CLAIM + p.Pmax : nullptr;
+  if ((rc = dispatch<T>(true, a, p, st, done))) return rc;
   dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 32);
-  grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT,
-                                                  (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0, p.sum_coils, (T)-1, (T*)a->grf,
-                                                  (T*)a->ggr, (p.rows & 1) ? 0 : 2 * p.NC, (p.rows & 2) ? p.W : 2 * p.NC);
+  const int coil_dim = (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0;
+  const int w_lo = (p.rows & 1) ? 0 : 2 * p.NC, w_hi = (p.rows & 2) ? p.W : 2 * p.NC;
+  if (d)
+    grad_finalize_design_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT, coil_dim,
+                                                           p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi, *d, done);
+  else
+    grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT, coil_dim,
+                                                    p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;
@@ -1084,5 +1114,14 @@ extern "C" int mrphy_blochsim_fused_bwd(const mrphy_fused_args* a, int wave_is_p
   g_err[0] = 0;
   if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  return a->dtype == MRPHY_F64 ? run_bwd<double>(a, wave_is_packed, st) : run_bwd<float>(a, wave_is_packed, st);
+  return a->dtype == MRPHY_F64 ? run_bwd<double>(a, wave_is_packed, nullptr, st) : run_bwd<float>(a, wave_is_packed, nullptr, st);
+}
+
+extern "C" int mrphy_blochsim_fused_bwd_design(const mrphy_fused_args* a, int wave_is_packed, const mrphy_reparam_args* d,
+                                               void* cuda_stream) {
+  g_launches = 0;
+  g_err[0] = 0;
+  if (!a || !d) return fail(MRPHY_ERR_ARG, "null args%s");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  return a->dtype == MRPHY_F64 ? run_bwd<double>(a, wave_is_packed, d, st) : run_bwd<float>(a, wave_is_packed, d, st);
 }

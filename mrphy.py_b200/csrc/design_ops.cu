@@ -17,115 +17,24 @@
 
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
+#include "design_math.cuh"
 
 namespace mrphy {
 
 constexpr int RP_THREADS = 256;
-constexpr double TWO_OVER_PI = 0.63661977236758134307553505349006;
-
-// inclusive scan of one value per thread across the CTA (256 threads); returns the CTA total through `total`
-__device__ __forceinline__ double block_scan_incl(double v, double* warp_tot, double& total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double u = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += u;
-  }
-  if (lane == 31) warp_tot[w] = v;
-  __syncthreads();
-  double pre = 0.0, tot = 0.0;
-#pragma unroll
-  for (int q = 0; q < RP_THREADS / 32; ++q) {
-    const double x = warp_tot[q];
-    if (q < w) pre += x;
-    tot += x;
-  }
-  __syncthreads();   // warp_tot is reused by the next chunk
-  total = tot;
-  return v + pre;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(RP_THREADS) design_waveform_kernel(const mrphy_reparam_args a, const int gr_rows) {
   __shared__ double warp_tot[RP_THREADS / 32];
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < gr_rows) {
-    // ---- gradient half: one CTA per (n, xyz) row, chunks of 256 samples, running carry between chunks
-    const int row = blockIdx.x, n = row / 3, x = row % 3, nT = a.nT;
-    const bool use_atan = a.gr_kind != 2, scan = a.gr_kind != 3;
-    const double smax = use_atan ? (double)((const T*)a.smax)[(int64_t)n * a.smax_sn + (int64_t)x * a.smax_sx] : 1.0;
-    const double dt = scan ? ld_param(a.dt, n, 0) : 1.0;
-    const T* in = (const T*)a.ts + (int64_t)row * nT;
-    if (!a.adjoint) {
-      T* out = (T*)a.gr + (int64_t)row * nT;
-      double carry = 0.0;
-      for (int base = 0; base < nT; base += RP_THREADS) {
-        const int t = base + tid;
-        double s = 0.0;
-        if (t < nT) s = use_atan ? atan((double)in[t]) * TWO_OVER_PI * smax : (double)in[t];
-        if (!scan) {
-          if (t < nT) out[t] = (T)s;
-          continue;
-        }
-        double tot;
-        const double inc = block_scan_incl(s, warp_tot, tot);
-        if (t < nT) out[t] = (T)(dt * (carry + inc));
-        carry += tot;
-      }
-    } else {
-      // dL/ds[t] = dt * sum_{t' >= t} dL/dg[t']  (reversed running sum), then through atan
-      const T* gg = (const T*)a.ggr + (int64_t)row * nT;
-      T* out = (T*)a.gts + (int64_t)row * nT;
-      double carry = 0.0;
-      for (int base = 0; base < nT; base += RP_THREADS) {
-        const int t = nT - 1 - (base + tid);
-        double g = t >= 0 ? (double)gg[t] : 0.0;
-        if (scan) {
-          double tot;
-          const double inc = block_scan_incl(g, warp_tot, tot);
-          g = dt * (carry + inc);
-          carry += tot;
-        }
-        if (t >= 0) {
-          if (use_atan) {
-            const double v = (double)in[t];
-            g *= TWO_OVER_PI * smax / (1.0 + v * v);
-          }
-          out[t] = (T)g;
-        }
-      }
-    }
+  if ((int)blockIdx.x < gr_rows) {   // gradient half: one CTA per (n, xyz) row
+    const int row = blockIdx.x;
+    design_gr_row<T, RP_THREADS>(a, row, a.adjoint ? (const T*)a.ggr + (int64_t)row * a.nT : nullptr, warp_tot, tid);
     return;
   }
-  // ---- rf half: one thread per (n, t, c)
-  const int64_t per = (int64_t)a.nT * a.nC;
+  // rf half: one thread per (n, t, c)
   const int64_t e = (int64_t)(blockIdx.x - gr_rows) * RP_THREADS + tid;
-  if (e >= (int64_t)a.N * per) return;
-  const int n = (int)(e / per);
-  const int64_t r = e - (int64_t)n * per;
-  const int c = (int)(r % a.nC);
-  const double rho = (double)((const T*)a.rho)[e], th = (double)((const T*)a.theta)[e];
-  const double rfmax = (double)((const T*)a.rfmax)[(int64_t)n * a.rfmax_sn + (int64_t)c * a.rfmax_sc];
-  double A, dA;
-  if (a.rf_kind == 1) {
-    A = atan(rho) * TWO_OVER_PI;
-    dA = TWO_OVER_PI / (1.0 + rho * rho);
-  } else {
-    A = 1.0 / (1.0 + exp(-rho));
-    dA = A * (1.0 - A);
-  }
-  double sn, cs;
-  sincos(th, &sn, &cs);
-  const int64_t ox = (int64_t)n * 2 * per + r, oy = ox + per;
-  if (!a.adjoint) {
-    T* rf = (T*)a.rf;
-    rf[ox] = (T)(A * rfmax * cs);
-    rf[oy] = (T)(A * rfmax * sn);
-  } else {
-    const double gx = (double)((const T*)a.grf)[ox], gy = (double)((const T*)a.grf)[oy];
-    ((T*)a.grho)[e] = (T)(dA * rfmax * (cs * gx + sn * gy));
-    ((T*)a.gtheta)[e] = (T)(A * rfmax * (cs * gy - sn * gx));
-  }
+  if (e < (int64_t)a.N * a.nT * a.nC) design_rf_elem<T>(a, e, (const T*)a.grf);
 }
 
 // utils.rfclamp / utils.sclamp and their adjoints: one thread per (n, t, c) rf sample pair, or per slew sample

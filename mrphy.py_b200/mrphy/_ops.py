@@ -161,11 +161,9 @@ def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flag
             Mi.new_empty((N * chunks * WS * ((K + 3) // 4 * 4),)))
 
 
-def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
-                       df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
-                       gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
-    """-> (gMi (N,nM,3) or empty, flat): flat = [dL/drf like rf (absent with FLAG_SKIP_GRF) | dL/dgr (N,3,nT) (absent with
-    FLAG_SKIP_GGR) | GRAD_TAIL spare elements, zero]; `split_wave_grads` cuts the views."""
+def _fused_bwd_call(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags, design=None):
+    """The backward launch sequence; `design` = (rho, theta, rfmax, ts, smax, ddt, rf_kind, gr_kind) adds the adjoint of the
+    re-parametrisation to the gradient epilogue (mrphy_blochsim_fused_bwd_design).  -> (gMi, flat, grho, gtheta, gts)."""
     L = _cabi.lib()
     a = _cabi.FusedArgs()
     _fill_common(a, None, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
@@ -186,10 +184,49 @@ def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor
     a.gMo, a.gMo_sn, a.gMo_sm = gMo.data_ptr(), _bstride(gMo, 0), _bstride(gMo, 1)
     a.gMi, a.grf, a.ggr, a.partials = (gMi.data_ptr() if need_gmi else None), (grf.data_ptr() if want_rf else None), \
         (ggr.data_ptr() if want_gr else None), partials.data_ptr()
-    with torch.cuda.device(Mo.device):
-        _cabi.check(L.mrphy_blochsim_fused_bwd(a, 1, _stream()), 'blochsim_fused_bwd')
+    grho = gtheta = gts = flat[:0]
+    if design is None:
+        with torch.cuda.device(Mo.device):
+            _cabi.check(L.mrphy_blochsim_fused_bwd(a, 1, _stream()), 'blochsim_fused_bwd')
+    else:
+        rho, theta, rfmax, ts, smax, ddt, rf_kind, gr_kind = design
+        d, _ = _reparam_args(rho, theta, rfmax, ts, smax, ddt, rf_kind, gr_kind, True)
+        if rf_kind:
+            grho, gtheta = torch.empty(rho.shape, **kw), torch.empty(theta.shape, **kw)
+            d.grho, d.gtheta = grho.data_ptr(), gtheta.data_ptr()
+        if gr_kind:
+            gts = torch.empty(ts.shape, **kw)
+            d.gts = gts.data_ptr()
+        with torch.cuda.device(Mo.device):
+            _cabi.check(L.mrphy_blochsim_fused_bwd_design(a, 1, d, _stream()), 'blochsim_fused_bwd_design')
     _cabi.count_launches()
-    return gMi, flat
+    return gMi, flat, grho, gtheta, gts
+
+
+def _impl_blochsim_fused_bwd(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
+                       df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
+                       gamma: Tensor, dt: Tensor, K: int, flags: int) -> Tuple[Tensor, Tensor]:
+    """-> (gMi (N,nM,3) or empty, flat): flat = [dL/drf like rf (absent with FLAG_SKIP_GRF) | dL/dgr (N,3,nT) (absent with
+    FLAG_SKIP_GGR) | GRAD_TAIL spare elements, zero]; `split_wave_grads` cuts the views."""
+    return _fused_bwd_call(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)[:2]
+
+
+def _impl_blochsim_fused_bwd_design(gMo: Tensor, Mo: Tensor, ckpt: Tensor, wave: Tensor, rf: Tensor, gr: Tensor, loc: Tensor,
+                                    df: Optional[Tensor], b1: Optional[Tensor], T1: Optional[Tensor], T2: Optional[Tensor],
+                                    gamma: Tensor, dt: Tensor, K: int, flags: int, rho: Optional[Tensor],
+                                    theta: Optional[Tensor], rfmax: Optional[Tensor], ts: Optional[Tensor],
+                                    smax: Optional[Tensor], ddt: Optional[Tensor], rf_kind: int, gr_kind: int):
+    """As blochsim_fused_bwd, plus (dL/drho, dL/dtheta, dL/dts) of the re-parametrisation that produced rf / gr (empty for an
+    absent half), evaluated in the tail of the gradient epilogue: no launch of its own."""
+    return _fused_bwd_call(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags,
+                           (rho, theta, rfmax, ts, smax, ddt, rf_kind, gr_kind))
+
+
+def _fake_blochsim_fused_bwd_design(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags, rho, theta, rfmax,
+                                    ts, smax, ddt, rf_kind, gr_kind):
+    gMi, flat = _fake_blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
+    e = lambda like, on: Mo.new_empty(like.shape if on else (0,))
+    return gMi, flat, e(rho, rf_kind), e(theta, rf_kind), e(ts, gr_kind)
 
 
 def _fake_blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags):
@@ -674,7 +711,7 @@ def _mask_backward(ctx, g):
 # registration: raw torch.library definitions (schema + CUDA impl + fake), which cost ~20 us per call instead of
 # the ~130 us of the `torch.library.custom_op` convenience wrapper -- it matters for test-scale problems
 _LIB = torch.library.Library('mrphy_b200', 'DEF')
-_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'rfgr2beff_spin_grads': '(Tensor gB, Tensor rf, Tensor gr, bool want_loc, bool want_b1) -> (Tensor, Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor', 'clamp_waveform': '(Tensor x, Tensor lim, float eps, int kind) -> Tensor', 'clamp_waveform_bwd': '(Tensor g, Tensor x, Tensor lim, float eps, int kind) -> Tensor'}
+_SCHEMAS = {'blochsim_fused_fwd': '(Tensor Mi, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'blochsim_fused_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_fused_bwd_design': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor wave, Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? ddt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor, Tensor, Tensor)', 'blochsim_beff_fwd': '(Tensor Mi, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'blochsim_beff_bwd': '(Tensor gMo, Tensor Mo, Tensor ckpt, Tensor Beff, Tensor? T1, Tensor? T2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'rfgr2beff': '(Tensor rf, Tensor gr, Tensor loc, Tensor? df, Tensor? b1, Tensor gamma) -> Tensor', 'rfgr2beff_bwd': '(Tensor gB, Tensor rf, Tensor gr, Tensor loc, Tensor? b1) -> (Tensor, Tensor)', 'rfgr2beff_spin_grads': '(Tensor gB, Tensor rf, Tensor gr, bool want_loc, bool want_b1) -> (Tensor, Tensor, Tensor)', 'beff2ab': '(Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor, Tensor)', 'beff2ab_bwd': '(Tensor gA, Tensor gB, Tensor A, Tensor B, Tensor ckpt, Tensor beff, Tensor E1, Tensor E2, Tensor gamma, Tensor dt, int K, int flags) -> (Tensor, Tensor)', 'beff2uphi': '(Tensor beff, Tensor g) -> (Tensor, Tensor)', 'beff2uphi_bwd': '(Tensor? gU, Tensor? gPhi, Tensor beff, Tensor g) -> (Tensor, Tensor)', 'freeprec': '(Tensor Mi, Tensor dur, Tensor? T1, Tensor? T2, Tensor? df, bool adjoint) -> Tensor', 'design_waveform': '(Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor)', 'design_waveform_bwd': '(Tensor? grf, Tensor? ggr, Tensor? rho, Tensor? theta, Tensor? rfmax, Tensor? ts, Tensor? smax, Tensor? dt, int rf_kind, int gr_kind) -> (Tensor, Tensor, Tensor)', 'mask_copy': '(Tensor v, Tensor idx, Tensor inv, bool fill_zero) -> Tensor', 'clamp_waveform': '(Tensor x, Tensor lim, float eps, int kind) -> Tensor', 'clamp_waveform_bwd': '(Tensor g, Tensor x, Tensor lim, float eps, int kind) -> Tensor'}
 
 
 def _register(name, impl, fake):
@@ -686,6 +723,7 @@ def _register(name, impl, fake):
 
 blochsim_fused_fwd = _register('blochsim_fused_fwd', _impl_blochsim_fused_fwd, _fake_blochsim_fused_fwd)
 blochsim_fused_bwd = _register('blochsim_fused_bwd', _impl_blochsim_fused_bwd, _fake_blochsim_fused_bwd)
+blochsim_fused_bwd_design = _register('blochsim_fused_bwd_design', _impl_blochsim_fused_bwd_design, _fake_blochsim_fused_bwd_design)
 blochsim_beff_fwd = _register('blochsim_beff_fwd', _impl_blochsim_beff_fwd, _fake_blochsim_beff_fwd)
 blochsim_beff_bwd = _register('blochsim_beff_bwd', _impl_blochsim_beff_bwd, _fake_blochsim_beff_bwd)
 rfgr2beff_cuda = _register('rfgr2beff', _impl_rfgr2beff, _fake_rfgr2beff)
@@ -705,6 +743,80 @@ torch.library.register_autograd('mrphy_b200::blochsim_fused_fwd', _fused_backwar
 torch.library.register_autograd('mrphy_b200::design_waveform', _design_backward, setup_context=_design_setup, lib=_LIB)
 torch.library.register_autograd('mrphy_b200::mask_copy', _mask_backward, setup_context=_mask_setup, lib=_LIB)
 torch.library.register_autograd('mrphy_b200::clamp_waveform', _clamp_backward, setup_context=_clamp_setup, lib=_LIB)
+
+
+# ------------------------------------------------------------------------------------------------
+# re-parametrisation fused into the gradient epilogue.  utils.tρθ2rf / lρθ2rf / s2g / ts2g / tρθts2rfgr tag the
+# waveforms they return with the design variables they came from (`tag_design`); when such a waveform reaches
+# `fused_applypulse`, the simulation is recorded in autograd as a function of the DESIGN VARIABLES, and its backward evaluates
+# their gradients in the tail of the simulation's own gradient epilogue -- the backward launch of the chain disappears.
+class _DesignRecord:
+    __slots__ = ('tensors', 'kind', 'versions', 'out_version')
+
+    def __init__(self, tensors, kind, out):
+        self.tensors, self.kind = tensors, kind
+        self.versions = tuple(t._version for t in tensors if t is not None)
+        self.out_version = out._version
+
+    def valid_for(self, out: Tensor) -> bool:      # nothing was modified in place since the chain ran
+        return out._version == self.out_version and \
+            self.versions == tuple(t._version for t in self.tensors if t is not None)
+
+
+def tag_design(rf: Optional[Tensor], gr: Optional[Tensor], rho, theta, rfmax, ts, smax, dt, rf_kind: int, gr_kind: int):
+    """Remember on rf / gr (outputs of `design_waveform_cuda`) the inputs of the chain; gr only when it IS a gradient
+    (gr_kind 1: ts -> g, 2: s -> g)."""
+    if rf is not None and rf_kind:
+        rf._mrphy_design = _DesignRecord((rho, theta, rfmax), rf_kind, rf)
+    if gr is not None and gr_kind in (1, 2):
+        gr._mrphy_design = _DesignRecord((ts, smax, dt), gr_kind, gr)
+
+
+def _design_of(x: Tensor, used: Tensor) -> Optional[_DesignRecord]:
+    rec = getattr(x, '_mrphy_design', None)
+    if rec is None or used is not x or not x.requires_grad or x.retains_grad or not rec.valid_for(x):
+        return None
+    return rec
+
+
+class _FusedDesignApply(torch.autograd.Function):
+    """Mo(Mi, rf | (rho, theta), gr | ts): forward = the fused simulation on the waveforms the chain already produced;
+    backward = mrphy_blochsim_fused_bwd_design."""
+
+    @staticmethod
+    def forward(ctx, Mi, rf, gr, rho, theta, ts, loc, df, b1, T1, T2, gamma, dt, rfmax, smax, ddt, K, flags, rf_kind, gr_kind):
+        Mo, ckpt, wave = blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags)
+        opt = (df, b1, T1, T2, rho, theta, rfmax, ts, smax, ddt)
+        ctx.has = [x is not None for x in opt]
+        ctx.K, ctx.flags, ctx.kinds = K, flags, (rf_kind, gr_kind)
+        ctx.save_for_backward(Mo, ckpt, wave, rf, gr, loc, gamma, dt, *[x for x in opt if x is not None])
+        return Mo
+
+    @staticmethod
+    def backward(ctx, gMo):
+        Mo, ckpt, wave, rf, gr, loc, gamma, dt, *rest = ctx.saved_tensors
+        rest = list(rest)
+        df, b1, T1, T2, rho, theta, rfmax, ts, smax, ddt = (rest.pop(0) if h else None for h in ctx.has)
+        need = ctx.needs_input_grad          # Mi, rf, gr, rho, theta, ts
+        rk = ctx.kinds[0] if (need[3] or need[4]) else 0
+        gk = ctx.kinds[1] if need[5] else 0
+        if not (need[0] or need[1] or need[2] or rk or gk):
+            return (None,) * 20
+        if gMo.stride(-1) != 1 or gMo.dtype != Mo.dtype:
+            gMo = gMo.to(Mo.dtype).contiguous()
+        flags = ctx.flags | (_cabi.FLAG_NEED_GMI if need[0] else 0) | (0 if (need[1] or rk) else _cabi.FLAG_SKIP_GRF) | \
+            (0 if (need[2] or gk) else _cabi.FLAG_SKIP_GGR)
+        if rk or gk:
+            gMi, flat, grho, gtheta, gts = blochsim_fused_bwd_design(
+                gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags, rho if rk else None,
+                theta if rk else None, rfmax if rk else None, ts if gk else None, smax if gk else None, ddt if gk else None,
+                rk, gk)
+        else:
+            gMi, flat = blochsim_fused_bwd(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, ctx.K, flags)
+            grho = gtheta = gts = None
+        grf, ggr = split_wave_grads(flat, rf, flags)
+        return (gMi if need[0] else None, grf if need[1] else None, ggr if need[2] else None,
+                grho if (rk and need[3]) else None, gtheta if (rk and need[4]) else None, gts if gk else None) + (None,) * 14
 
 
 # ------------------------------------------------------------------------------------------------
@@ -854,6 +966,7 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
     assert rf.shape[0] == N and rf.shape[1] == 2 and gr.shape == (N, 3, rf.shape[2])
     cast = lambda x: None if x is None else x.to(device=dev, dtype=dtype)
     move = lambda x: None if x is None else (on_device(x, dev) if x.dtype in _F else on_device(x, dev, dtype))
+    rf_in, gr_in = rf, gr
     rf, gr = cast(rf), cast(gr)
     Mi = _inner_contig(cast(M_), 1)
     loc = _inner_contig(cast(loc_), 1)
@@ -870,5 +983,15 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
     df, T1, T2, gam, dtt = (move(x) for x in (Δf_, T1_, T2_, γ_, dt))
     K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2)
     fl = default_flags() if flags is None else flags
+    if torch.is_grad_enabled() and os.environ.get('MRPHY_B200_FUSE_DESIGN', '1') != '0':
+        # rf and/or gr straight out of the re-parametrisation chain: differentiate w.r.t. the design variables in the
+        # simulation's own gradient epilogue (see _FusedDesignApply)
+        r_rf, r_gr = _design_of(rf_in, rf), _design_of(gr_in, gr)
+        if r_rf is not None or r_gr is not None:
+            rho, theta, rfmax = r_rf.tensors if r_rf is not None else (None, None, None)
+            ts, smax, ddt = r_gr.tensors if r_gr is not None else (None, None, None)
+            return _FusedDesignApply.apply(Mi, rf.detach() if r_rf is not None else rf, gr.detach() if r_gr is not None else gr,
+                                           rho, theta, ts, loc, df, b1, T1, T2, gam, dtt, rfmax, smax, ddt, K, fl,
+                                           r_rf.kind if r_rf is not None else 0, r_gr.kind if r_gr is not None else 0)
     Mo, _, _ = blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gam, dtt, K, fl)
     return Mo

@@ -48,6 +48,17 @@ def _aux(x: Tensor, like: Tensor, rows: int, cols: int):
     return v
 
 
+def _design_call(hr, hg, rf_kind: int, gr_kind: int):
+    """One launch of the chain on prepared halves (either may be None) -> (rf, gr); the outputs remember their design
+    variables so that `applypulse` can fold the chain's adjoint into its own gradient epilogue (`_ops.tag_design`)."""
+    from mrphy import _ops
+    rho, theta, rfmax = hr if hr is not None else (None, None, None)
+    ts, smax, dt = hg if hg is not None else (None, None, None)
+    rf, gr = _ops.design_waveform_cuda(rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind)
+    _ops.tag_design(rf if rf_kind else None, gr if gr_kind else None, rho, theta, rfmax, ts, smax, dt, rf_kind, gr_kind)
+    return rf, gr
+
+
 def _rf_half(ρ: Tensor, θ: Tensor, rfmax: Tensor):
     """(ρ, θ, rfmax2) ready for the kernel, or None -> torch expression."""
     if os.environ.get('MRPHY_B200_REPARAM') == 'torch':      # measurement switch (profiles/design_step.py)
@@ -137,8 +148,7 @@ def s2g(s: Tensor, dt: Tensor = dt0) -> Tensor:
     r"""Slew rate `(N,xyz,nT)` -> gradient (running sum * dt)."""
     h = _gr_half(s, None, dt)
     if h is not None:
-        from mrphy import _ops
-        return _ops.design_waveform_cuda(None, None, None, h[0], None, h[2], 0, 2)[1]
+        return _design_call(None, h, 0, 2)[1]
     return _tail(dt, s.ndim) * torch.cumsum(s, dim=2)
 
 
@@ -150,8 +160,7 @@ def lρθ2rf(lρ: Tensor, θ: Tensor, rfmax: Tensor) -> Tensor:
     r"""logit(ρ/rfmax), θ `(N,1,nT,(nCoils))` -> rf `(N,xy,nT,(nCoils))`."""
     h = _rf_half(lρ, θ, rfmax)
     if h is not None:
-        from mrphy import _ops
-        return _ops.design_waveform_cuda(h[0], h[1], h[2], None, None, None, 2, 0)[0]
+        return _design_call(h, None, 2, 0)[0]
     return lρ.sigmoid() * _per_pulse(rfmax) * _unit(θ)
 
 
@@ -159,8 +168,7 @@ def tρθ2rf(tρ: Tensor, θ: Tensor, rfmax: Tensor) -> Tensor:
     r"""tan(ρ/rfmax·π/2), θ `(N,1,nT,(nCoils))` -> rf `(N,xy,nT,(nCoils))`."""
     h = _rf_half(tρ, θ, rfmax)
     if h is not None:
-        from mrphy import _ops
-        return _ops.design_waveform_cuda(h[0], h[1], h[2], None, None, None, 1, 0)[0]
+        return _design_call(h, None, 1, 0)[0]
     return tρ.atan() / π * 2 * _per_pulse(rfmax) * _unit(θ)
 
 
@@ -202,8 +210,7 @@ def ts2s(ts: Tensor, smax: Tensor) -> Tensor:
     r"""tan(s/smax·π/2) -> slew `(N,xyz,nT)`."""
     h = _gr_half(ts, smax, None)
     if h is not None:
-        from mrphy import _ops
-        return _ops.design_waveform_cuda(None, None, None, h[0], h[1], None, 0, 3)[1]
+        return _design_call(None, h, 0, 3)[1]
     return ts.atan() / π * 2 * smax[..., None]
 
 
@@ -211,8 +218,7 @@ def ts2g(ts: Tensor, smax: Tensor, dt: Tensor = dt0) -> Tensor:
     r"""``s2g(ts2s(ts, smax), dt)`` in one launch (not in the reference; the chain every slew-constrained design runs)."""
     h = _gr_half(ts, smax, dt)
     if h is not None:
-        from mrphy import _ops
-        return _ops.design_waveform_cuda(None, None, None, h[0], h[1], h[2], 0, 1)[1]
+        return _design_call(None, h, 0, 1)[1]
     return s2g(ts2s(ts, smax), dt)
 
 
@@ -223,8 +229,7 @@ def tρθts2rfgr(tρ: Tensor, θ: Tensor, ts: Tensor, rfmax: Tensor, smax: Tenso
     hr, hg = _rf_half(tρ, θ, rfmax), _gr_half(ts, smax, dt)
     if hr is not None and hg is not None and hr[0].dtype == hg[0].dtype and hr[0].shape[0] == hg[0].shape[0] \
             and hr[0].shape[2] == hg[0].shape[2] and hr[0].device == hg[0].device:
-        from mrphy import _ops
-        return tuple(_ops.design_waveform_cuda(hr[0], hr[1], hr[2], hg[0], hg[1], hg[2], 2 if logit else 1, 1))
+        return _design_call(hr, hg, 2 if logit else 1, 1)
     return (lρθ2rf if logit else tρθ2rf)(tρ, θ, rfmax), ts2g(ts, smax, dt)
 
 

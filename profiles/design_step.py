@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """One iteration of a slew- and amplitude-constrained pulse design: unconstrained variables (tρ, θ, ts) ->
 rf = tρθ2rf, gr = s2g(ts2s) -> cube.applypulse -> loss -> backward to the variables.  Compares the re-parametrisation as
-the reference's torch expressions (MRPHY_B200_REPARAM=torch), as one kernel per utils function, and as the single fused
-launch `utils.tρθts2rfgr`; reports ms per iteration (CUDA events, eager launches) and kernels launched per iteration."""
+the reference's torch expressions (MRPHY_B200_REPARAM=torch), as one kernel per utils function, as the single fused
+launch `utils.tρθts2rfgr`, and with the chain's adjoint folded into the simulation's gradient epilogue ("+tail", the default;
+the other rows run with MRPHY_B200_FUSE_DESIGN=0); reports ms per iteration (CUDA events, eager launches) and kernels launched
+per iteration."""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -47,15 +49,16 @@ for n, nT in ((16, 256), (32, 512), (64, 1000)):
     g = torch.Generator(device='cuda').manual_seed(1)
     v = [torch.randn((1, c, nT), generator=g, **kw).mul_(0.3).requires_grad_(True) for c in (1, 1, 3)]
     ref = None
-    for mode in ('torch', 'per-function', 'fused', 'fused+graph'):
+    for mode in ('torch', 'per-function', 'fused', 'fused+tail', 'fused+tail+graph'):
         os.environ['MRPHY_B200_REPARAM'] = 'torch' if mode == 'torch' else 'cuda'
+        os.environ['MRPHY_B200_FUSE_DESIGN'] = '1' if 'tail' in mode else '0'
         for _ in range(5):
             iteration(mode, sp, d, v, tgt)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K = 50 if n < 64 else 20
         run = lambda: iteration(mode, sp, d, v, tgt)
-        if mode == 'fused+graph':           # the whole iteration as one CUDA graph (it is free of host synchronisation)
+        if mode.endswith('+graph'):           # the whole iteration as one CUDA graph (it is free of host synchronisation)
             from mrphy import graphs
             loss = None
             cap = graphs.capture(run, params=v)
@@ -72,5 +75,5 @@ for n, nT in ((16, 256), (32, 512), (64, 1000)):
             nk = count_kernels(run)
         except Exception as ex:   # profiler unavailable: report time only
             nk = f'n/a ({type(ex).__name__})'
-        print(f'{n}^3 x {nT}: {mode:13s} {ms:7.3f} ms/iteration  kernels/iteration {nk}  loss {float(loss):.6e}  '
+        print(f'{n}^3 x {nT}: {mode:17s} {ms:7.3f} ms/iteration  kernels/iteration {nk}  loss {float(loss):.6e}  '
               f'max rel grad diff vs torch chain {float((grads - ref).abs().max() / ref.abs().max()):.2e}', flush=True)

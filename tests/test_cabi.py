@@ -56,8 +56,9 @@ def test_sizing_entry_points(cabi):
     a.b1 = 1  # non-null: per-coil path
     assert L.mrphy_fused_ckpt_elems(a) == 2 * 15 * 3 * 1000          # ceil(1000/64)-1 = 15 checkpoints
     assert L.mrphy_fused_wave_elems(a) == 2 * 16 * 5 * 64
-    # ceil(1000/128) = 8 CTAs per batch entry, plus the backward's scheduling ints (264 + 8) behind the partial sums
-    assert L.mrphy_fused_partial_elems(a) == 2 * 8 * 5 * 1000 + 264 + 8
+    # ceil(1000/128) = 8 CTAs per batch entry, plus the backward's scheduling ints (264 + 8) and the epilogue's finished-CTA
+    # counters (one per batch entry) behind the partial sums
+    assert L.mrphy_fused_partial_elems(a) == 2 * 8 * 5 * 1000 + 264 + 8 + 2
     a.K = 0
     assert L.mrphy_fused_ckpt_elems(a) == 0 and b'K must be' in L.mrphy_last_error()
 

@@ -789,6 +789,133 @@ def test_multiscale_design_loop_through_public_api(dev):
     assert h2[-1] < h2[0]
 
 
+def _design_problem(dev, dtype, nC, seed=3, N=2, nM=301, nT=333):
+    """Design variables (tρ, θ, ts), limits, and a spin set; sizes ragged on purpose (nT not a multiple of 32)."""
+    gen = torch.Generator().manual_seed(seed)
+    U = lambda *s: torch.rand(s, generator=gen, dtype=f64) * 2 - 1
+    shp = (N, 1, nT, nC) if nC > 1 else (N, 1, nT)
+    d = dict(rho=U(*shp) * 2, theta=U(*shp) * 3, ts=U(N, 3, nT) * 1.5,
+             rfmax=(0.15 + 0.05 * U(N, nC).abs()) if nC > 1 else (0.15 + 0.05 * U(N).abs()),
+             smax=1.2e4 + 2e3 * U(N, 3).abs(), dt=tensor([4e-6], dtype=f64))
+    p = _random_problem(seed + 40, N, nM, nT, nC if nC > 1 else 1, has_b1=True, relax=True)
+    return {k: v.to(dtype).to(f64) for k, v in d.items()}, p
+
+
+def _design_step(dev, dtype, d, p, mode, fuse, extra_penalty=False, retain=False):
+    """loss = Σ w·Mo(applypulse(chain(tρ, θ, ts))) -> (Mo, dL/dtρ, dL/dθ, dL/dts, backward launches)."""
+    from mrphy import utils, _ops, _cabi
+    os.environ['MRPHY_B200_FUSE_DESIGN'] = '1' if fuse else '0'
+    try:
+        t = {k: T(v.numpy(), dev, dtype) for k, v in d.items()}
+        rho, theta, ts = (t[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
+        if mode == 'joint':
+            rf, gr = utils.tρθts2rfgr(rho, theta, ts, t['rfmax'], t['smax'], t['dt'])
+        elif mode == 'split':                    # two chains, logit amplitude, slew given directly
+            rf, gr = utils.lρθ2rf(rho, theta, t['rfmax']), utils.s2g(ts, t['dt'])
+        elif mode == 'rf_only':                  # gr is a plain leaf
+            rf, gr = utils.tρθ2rf(rho, theta, t['rfmax']), ts
+        else:                                    # 'gr_only': rf is a plain leaf
+            rf = torch.cat([rho, theta], dim=1).mul(0.05).detach().requires_grad_(True)
+            gr = utils.ts2g(ts, t['smax'], t['dt'])
+        if retain:
+            rf.retain_grad()
+        q = {k: (None if v is None else T(v.numpy(), dev, dtype)) for k, v in p.items()}
+        Mo = _ops.fused_applypulse(q['M0'], rf, gr, q['loc'], Δf_=q['df'], b1Map_=q['b1'], T1_=q['T1'], T2_=q['T2'],
+                                   γ_=T(p['gam'].numpy(), dev, f64), dt=T(p['dt'].numpy(), dev, f64))
+        loss = (Mo * q['w']).sum()
+        if extra_penalty:                        # a second consumer of rf: its gradient must add up at the leaves
+            loss = loss + 3.0 * (rf ** 2).sum()
+        n0 = _cabi.launch_counter
+        loss.backward()
+        launches = _cabi.launch_counter - n0
+        grads = (rho.grad, theta.grad, ts.grad)
+        leaf_rf = rf.grad if (retain or mode == 'gr_only') else None
+        return Mo.detach(), grads, launches, leaf_rf
+    finally:
+        os.environ.pop('MRPHY_B200_FUSE_DESIGN', None)
+
+
+@pytest.mark.parametrize('dtype', [f64, f32])
+@pytest.mark.parametrize('mode,nC', [('joint', 1), ('joint', 2), ('split', 1), ('split', 4), ('rf_only', 1), ('gr_only', 1)])
+def test_design_adjoint_fused_into_gradient_epilogue(dev, dtype, mode, nC):
+    """waveforms that come out of utils.tρθ2rf / lρθ2rf / s2g / ts2g / tρθts2rfgr carry their design variables,
+    and `applypulse`'s backward evaluates dL/dtρ, dL/dθ, dL/dts in the tail of its own gradient epilogue
+    (grad_finalize_design_kernel) -- one launch fewer, same numbers.  Checked against (a) the two-stage path (simulation
+    backward, then the chain's own adjoint kernel, itself pinned to the reference's autograd in
+    test_design_waveform_kernel_matches_reference) and (b) the fp64 oracle's dL/drf, dL/dgr pushed through the reference
+    chain's torch expressions on the CPU.  Tolerance: fp64 1e-9 relative, fp32 1e-4 relative (north_star's gradient bound);
+    fused vs two-stage 1e-12 / 1e-6 relative (the same double arithmetic on the same waveform gradients)."""
+    from oracle import bloch_oracle as orc
+    from mrphy import utils
+    d, p = _design_problem(dev, dtype, nC)
+    Mo_f, g_f, n_f, _ = _design_step(dev, dtype, d, p, mode, fuse=True)
+    Mo_u, g_u, n_u, _ = _design_step(dev, dtype, d, p, mode, fuse=False)
+    assert torch.equal(Mo_f, Mo_u)
+    assert n_f == n_u - (2 if mode == 'split' else 1), (n_f, n_u)       # the chain's backward launch(es) are gone
+    tol_same = 1e-12 if dtype == f64 else 1e-6
+    for a, b in zip(g_f, g_u):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert rel(a, b) < tol_same, (mode, rel(a, b))
+    # (b) oracle: chain on the CPU in fp64 torch expressions (the reference formulas), simulation gradients from the oracle
+    rho, theta, ts = (d[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
+    if mode == 'joint':
+        rf, gr = utils.tρθ2rf(rho, theta, d['rfmax']), utils.s2g(utils.ts2s(ts, d['smax']), d['dt'])
+    elif mode == 'split':
+        rf, gr = utils.lρθ2rf(rho, theta, d['rfmax']), utils.s2g(ts, d['dt'])
+    elif mode == 'rf_only':
+        rf, gr = utils.tρθ2rf(rho, theta, d['rfmax']), ts
+    else:
+        rf, gr = torch.cat([rho, theta], dim=1).mul(0.05), utils.ts2g(ts, d['smax'], d['dt'])
+    rf32, gr32 = rf.detach().to(dtype).to(f64), gr.detach().to(dtype).to(f64)     # what the kernels were handed
+    ref = orc.applypulse_fwd_bwd(p['M0'], rf32, gr32, p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'], T2=p['T2'],
+                                 gamma=p['gam'], dt=p['dt'])
+    torch.autograd.backward([rf, gr], [torch.as_tensor(ref['grf']).reshape(rf.shape), torch.as_tensor(ref['ggr'])])
+    tol = RTOL_G64 if dtype == f64 else RTOL_G32
+    want = (rho.grad, theta.grad, ts.grad)
+    if mode == 'gr_only':
+        want = (None, None, ts.grad)
+        g_f = (None, None, g_f[2])
+    for name, a, b in zip(('rho', 'theta', 'ts'), g_f, want):
+        if b is not None:
+            print(f'[design tail {mode} nC={nC} {dtype}] d{name}: rel {rel(a, b):.2e}')
+            assert rel(a, b) < tol, (name, rel(a, b))
+
+
+def test_design_tail_second_consumer_retain_grad_and_graph_replay(dev):
+    """(1) rf also feeds a penalty term: the simulation's share arrives through the fused tail, the penalty's through the
+    chain's own backward, and autograd adds them at the leaves.  (2) `rf.retain_grad()`: the caller wants dL/drf itself, so
+    the two-stage path runs and rf.grad is filled.  (3) a captured step replays with the finished-CTA counters reset by the
+    kernels themselves: three replays, bit-identical gradients."""
+    from mrphy import utils, _ops, graphs
+    d, p = _design_problem(dev, f32, 1, seed=9, N=1, nM=700, nT=130)
+    _, g_f, _, _ = _design_step(dev, f32, d, p, 'joint', fuse=True, extra_penalty=True)
+    _, g_u, _, _ = _design_step(dev, f32, d, p, 'joint', fuse=False, extra_penalty=True)
+    for a, b in zip(g_f, g_u):
+        assert rel(a, b) < 1e-6
+    _, g_r, n_r, rf_grad = _design_step(dev, f32, d, p, 'joint', fuse=True, retain=True)
+    _, g_0, n_0, _ = _design_step(dev, f32, d, p, 'joint', fuse=False)
+    assert rf_grad is not None and n_r == n_0 and all(torch.equal(a, b) for a, b in zip(g_r, g_0))
+    t = {k: T(v.numpy(), dev, f32) for k, v in d.items()}
+    rho, theta, ts = (t[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
+    q = {k: (None if v is None else T(v.numpy(), dev, f32)) for k, v in p.items()}
+    gam, dts = T(p['gam'].numpy(), dev, f64), T(p['dt'].numpy(), dev, f64)
+
+    def step():
+        rf, gr = utils.tρθts2rfgr(rho, theta, ts, t['rfmax'], t['smax'], t['dt'])
+        Mo = _ops.fused_applypulse(q['M0'], rf, gr, q['loc'], Δf_=q['df'], b1Map_=q['b1'], T1_=q['T1'], T2_=q['T2'], γ_=gam,
+                                   dt=dts)
+        (Mo * q['w']).sum().backward()
+
+    step()
+    want = [x.grad.clone() for x in (rho, theta, ts)]
+    captured = graphs.capture(step, params=(rho, theta, ts))
+    for _ in range(3):
+        captured.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(x.grad, w) for x, w in zip((rho, theta, ts), want))
+
+
 def test_step_is_cuda_graph_capturable(dev):
     """A whole design step (applypulse forward, loss, adjoint backward) records into a CUDA graph after warm-up: no
     host synchronisation, no allocation outside torch's allocator, every launch on the capturing stream.  Replays with
