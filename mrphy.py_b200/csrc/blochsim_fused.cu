@@ -25,8 +25,12 @@
 #include "../../include/mrphy_b200.h"
 #include "abi_common.cuh"
 #define MRPHY_VOTE_MASK 0xffffffffu   /* every loop of the fused kernels runs with all lanes of the warp (padding lanes compute too) */
+#ifndef MRPHY_TC_MIN_NC
+#define MRPHY_TC_MIN_NC 4   /* fp32, this many coils or more: transmit field on the tensor cores (fused_*_tc_kernel) */
+#endif
 #include "bloch_math.cuh"
 #include "ptx_helpers.cuh"
+#include "tc_helpers.cuh"
 #include "grad_finalize.cuh"
 
 namespace mrphy {
@@ -121,6 +125,7 @@ template <typename T, int NC, int BLKT> struct BwdSmem {
 
 template <typename T> struct KArgs {
   int N, nM, nT, K, TCP, nChunks, P;
+  int chunk_elems;     // elements of T per staged waveform chunk
   const T* Mi; int64_t Mi_sn, Mi_sm;
   const T* loc; int64_t loc_sn, loc_sm;
   const T* b1; int64_t b1_sn, b1_sm; int nC;
@@ -709,6 +714,273 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
 #endif
 }
 
+
+// ==========================================================================================
+// Multi-coil (pTx) path on the tensor cores, fp32, NC >= 4 coils.
+//
+// The transmit field  Bx + i By [spin][step] = sum_c g b1[spin][c] rf[c][step]  is the one contraction on this path: per
+// spin tile (128 spins = one CTA = the 128 TMEM lanes) and staged chunk (<= 64 steps) it is ONE product
+//     D[128 spins][2 steps] = A[128][2 NC] * B[2 steps][2 NC]^T        A[s] = (g Re b1_c, g Im b1_c)_c
+//                                                                       B[(j,x)] = (rx_c, -ry_c)_c   B[(j,y)] = (ry_c, rx_c)_c
+// issued by one thread as tcgen05.mma (kind::tf32), accumulated in TMEM, and read back by the thread that owns the spin
+// (thread t of warp w <-> TMEM lane 32 w + t) with tcgen05.ld -- 4 NC FMAs and 2 NC shared-memory operands per spin and
+// step become one 64-bit TMEM read.  fp32 accuracy: every operand is split into two TF32-representable parts
+// (hi = rn_tf32(x), mid = rn_tf32(x - hi)); the products mid*hi + hi*mid + hi*hi are exact in the tensor core and leave
+// 2^-22 relative -- measured as accurate as the fp32 FMA chain it replaces (profiles/ubench/tc_field.cu: 7.5e-8 vs 7.4e-8).
+// The pack kernel writes B (both parts) in the canonical K-major operand layout (tc_helpers.cuh), so a chunk still arrives
+// with one TMA bulk copy; A is written once per tile by the threads.
+constexpr int TC_TCMAX = 32;   // steps per staged chunk (= checkpoint interval) of the tensor-core kernels
+template <int NC> struct TcLayout {
+  static constexpr int KC = NC / 2;       // 16-byte K-chunks per operand row (K = 2 NC values)
+  static constexpr int KSTEPS = NC / 4;   // tcgen05.mma instructions along K (8 values each)
+  static constexpr int PER_STEP = 16 * KC + 3;                 // floats per step of a staged chunk: 2 parts x 2 rows x 2 NC + gr
+  static constexpr int CHUNK_MAX = TC_TCMAX * PER_STEP;        // floats
+  static constexpr int A_FLOATS = 2 * KC * 128 * 4;
+  static constexpr int BUF_COLS = 2 * TC_TCMAX;                // TMEM columns of one chunk's field: (Bx, By) per step
+  static constexpr int TMEM_COLS = 2 * BUF_COLS;               // double-buffered: 128
+};
+
+// pack for the tensor-core path: one thread per (n, chunk, step j < TCP, coil q < NC)
+template <int NC>
+__global__ void pack_waveform_tc_kernel(const float* __restrict__ rf, int64_t rf_sn, int64_t rf_sx, int64_t rf_st, int64_t rf_sc,
+                                        const float* __restrict__ gr, int64_t gr_sn, int64_t gr_sx, int64_t gr_st, int nC,
+                                        int nT, int K, int TCP, int nChunks, int64_t total, float* __restrict__ wave) {
+  using L = TcLayout<NC>;
+  const int rows = 2 * TCP;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e % NC);
+    const int j = (int)((e / NC) % TCP);
+    const int c = (int)((e / ((int64_t)NC * TCP)) % nChunks);
+    const int n = (int)(e / ((int64_t)NC * TCP * nChunks));
+    const int t = c * K + j;
+    const bool live = j < K && t < nT;
+    float rx = 0.f, ry = 0.f;
+    if (live && q < nC) {
+      const float* p = rf + n * rf_sn + t * rf_st + q * rf_sc;
+      rx = p[0];
+      ry = p[rf_sx];
+    }
+    float* chunk = wave + ((size_t)n * nChunks + c) * (size_t)(TCP * L::PER_STEP);
+    const float xh = tc::tf32_rn(rx), xm = tc::tf32_rn(rx - xh), yh = tc::tf32_rn(ry), ym = tc::tf32_rn(ry - yh);
+    const int kc = q >> 1, pos = (q & 1) * 2;
+    float* b_hi = chunk + ((size_t)(0 * L::KC + kc) * rows) * 4 + pos;
+    float* b_mid = chunk + ((size_t)(1 * L::KC + kc) * rows) * 4 + pos;
+    *reinterpret_cast<float2*>(b_hi + (size_t)(2 * j) * 4) = make_float2(xh, -yh);       // row (j, x)
+    *reinterpret_cast<float2*>(b_hi + (size_t)(2 * j + 1) * 4) = make_float2(yh, xh);    // row (j, y)
+    *reinterpret_cast<float2*>(b_mid + (size_t)(2 * j) * 4) = make_float2(xm, -ym);
+    *reinterpret_cast<float2*>(b_mid + (size_t)(2 * j + 1) * 4) = make_float2(ym, xm);
+    if (q < 3) chunk[(size_t)2 * L::KC * rows * 4 + (size_t)q * TCP + j] = live ? gr[n * gr_sn + q * gr_sx + t * gr_st] : 0.f;
+  }
+}
+
+// Per-spin prologue of the tensor-core kernel: the scalar constants (no b1: SpinConst<float, 1>) and this thread's row of A
+// = (g Re b1_c, g Im b1_c)_c in both TF32 parts.  The coils are walked two
+// at a time so that the 2 NC sensitivities never sit in registers together.  A CTA barrier must follow before the first
+// tcgen05.mma.
+template <int NC, bool RELAX>
+__device__ __forceinline__ void tc_load_spin(const KArgs<float>& a, int n, int i, float lx, float ly, float lz,
+                                             SpinConst<float, 1>& k, float* sa, int tid) {
+  using L = TcLayout<NC>;
+  const double gam = ld_param(a.gamma, n, i);
+  const double dt = ld_param(a.dt, n, 0);
+  const double df = a.df.ptr ? ld_param(a.df, n, i) : 0.0;
+  const double t1 = RELAX ? ld_param(a.T1, n, i) : 1.0;
+  const double t2 = RELAX ? ld_param(a.T2, n, i) : 1.0;
+  make_consts<float, 1>(k, gam, dt, RELAX, t1, t2, df, lx, ly, lz, nullptr, nullptr);
+  const double g = 6.283185307179586476925286766559 * gam * dt;
+  const float* bp = a.b1 + (int64_t)n * a.b1_sn + (int64_t)i * a.b1_sm;   // [re (nC) | im (nC)]
+#pragma unroll 2
+  for (int kc = 0; kc < L::KC; ++kc) {
+    float v[4], h[4], m[4];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 2 * kc + e;
+      v[2 * e] = c < a.nC ? (float)(g * (double)bp[c]) : 0.f;              // one rounding per constant, as make_consts
+      v[2 * e + 1] = c < a.nC ? (float)(g * (double)bp[a.nC + c]) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { h[e] = tc::tf32_rn(v[e]); m[e] = tc::tf32_rn(v[e] - h[e]); }
+    *reinterpret_cast<float4*>(sa + ((size_t)(0 * L::KC + kc) * 128 + tid) * 4) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(sa + ((size_t)(1 * L::KC + kc) * 128 + tid) * 4) = make_float4(m[0], m[1], m[2], m[3]);
+  }
+  fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's (async-proxy) reads
+}
+// the products of one staged chunk, by ONE thread: D = A_mid B_hi^T + A_hi B_mid^T + A_hi B_hi^T, then commit to `bar`
+template <int NC>
+__device__ __forceinline__ void tc_issue(const float* sa, const float* wb, int rows, uint32_t tmem, uint64_t* bar) {
+  using L = TcLayout<NC>;
+  const uint32_t idesc = tc::idesc_tf32(128, rows);
+  const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+  bool acc = false;
+  tc::fence_after_sync();
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int ks = 0; ks < L::KSTEPS; ++ks) {
+      tc::mma_tf32(tmem, tc::kmajor_desc(sa + ((size_t)(pa[q] * L::KC + 2 * ks) * 128) * 4, 128),
+                   tc::kmajor_desc(wb + ((size_t)(pb[q] * L::KC + 2 * ks) * rows) * 4, rows), idesc, acc);
+      acc = true;
+    }
+  }
+  tc::commit(bar);
+}
+
+template <int NC> struct TcSmem {   // dynamic shared memory of the tensor-core kernel, in bytes from a 128-byte aligned base
+  static constexpr int NST = NC <= 8 ? 3 : 2;                                                         // staged chunks
+  static constexpr size_t wbuf = 0;                                                                   // float[NST][CHUNK_MAX]
+  static constexpr size_t sa = ((size_t)NST * TcLayout<NC>::CHUNK_MAX * 4 + 127) / 128 * 128;         // float[2][KC][128][4]
+  static constexpr size_t scr = sa + (size_t)TcLayout<NC>::A_FLOATS * 4;                              // float[3 * 128]
+  static constexpr size_t bars = scr + 3 * 128 * 4;                                  // full[NST], mma[2], tmem slot: 64 B
+  static constexpr size_t fwd_bytes = bars + 64;
+};
+
+// Per chunk iteration `it` of a CTA (its tiles x chunks in order) thread 0 works ahead of the stepping threads, so that neither
+// the copy nor the tensor-core latency is exposed.  NST = 3 staged chunks (<= 8 coils):
+//   TC_CHUNK_BEGIN   TMA(it + 2) into stage (it + 2) % 3 (free: product and steps of it - 1 are done) and product(it + 1) into
+//                    the other TMEM buffer (its operands landed an iteration ago); a tile's FIRST chunk also issues its own
+//                    product here and everybody waits for it (A changes with the tile, so products never run ahead of a tile).
+// NST = 2 (16 coils: a stage is 17 KB): TMA(it + 1) at the beginning, and
+//   TC_PRODUCT_AHEAD product(it + 1) after 16 steps, when its operands have landed (a copy takes ~1-2 us, 8 steps ~1 us).
+// full[s] / mma_bar[b]: the k-th use has parity k & 1.
+#define TC_CHUNK_BEGIN(CHUNK_OF, FIRST_OF_TILE, HAS_NEXT_IN_TILE)                                                          \
+  if (tid == 0) {                                                                                                          \
+    if (it + (NST - 1) < total) {                                                                                          \
+      const uint32_t sq = (it + (NST - 1)) % NST;                                                                          \
+      mbar_arrive_expect_tx(&full[sq], chunk_bytes);                                                                       \
+      bulk_g2s(wbuf[sq], wave_n + (size_t)(CHUNK_OF(it + (NST - 1))) * a.chunk_elems, chunk_bytes, &full[sq]);              \
+    }                                                                                                                      \
+    if (FIRST_OF_TILE) {                                                                                                   \
+      mbar_wait(&full[it % NST], (it / NST) & 1);                                                                          \
+      tc_issue<NC>(sa, wbuf[it % NST], rows, tmem + (it & 1) * L::BUF_COLS, &mma_bar[it & 1]);                              \
+    }                                                                                                                      \
+    if (NST == 3 && (HAS_NEXT_IN_TILE)) {                                                                                  \
+      mbar_wait(&full[(it + 1) % NST], ((it + 1) / NST) & 1);                                                              \
+      tc_issue<NC>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) & 1) * L::BUF_COLS, &mma_bar[(it + 1) & 1]);            \
+    }                                                                                                                      \
+  }                                                                                                                        \
+  mbar_wait(&full[it % NST], (it / NST) & 1);                                                                              \
+  mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);                                                                              \
+  tc::fence_after_sync();
+#define TC_PRODUCT_AHEAD(HAS_NEXT_IN_TILE)                                                                                 \
+  if (NST == 2 && tid == 0 && (HAS_NEXT_IN_TILE)) {                                                                        \
+    mbar_wait(&full[(it + 1) % NST], ((it + 1) / NST) & 1);                                                                \
+    tc_issue<NC>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) & 1) * L::BUF_COLS, &mma_bar[(it + 1) & 1]);              \
+  }
+
+template <int POL, bool RELAX, int NC>
+__global__ void __launch_bounds__(128, (NC <= 8 ? 4 : 3)) fused_fwd_tc_kernel(const KArgs<float> a) {
+  using L = TcLayout<NC>;
+  typedef float T;
+  constexpr int BLKT = 128, NST = TcSmem<NC>::NST;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float(*wbuf)[L::CHUNK_MAX] = reinterpret_cast<float(*)[L::CHUNK_MAX]>(smem_raw + TcSmem<NC>::wbuf);
+  float* const sa = reinterpret_cast<float*>(smem_raw + TcSmem<NC>::sa);
+  float* const scr = reinterpret_cast<float*>(smem_raw + TcSmem<NC>::scr);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + TcSmem<NC>::bars);
+  uint64_t* const mma_bar = full + NST;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(full + NST + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, n = blockIdx.y;
+  const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM, rows = 2 * TCP;
+  const uint32_t chunk_bytes = (uint32_t)(a.chunk_elems * sizeof(float));
+  const float* wave_n = a.wave + (size_t)n * nChunks * a.chunk_elems;
+  const int tiles = (nM + BLKT - 1) / BLKT;
+  const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NST; ++q) mbar_init(&full[q], 1);
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tc::tmem_alloc<L::TMEM_COLS>(tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot, tlane = tmem + ((uint32_t)(warp * 32) << 16);
+#define FWD_CHUNK_OF(i) ((i) % (uint32_t)nChunks)
+  if (tid == 0) {
+    for (uint32_t q = 0; q + 1 < (uint32_t)NST && q < total; ++q) {
+      mbar_arrive_expect_tx(&full[q], chunk_bytes);
+      bulk_g2s(wbuf[q], wave_n + (size_t)FWD_CHUNK_OF(q) * a.chunk_elems, chunk_bytes, &full[q]);
+    }
+  }
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    SpinConst<T, 1> k;
+    T mx, my, mz;
+    int idx[1];
+    const int i = tile * BLKT + tid;
+    const bool ok = i < nM;
+    idx[0] = ok ? i : nM - 1;
+    {   // (the previous tile's products have completed: every chunk waits on its mma_bar, so A may be rewritten)
+      T lx, ly, lz;
+      load_vec3_tile<T, T, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idx, scr, lx, ly, lz);
+      tc_load_spin<NC, RELAX>(a, n, idx[0], lx, ly, lz, k, sa, tid);
+    }
+    load_vec3_tile<T, T, 1, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idx, scr, mx, my, mz);
+    tc::fence_before_sync();
+    __syncthreads();
+    const T glx = k.glx, gly = k.gly, glz = k.glz, gbz0 = k.gbz0, e1 = k.e1, e2 = k.e2;
+    for (int c = 0; c < nChunks; ++c, ++it) {
+      TC_CHUNK_BEGIN(FWD_CHUNK_OF, c == 0, c + 1 < nChunks)
+      const float* gw = wbuf[it % NST] + (size_t)2 * L::KC * rows * 4;   // gr rows [3][TCP]
+      const int ns = min(K, nT - c * K);
+      const uint32_t tcol = tlane + (it & 1) * L::BUF_COLS;
+      auto steps8 = [&](const float (&b)[16], int j0) {
+        float g[3][8];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          load4(gw + w * TCP + j0, *reinterpret_cast<float(*)[4]>(&g[w][0]));
+          load4(gw + w * TCP + j0 + 4, *reinterpret_cast<float(*)[4]>(&g[w][4]));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (j0 + u < ns) {
+            const T bz = fma_(glx, g[0][u], fma_(gly, g[1][u], fma_(glz, g[2][u], gbz0)));
+            step_fwd<T, POL, RELAX>(b[2 * u], b[2 * u + 1], bz, e1, e2, mx, my, mz);
+          }
+        }
+      };
+      float b0[16], b1[16];
+      tc::tmem_ld16_issue(tcol, b0);
+#pragma unroll 1
+      for (int g = 0; g < TC_TCMAX / 8; g += 2) {   // the read of the next 8 steps is in flight while these 8 are computed
+        if (8 * g < ns) {
+          tc::tmem_ld_wait(b0);
+          if (8 * (g + 1) < ns) tc::tmem_ld16_issue(tcol + 16 * (g + 1), b1);
+          steps8(b0, 8 * g);
+          if (ns <= 8) { TC_PRODUCT_AHEAD(c + 1 < nChunks) }
+        }
+        if (8 * (g + 1) < ns) {
+          tc::tmem_ld_wait(b1);
+          if (g + 2 < TC_TCMAX / 8 && 8 * (g + 2) < ns) tc::tmem_ld16_issue(tcol + 16 * (g + 2), b0);
+          steps8(b1, 8 * (g + 1));
+          if (g == 0) { TC_PRODUCT_AHEAD(c + 1 < nChunks) }
+        }
+      }
+      if (c + 1 < nChunks && ok) {   // checkpoint: state after (c+1)*K steps (streaming stores, see fused_fwd_kernel)
+        T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
+        __stcs(cp + idx[0], mx);
+        __stcs(cp + (size_t)nM + idx[0], my);
+        __stcs(cp + 2 * (size_t)nM + idx[0], mz);
+      }
+      tc::fence_before_sync();
+      __syncthreads();   // everyone is done with this chunk's stage and TMEM buffer
+      tc::fence_after_sync();
+    }
+    if (ok) {
+      T* op = a.Mo + ((size_t)n * nM + idx[0]) * 3;
+      op[0] = mx; op[1] = my; op[2] = mz;
+    }
+  }
+#undef FWD_CHUNK_OF
+  if (warp == 0) tc::tmem_free<L::TMEM_COLS>(tmem);
+}
+
+#undef TC_CHUNK_BEGIN
+#undef TC_PRODUCT_AHEAD
+
 }  // namespace mrphy
 
 // =============================================================================================
@@ -787,6 +1059,9 @@ struct Plan {
   int tiles;     // spin tiles per batch entry (BLKT*PK spins each)
   int Pmax;      // upper bound on CTAs per batch entry (sizes the partial-sum workspace)
   int rows;      // gradients wanted by the backward: bit 0 dL/drf, bit 1 dL/dgr (MRPHY_SKIP_GRF / _GGR clear them)
+  int chunk_elems;   // elements per staged waveform chunk (WS * TCP)
+  int tc;        // fp32 forward with >= 4 coils on the tensor cores (fused_fwd_tc_kernel); its staged chunks (TcLayout) have
+  int tc_TCP, tc_chunk_elems;   // tc_TCP (multiple of 8) steps and tc_chunk_elems elements; the backward re-packs for itself
 };
 
 int sm_count_cached() {
@@ -831,6 +1106,12 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   p->K = a->K;
   p->TCP = (a->K + 3) & ~3;
   p->nChunks = (a->nT + a->K - 1) / a->K;
+  p->chunk_elems = p->WS * p->TCP;
+  // fp32 with >= 4 coils: the transmit field as a TF32 tensor-core product (MRPHY_B200_TC=0: the FMA kernels)
+  const char* tc_env = getenv("MRPHY_B200_TC");
+  p->tc = a->dtype == MRPHY_F32 && p->NC >= MRPHY_TC_MIN_NC && a->K <= 32 && !(tc_env && tc_env[0] == '0');   // TC_TCMAX
+  p->tc_TCP = (a->K + 7) & ~7;
+  p->tc_chunk_elems = p->tc ? p->tc_TCP * (16 * (p->NC / 2) + 3) : 0;   // TcLayout<NC>::PER_STEP
   // fp32 single coil: two spins per thread, packed FFMA2 arithmetic.  fp64 and multi-coil: one spin per thread (scalar
   // kernels); a build with -DMRPHY_FP32_SCALAR also carries the fp32 single-coil scalar kernels (MRPHY_B200_PACK=1)
 #ifdef MRPHY_FP32_SCALAR
@@ -890,7 +1171,7 @@ extern "C" size_t mrphy_fused_ckpt_elems(const mrphy_fused_args* a) {
 extern "C" size_t mrphy_fused_wave_elems(const mrphy_fused_args* a) {
   Plan p;
   if (make_plan(a, &p, false) != MRPHY_OK) return 0;
-  return (size_t)a->N * p.nChunks * p.WS * p.TCP;
+  return (size_t)a->N * p.nChunks * (p.tc_chunk_elems > p.chunk_elems ? p.tc_chunk_elems : p.chunk_elems);
 }
 extern "C" size_t mrphy_fused_partial_elems(const mrphy_fused_args* a) {
   Plan p;
@@ -920,6 +1201,7 @@ KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
   KArgs<T> k;
   memset(&k, 0, sizeof(k));
   k.N = a->N; k.nM = a->nM; k.nT = a->nT; k.K = p.K; k.TCP = p.TCP; k.nChunks = p.nChunks; k.P = p.Pmax;
+  k.chunk_elems = p.chunk_elems;
   k.Mi = (const T*)a->Mi; k.Mi_sn = a->Mi_sn; k.Mi_sm = a->Mi_sm;
   k.loc = (const T*)a->loc; k.loc_sn = a->loc_sn; k.loc_sm = a->loc_sm;
   k.b1 = (const T*)a->b1; k.b1_sn = a->b1_sn; k.b1_sm = a->b1_sm; k.nC = a->nC;
@@ -931,8 +1213,26 @@ KArgs<T> make_kargs(const mrphy_fused_args* a, const Plan& p) {
   return k;
 }
 
+template <int NC>
+int launch_pack_tc(const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
+  const int64_t total = (int64_t)a->N * p.nChunks * p.tc_TCP * NC;
+  const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  const int64_t rf_sc = (a->flags & MRPHY_RF_COIL_DIM) ? a->rf_sc : 0;
+  pack_waveform_tc_kernel<NC><<<grid, 256, 0, st>>>((const float*)a->rf, a->rf_sn, a->rf_sx, a->rf_st, rf_sc, (const float*)a->gr,
+                                                    a->gr_sn, a->gr_sx, a->gr_st, a->nC, a->nT, p.K, p.tc_TCP, p.nChunks, total,
+                                                    (float*)a->wave);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
+
 template <typename T>
-int launch_pack(const mrphy_fused_args* a, const Plan& p, cudaStream_t st) {
+int launch_pack(const mrphy_fused_args* a, const Plan& p, cudaStream_t st, bool tc_layout = false) {
+  if (tc_layout) {
+    if (p.NC == 4) return launch_pack_tc<4>(a, p, st);
+    if (p.NC == 8) return launch_pack_tc<8>(a, p, st);
+    return launch_pack_tc<16>(a, p, st);
+  }
   const int64_t total = (int64_t)a->N * p.nChunks * p.WS * p.TCP;
   const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   const int64_t rf_sc = (a->flags & MRPHY_RF_COIL_DIM) ? a->rf_sc : 0;
@@ -996,6 +1296,50 @@ int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
   return MRPHY_OK;
 }
 
+// Resident CTAs per SM of a tensor-core kernel.  cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for kernels that
+// allocate TMEM (measured), although CTAs do share an SM as long as their TMEM columns fit: count registers, shared memory
+// and the 512 TMEM columns by hand.
+template <typename Kern>
+int tc_occupancy(Kern kern, size_t dyn_smem, int tmem_cols) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+  int occ = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
+  const size_t per_cta = dyn_smem + fa.sharedSizeBytes + 1024;   // 1 KB reserved per CTA
+  const int by_smem = (int)((size_t)228 * 1024 / per_cta);
+  if (by_smem < occ) occ = by_smem;
+  if (512 / tmem_cols < occ) occ = 512 / tmem_cols;
+  const int forced = env_int("MRPHY_B200_TC_OCC", 0);
+  if (forced) occ = forced;
+  return occ < 1 ? 1 : occ;
+}
+
+// tensor-core multi-coil kernels (fp32): at most 4 CTAs per SM, each owns 128 of the 512 TMEM columns
+template <int POL, bool RELAX, int NC>
+int launch_fwd_tc(KArgs<float> k, const Plan& p, cudaStream_t st) {
+  constexpr size_t smem = TcSmem<NC>::fwd_bytes;
+  auto kern = fused_fwd_tc_kernel<POL, RELAX, NC>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k.TCP = p.tc_TCP;
+  k.chunk_elems = p.tc_chunk_elems;
+  const int occ = tc_occupancy(kern, smem, TcLayout<NC>::TMEM_COLS);
+  // the one-spin-per-thread step loop is latency-bound: fill every resident slot (pick_ctas trades slots for even passes)
+  k.P = (int)((int64_t)sm_count_cached() * occ / k.N);
+  if (k.P < 1) k.P = 1;
+  if (k.P > p.Pmax) k.P = p.Pmax;
+  dim3 grid(k.P, k.N);
+  if (getenv("MRPHY_B200_DEBUG"))
+    fprintf(stderr, "[mrphy_b200] fused_fwd_tc<NC=%d> grid=(%d,%d) tiles=%d occ=%d smem=%zu K=%d\n", NC, k.P, k.N, p.tiles, occ, smem, p.K);
+  timing_begin(st);
+  kern<<<grid, 128, smem, st>>>(k);
+  timing_end(st);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return MRPHY_OK;
+}
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
 int launch_any(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {
   return bwd ? launch_bwd_s<T, POL, RELAX, NC, PK, BLKT>(k, p, need_gmi, st)
@@ -1015,6 +1359,13 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
 #ifdef MRPHY_ONLY_PK2   /* tuning builds (profiles/operand_model.py): compile the default fp32 kernels only */
   return fail(MRPHY_ERR_ARG, "built with MRPHY_ONLY_PK2%s");
 #else
+  if constexpr (sizeof(T) == 4) {
+    if (p.tc && !bwd) {   // forward with >= 4 coils: transmit field on the tensor cores
+      if (p.NC == 4) return launch_fwd_tc<POL, RELAX, 4>(k, p, st);
+      if (p.NC == 8) return launch_fwd_tc<POL, RELAX, 8>(k, p, st);
+      return launch_fwd_tc<POL, RELAX, 16>(k, p, st);
+    }
+  }
   switch (p.NC) {
     case 1:
 #ifndef MRPHY_FP32_SCALAR
@@ -1052,7 +1403,7 @@ int run_fwd(const mrphy_fused_args* a, cudaStream_t st) {
   int rc = make_plan(a, &p, true);
   if (rc) return rc;
   if ((rc = check_common<T>(a, false))) return rc;
-  if ((rc = launch_pack<T>(a, p, st))) return rc;
+  if ((rc = launch_pack<T>(a, p, st, p.tc != 0))) return rc;
   return dispatch<T>(false, a, p, st);
 }
 
@@ -1081,7 +1432,8 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, const mrphy_reparam_a
   if (rc) return rc;
   if ((rc = check_common<T>(a, true))) return rc;
   if (d && (rc = check_design(a, d))) return rc;
-  if (!wave_is_packed && (rc = launch_pack<T>(a, p, st))) return rc;
+  // (after a tensor-core forward `wave` holds that kernel's operand tiles: the backward stages its own layout over them)
+  if ((!wave_is_packed || p.tc) && (rc = launch_pack<T>(a, p, st))) return rc;
   // finished-CTA counters of the design tail: behind the scheduling ints, zeroed by the backward kernel itself
   int* const done = d ? reinterpret_cast<int*>((T*)a->partials + (size_t)a->N * p.Pmax * p.W * (size_t)a->nT) + SCHED_CLAIM + p.Pmax : nullptr;
   if ((rc = dispatch<T>(true, a, p, st, done))) return rc;

@@ -16,6 +16,7 @@ from mrphy import _cabi
 
 _F = (torch.float32, torch.float64)
 K_MAX = 64                  # checkpoint interval cap == staged chunk length (csrc: TCMAX)
+TC_K_MAX = 32               # ... of the tensor-core multi-coil kernels (fp32, >= 3 coils with a b1Map; csrc: TC_TCMAX)
 _AMPLIFY_BUDGET = 0.4       # resync before exp(K*dt/T2) exceeds e^0.4 ~ 1.5 (time-reversed states)
 
 
@@ -157,8 +158,11 @@ def _fake_blochsim_fused_fwd(Mi, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flag
     NC = next(c for c in (1, 2, 4, 8, 16) if nc <= c)           # coils held in registers (csrc: make_plan)
     W = 2 * NC + 3
     WS = (W + 3) // 4 * 4 if W * Mi.element_size() > 44 else W  # csrc: WaveLayout (step-major staging for many rows)
+    chunk = WS * ((K + 3) // 4 * 4)
+    if Mi.element_size() == 4 and NC >= 4 and K <= TC_K_MAX and os.environ.get('MRPHY_B200_TC', '1')[:1] != '0':
+        chunk = max(chunk, ((K + 7) // 8 * 8) * (16 * (NC // 2) + 3))   # csrc: TcLayout (tensor-core operand tiles + gr rows)
     return (Mi.new_empty((N, nM, 3)), Mi.new_empty((max(N * (chunks - 1) * 3 * nM, 1),)),
-            Mi.new_empty((N * chunks * WS * ((K + 3) // 4 * 4),)))
+            Mi.new_empty((N * chunks * chunk,)))
 
 
 def _fused_bwd_call(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt, K, flags, design=None):
@@ -982,6 +986,8 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
         b1 = _inner_contig(b1.expand(N, nM, 2, nC) if tuple(b1.shape) != (N, nM, 2, nC) else b1, 2)
     df, T1, T2, gam, dtt = (move(x) for x in (Δf_, T1_, T2_, γ_, dt))
     K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2)
+    if ckpt is None and dtype == torch.float32 and b1 is not None and b1.shape[3] >= 3:
+        K = min(K, TC_K_MAX)                     # the tensor-core kernels stage 32 steps per chunk
     fl = default_flags() if flags is None else flags
     if torch.is_grad_enabled() and os.environ.get('MRPHY_B200_FUSE_DESIGN', '1') != '0':
         # rf and/or gr straight out of the re-parametrisation chain: differentiate w.r.t. the design variables in the

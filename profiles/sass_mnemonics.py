@@ -4,13 +4,14 @@
     python profiles/sass_mnemonics.py [lib.so] > profiles/sass_mnemonics.txt
 
 UBLKCP = 1-D TMA bulk copy (cp.async.bulk), SYNCS = mbarrier ops, LDGSTS = cp.async 16 B, FFMA2/FMUL2/FADD2 = packed fp32,
-DFMA = FP64 pipe, MUFU = XU, VOTE/CALL = the large-angle guard of the half-angle coefficients, REDG/RED = partial-sum RED."""
+DFMA = FP64 pipe, MUFU = XU, VOTE/CALL = the large-angle guard of the half-angle coefficients, REDG/RED = partial-sum RED,
+UTCHMMA = tcgen05.mma (kind::tf32), LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc."""
 import collections
 import re
 import subprocess
 import sys
 
-WANT = ('UBLKCP', 'SYNCS', 'LDGSTS', 'FFMA2', 'FMUL2', 'FADD2', 'FFMA', 'DFMA', 'MUFU', 'VOTE', 'CALL', 'REDG', 'RED', 'SHFL', 'LDS', 'STS')
+WANT = ('UTCHMMA', 'LDTM', 'UTCBAR', 'UTCATOMSWS', 'UBLKCP', 'SYNCS', 'LDGSTS', 'FFMA2', 'FMUL2', 'FADD2', 'FFMA', 'DFMA', 'MUFU', 'VOTE', 'CALL', 'REDG', 'RED', 'SHFL', 'LDS', 'STS')
 
 lib = sys.argv[1] if len(sys.argv) > 1 else 'mrphy.py_b200/libmrphy_b200.so'
 out = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout

@@ -1,0 +1,131 @@
+// Validation + timing of the tensor-core transmit-field product (csrc/tc_helpers.cuh) before it goes into the kernels:
+//   D[128 spins][N] = A[128][K] * B[N][K]^T   (K = 2 nC, N = 2 steps per chunk), TF32 tcgen05.mma with 3-way operand split,
+// D read back per thread (= per spin = per TMEM lane) with tcgen05.ld.  Compares with an fp64 host product.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/tc_field profiles/ubench/tc_field.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../../mrphy.py_b200/csrc/tc_helpers.cuh"
+
+using namespace mrphy;
+
+template <int K, int N>
+__global__ void __launch_bounds__(128) tc_field_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D,
+                                                        int reps, int nprod) {
+  constexpr int KC = K / 4;                        // 16-byte chunks along K
+  extern __shared__ __align__(128) unsigned char dyn[];
+  float (*sa)[KC][128][4] = reinterpret_cast<float (*)[KC][128][4]>(dyn);
+  float (*sb)[KC][N][4] = reinterpret_cast<float (*)[KC][N][4]>(dyn + sizeof(float) * 3 * KC * 128 * 4);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc<N>(&tmem_slot);
+  // operands: thread s owns row s of A; rows of B are spread over the threads
+  for (int e = 0; e < K; ++e) {
+    float h, m, l;
+    tc::split3(A[tid * K + e], h, m, l);
+    sa[0][e / 4][tid][e % 4] = h; sa[1][e / 4][tid][e % 4] = m; sa[2][e / 4][tid][e % 4] = l;
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int n = i / K, e = i % K;
+    float h, m, l;
+    tc::split3(B[i], h, m, l);
+    sb[0][e / 4][n][e % 4] = h; sb[1][e / 4][n][e % 4] = m; sb[2][e / 4][n][e % 4] = l;
+  }
+  fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  constexpr uint32_t idesc = tc::idesc_tf32(128, N);
+  float acc[16];
+  float sum = 0.f;
+  for (int r = 0; r < reps; ++r) {
+    if (tid == 0) {
+      // small terms first: (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
+      const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+      bool first = true;
+      for (int q = 6 - nprod; q < 6; ++q)
+        for (int ks = 0; ks < K / 8; ++ks) {
+          tc::mma_tf32(tmem, tc::kmajor_desc(&sa[pa[q]][2 * ks][0][0], 128), tc::kmajor_desc(&sb[pb[q]][2 * ks][0][0], N), idesc,
+                       !first);
+          first = false;
+        }
+      tc::commit(&bar);
+    }
+    mbar_wait(&bar, r & 1);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+      if (r == reps - 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[(size_t)(blockIdx.x * 128 + tid) * N + c0 + i] = acc[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum += acc[i];
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();           // every thread has read this round's D before the next MMA overwrites it
+    tc::fence_after_sync();
+  }
+  if (sum == 123.456f) D[0] = sum;
+  if (warp == 0) tc::tmem_free<N>(tmem);
+}
+
+template <int K, int N>
+int run(int nprod) {
+  std::vector<float> A(128 * K), B(N * K), D(128 * N);
+  srand(1);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2 - 1;
+  for (auto& x : B) x = ((float)rand() / RAND_MAX * 2 - 1) * 0.1f;
+  float *dA, *dB, *dD;
+  const int grid = 148 * 3;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, (size_t)grid * D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = sizeof(float) * 3 * (K / 4) * (128 + N) * 4;
+  cudaFuncSetAttribute(tc_field_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_field_kernel<K, N><<<1, 128, smem>>>(dA, dB, dD, 1, nprod);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("K=%d N=%d: CUDA error %s\n", K, N, cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0, maxref = 0, err32 = 0;
+  for (int s = 0; s < 128; ++s)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0; float f = 0.f;
+      for (int k = 0; k < K; ++k) { ref += (double)A[s * K + k] * (double)B[n * K + k]; f = fmaf(A[s * K + k], B[n * K + k], f); }
+      maxerr = fmax(maxerr, fabs(ref - (double)D[s * N + n]));
+      err32 = fmax(err32, fabs(ref - (double)f));
+      maxref = fmax(maxref, fabs(ref));
+    }
+  // timing: many chunks per CTA, 3 CTAs per SM
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 2000;
+  tc_field_kernel<K, N><<<grid, 128, smem>>>(dA, dB, dD, reps, nprod);
+  cudaEventRecord(e0);
+  tc_field_kernel<K, N><<<grid, 128, smem>>>(dA, dB, dD, reps, nprod);
+  cudaEventRecord(e1);
+  e = cudaDeviceSynchronize();
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  const double fields = (double)grid * reps * 128.0 * (N / 2);       // (spin, step) pairs
+  printf("K=%2d (nC=%2d) N=%3d products=%d: max|D - fp64| = %.3e (fp32 FMA chain: %.3e, max|D| = %.2f)   %.3f ms for %d chunks/CTA x %d CTAs"
+         " = %.3e spin-steps/s field-only (%s)\n", K, K / 2, N, nprod, maxerr, err32, maxref, ms, reps, grid, fields / (ms * 1e-3),
+         e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return 0;
+}
+
+int main() {
+  int rc = 0;
+  rc |= run<8, 128>(6);
+  rc |= run<16, 128>(6);
+  rc |= run<16, 128>(3);
+  rc |= run<16, 128>(1);
+  rc |= run<32, 128>(6);
+  rc |= run<16, 64>(6);
+  rc |= run<32, 64>(6);
+  return rc;
+}

@@ -194,6 +194,41 @@ def test_fused_vs_oracle_ragged(dev, K, shape):
     assert rel(grf32, ref['grf']) < RTOL_G32 and rel(ggr32, ref['ggr']) < RTOL_G32
 
 
+@pytest.mark.parametrize('nC', [3, 4, 8, 16])
+def test_tensor_core_transmit_field_matches_fma_path_and_oracle(dev, nC, monkeypatch):
+    """fp32 forward with >= 3 coils: the transmit field sum_c b1_c rf_c comes from tcgen05.mma (TF32 operands split in two
+    exactly representable parts, fused_fwd_tc_kernel) instead of 4 nCoils FMAs per spin and step.  Must (1) be taken
+    (debug line of the launcher), (2) agree with the FMA kernels (MRPHY_B200_TC=0) to fp32 rounding, (3) track the fp64 oracle
+    as well as the reference algorithm in fp32, (4) leave the gradients -- whose backward re-stages the waveform in its own
+    layout over the tensor-core operand tiles -- unchanged, (5) step aside for checkpoint intervals above 32 steps.
+    Three tiles of spins, ragged in spins and steps (nT = 203: 7 chunks, the last of 11 steps)."""
+    from oracle import bloch_oracle as orc
+    p = _random_problem(300 + nC, 2, 300, 203, nC, has_b1=True, relax=True, dtype=f32)
+    g = {('in_' + k): v.numpy() for k, v in p.items()}
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'], T2=p['T2'],
+                                 gamma=p['gam'], dt=p['dt'])
+    p32 = {k: v.to(f32) for k, v in p.items()}
+    ref32 = orc.applypulse_fwd_bwd(p32['M0'], p32['rf'], p32['gr'], p32['loc'], p32['w'], df=p32['df'], b1=p32['b1'],
+                                   T1=p32['T1'], T2=p32['T2'], gamma=p32['gam'], dt=p32['dt'], dtype=f32)
+    monkeypatch.setenv('MRPHY_B200_TC', '0')
+    Mo_fma, gM_fma, grf_fma, ggr_fma = run_fused(g, dev, f32, p['w'].numpy(), ckpt=32)
+    monkeypatch.setenv('MRPHY_B200_TC', '1')
+    Mo_tc, gM_tc, grf_tc, ggr_tc = run_fused(g, dev, f32, p['w'].numpy(), ckpt=32)
+    d_paths, d_tc, d_fma, floor = mx(Mo_tc, Mo_fma), mx(Mo_tc, ref['Mo']), mx(Mo_fma, ref['Mo']), mx(ref32['Mo'], ref['Mo'])
+    print(f'[tensor-core field nC={nC}] |M_tc - M_fma| {d_paths:.2e}; vs fp64 oracle: tc {d_tc:.2e}, fma {d_fma:.2e}, '
+          f'reference algorithm in fp32 {floor:.2e}')
+    assert not torch.equal(Mo_tc, Mo_fma), 'tensor-core path not taken'      # different rounding order: never bit-identical
+    assert d_paths < 3e-6
+    assert d_tc < _fp32_bound(ref32['Mo'], ref['Mo'])
+    assert rel(grf_tc, ref['grf']) < RTOL_G32 and rel(ggr_tc, ref['ggr']) < RTOL_G32 and rel(gM_tc, ref['gM0']) < RTOL_G32
+    assert rel(grf_tc, grf_fma) < 2e-5 and rel(ggr_tc, ggr_fma) < 2e-5
+    # K = 64 > 32: the FMA kernels run whatever the switch says -> bit-identical to MRPHY_B200_TC=0
+    Mo64, _, _, _ = run_fused(g, dev, f32, p['w'].numpy(), ckpt=64)
+    monkeypatch.setenv('MRPHY_B200_TC', '0')
+    Mo64_fma, _, _, _ = run_fused(g, dev, f32, p['w'].numpy(), ckpt=64)
+    assert torch.equal(Mo64, Mo64_fma)
+
+
 def test_multi_tile_ctas_accumulate(dev, monkeypatch):
     """Force a 3-CTA grid so every CTA walks several spin tiles (partial-sum read-modify-write path)."""
     from oracle import bloch_oracle as orc
