@@ -445,6 +445,39 @@ def multi_gpu_check(dtype, dev, rank, world):
 WORKLOADS['small32'] = (1, 32, 256)
 
 
+def multicoil_leg(dev, flush, nC=8, n=64, nT=1000, reps=5):
+    """Parallel transmit (b1Map with nC coils) at the C2 size, kernels only (CUDA events inside the C ABI around the
+    forward -- transmit field on tcgen05 -- and the backward kernel), best of `reps` after one warm-up, L2 flushed."""
+    from mrphy import _ops, _cabi
+    g = torch.Generator(device=dev).manual_seed(0)
+    U = lambda *s: torch.rand(s, generator=g, device=dev, dtype=torch.float32) * 2 - 1
+    nM = n ** 3
+    rf = (U(1, 2, nT, nC) * 0.1 / nC).requires_grad_(True)
+    gr = (U(1, 3, nT) * 2).requires_grad_(True)
+    b1, loc, df = U(1, nM, 2, nC), U(1, nM, 3) * 12, U(1, nM) * 200
+    M0 = torch.tensor([0., 0., 1.], device=dev).expand(1, nM, 3).contiguous()
+    c = lambda v: torch.tensor(v, device=dev)
+    L = _cabi.lib()
+    L.mrphy_kernel_timing(1)
+    f, b = [], []
+    try:
+        for i in range(reps + 1):
+            flush.fill_(1.0)
+            rf.grad = gr.grad = None
+            Mo = _ops.fused_applypulse(M0, rf, gr, loc, Δf_=df, b1Map_=b1, T1_=c(1.47), T2_=c(0.07), γ_=c(4257.6), dt=c(4e-6))
+            tf = L.mrphy_last_kernel_ms()
+            Mo.sum().backward()
+            tb = L.mrphy_last_kernel_ms()
+            if i:
+                f.append(tf)
+                b.append(tb)
+    finally:
+        L.mrphy_kernel_timing(0)
+    return {'workload': f'{n}^3 spins x {nT} steps, {nC} transmit coils with a b1Map, fp32', 'value': nM * nT / ((min(f) + min(b)) * 1e-3),
+            'unit': UNIT, 'fwd_kernel_ms': min(f), 'bwd_kernel_ms': min(b),
+            'how': 'kernels only; forward: transmit field as a split-operand TF32 tcgen05.mma product (fused_fwd_tc_kernel)'}
+
+
 def measure(workload, scaling, args, dev, rank, world, flush, full):
     """Timed region (+ with `full`: e2e, per-kernel times, alternative policies, parity) of one workload."""
     import torch.distributed as dist
@@ -582,6 +615,8 @@ def run_ours(args):
                           'frac_of_issue_roofline': v2 / issue_roof, 'policy': c2['policy'], 'loss': c2['loss']}
         if check is not None:
             line['multi_gpu_check'] = check
+        if world == 1 and not args.no_extras and args.dtype == 'f32':
+            line['ptx_8_coils'] = multicoil_leg(dev, flush)
         if world == 1 and not args.no_extras:      # CPU / eager baselines are timed at N=1 only; the other ranks must not wait on them
             line['cpu_baseline'] = reference_subprocess(args, 'cpu')
             line['torch_eager_same_gpu'] = reference_subprocess(args, 'cuda')
