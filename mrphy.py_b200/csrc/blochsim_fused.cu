@@ -735,9 +735,24 @@ template <int NC> struct TcLayout {
   static constexpr int KSTEPS = NC / 4;   // tcgen05.mma instructions along K (8 values each)
   static constexpr int PER_STEP = 16 * KC + 3;                 // floats per step of a staged chunk: 2 parts x 2 rows x 2 NC + gr
   static constexpr int CHUNK_MAX = TC_TCMAX * PER_STEP;        // floats
-  static constexpr int A_FLOATS = 2 * KC * 128 * 4;
-  static constexpr int BUF_COLS = 2 * TC_TCMAX;                // TMEM columns of one chunk's field: (Bx, By) per step
-  static constexpr int TMEM_COLS = 2 * BUF_COLS;               // double-buffered: 128
+  static constexpr int A_FLOATS = 2 * KC * 128 * 4;            // one tile's A, both parts
+  static constexpr int TILE_COLS = 2 * TC_TCMAX;               // TMEM columns of one tile's field for one chunk: (Bx, By) per step
+};
+// PK spin tiles (128 spins each) per CTA: thread t owns spin t of every tile.  PK = 1: one spin per thread (scalar step), two
+// TMEM buffers so that the product of chunk c+1 runs while chunk c is stepped.  PK = 2: two spins per thread as one f2 (FFMA2:
+// half the issue slots -- the scalar loop is issue-bound, ncu: 78 % of the slots, 61 % of the FMA pipe), one TMEM buffer (the
+// product of a chunk is waited for; four resident CTAs cover for it).  Either way 128 TMEM columns per CTA: 4 CTAs per SM.
+template <int NC, int PK> struct TcCfg {
+  static constexpr int NBUF = PK == 1 ? 2 : 1;                                   // TMEM buffers
+  static constexpr int NST = (PK == 1 && NC <= 8) ? 3 : 2;                       // staged chunks
+  static constexpr int BUF_COLS = PK * TcLayout<NC>::TILE_COLS;
+  static constexpr int TMEM_COLS = NBUF * BUF_COLS;                              // 128
+  // dynamic shared memory, in bytes from a 128-byte aligned base
+  static constexpr size_t wbuf = 0;                                                                   // float[NST][CHUNK_MAX]
+  static constexpr size_t sa = ((size_t)NST * TcLayout<NC>::CHUNK_MAX * 4 + 127) / 128 * 128;         // float[PK][2][KC][128][4]
+  static constexpr size_t scr = sa + (size_t)PK * TcLayout<NC>::A_FLOATS * 4;                         // float[3 * 128 * PK]
+  static constexpr size_t bars = scr + (size_t)3 * 128 * PK * 4;                     // full[NST], mma[2], tmem slot: 64 B
+  static constexpr size_t bytes = bars + 64;
 };
 
 // pack for the tensor-core path: one thread per (n, chunk, step j < TCP, coil q < NC)
@@ -805,43 +820,38 @@ __device__ __forceinline__ void tc_load_spin(const KArgs<float>& a, int n, int i
   }
   fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's (async-proxy) reads
 }
-// the products of one staged chunk, by ONE thread: D = A_mid B_hi^T + A_hi B_mid^T + A_hi B_hi^T, then commit to `bar`
-template <int NC>
+// the products of one staged chunk, by ONE thread: per tile D = A_mid B_hi^T + A_hi B_mid^T + A_hi B_hi^T, then commit to `bar`
+template <int NC, int PK>
 __device__ __forceinline__ void tc_issue(const float* sa, const float* wb, int rows, uint32_t tmem, uint64_t* bar) {
   using L = TcLayout<NC>;
   const uint32_t idesc = tc::idesc_tf32(128, rows);
   const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-  bool acc = false;
   tc::fence_after_sync();
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
+  for (int t = 0; t < PK; ++t) {
+    bool acc = false;
 #pragma unroll
-    for (int ks = 0; ks < L::KSTEPS; ++ks) {
-      tc::mma_tf32(tmem, tc::kmajor_desc(sa + ((size_t)(pa[q] * L::KC + 2 * ks) * 128) * 4, 128),
-                   tc::kmajor_desc(wb + ((size_t)(pb[q] * L::KC + 2 * ks) * rows) * 4, rows), idesc, acc);
-      acc = true;
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int ks = 0; ks < L::KSTEPS; ++ks) {
+        tc::mma_tf32(tmem + t * L::TILE_COLS, tc::kmajor_desc(sa + (size_t)t * L::A_FLOATS + ((size_t)(pa[q] * L::KC + 2 * ks) * 128) * 4, 128),
+                     tc::kmajor_desc(wb + ((size_t)(pb[q] * L::KC + 2 * ks) * rows) * 4, rows), idesc, acc);
+        acc = true;
+      }
     }
   }
   tc::commit(bar);
 }
 
-template <int NC> struct TcSmem {   // dynamic shared memory of the tensor-core kernel, in bytes from a 128-byte aligned base
-  static constexpr int NST = NC <= 8 ? 3 : 2;                                                         // staged chunks
-  static constexpr size_t wbuf = 0;                                                                   // float[NST][CHUNK_MAX]
-  static constexpr size_t sa = ((size_t)NST * TcLayout<NC>::CHUNK_MAX * 4 + 127) / 128 * 128;         // float[2][KC][128][4]
-  static constexpr size_t scr = sa + (size_t)TcLayout<NC>::A_FLOATS * 4;                              // float[3 * 128]
-  static constexpr size_t bars = scr + 3 * 128 * 4;                                  // full[NST], mma[2], tmem slot: 64 B
-  static constexpr size_t fwd_bytes = bars + 64;
-};
-
 // Per chunk iteration `it` of a CTA (its tiles x chunks in order) thread 0 works ahead of the stepping threads, so that neither
-// the copy nor the tensor-core latency is exposed.  NST = 3 staged chunks (<= 8 coils):
-//   TC_CHUNK_BEGIN   TMA(it + 2) into stage (it + 2) % 3 (free: product and steps of it - 1 are done) and product(it + 1) into
-//                    the other TMEM buffer (its operands landed an iteration ago); a tile's FIRST chunk also issues its own
-//                    product here and everybody waits for it (A changes with the tile, so products never run ahead of a tile).
-// NST = 2 (16 coils: a stage is 17 KB): TMA(it + 1) at the beginning, and
-//   TC_PRODUCT_AHEAD product(it + 1) after 16 steps, when its operands have landed (a copy takes ~1-2 us, 8 steps ~1 us).
-// full[s] / mma_bar[b]: the k-th use has parity k & 1.
+// the copy nor (with two TMEM buffers) the tensor-core latency is exposed.  NST staged chunks, NBUF TMEM buffers:
+//   TC_CHUNK_BEGIN   TMA(it + NST - 1) into the stage the steps of it - 1 have just left.  NBUF = 2, NST = 3: product(it + 1)
+//                    into the other TMEM buffer (its operands landed an iteration ago); a tile's FIRST chunk also issues its
+//                    own product here (A changes with the tile: products never run ahead of a tile).  NBUF = 1: every chunk
+//                    issues its own product here.  Then everybody waits for the product of chunk `it`.
+//   TC_PRODUCT_AHEAD NBUF = 2, NST = 2 (16 coils: a stage is 17 KB): product(it + 1) after 16 steps, when its operands have
+//                    landed (a copy takes ~1-2 us, 8 steps ~1 us).
+// full[s]: k-th use has parity k & 1; mma_bar[b] likewise.
 #define TC_CHUNK_BEGIN(CHUNK_OF, FIRST_OF_TILE, HAS_NEXT_IN_TILE)                                                          \
   if (tid == 0) {                                                                                                          \
     if (it + (NST - 1) < total) {                                                                                          \
@@ -849,41 +859,43 @@ template <int NC> struct TcSmem {   // dynamic shared memory of the tensor-core 
       mbar_arrive_expect_tx(&full[sq], chunk_bytes);                                                                       \
       bulk_g2s(wbuf[sq], wave_n + (size_t)(CHUNK_OF(it + (NST - 1))) * a.chunk_elems, chunk_bytes, &full[sq]);              \
     }                                                                                                                      \
-    if (FIRST_OF_TILE) {                                                                                                   \
+    if ((FIRST_OF_TILE) || NBUF == 1) {                                                                                    \
       mbar_wait(&full[it % NST], (it / NST) & 1);                                                                          \
-      tc_issue<NC>(sa, wbuf[it % NST], rows, tmem + (it & 1) * L::BUF_COLS, &mma_bar[it & 1]);                              \
+      tc_issue<NC, PK>(sa, wbuf[it % NST], rows, tmem + (it % NBUF) * C::BUF_COLS, &mma_bar[it % NBUF]);                    \
     }                                                                                                                      \
-    if (NST == 3 && (HAS_NEXT_IN_TILE)) {                                                                                  \
+    if (NBUF == 2 && NST == 3 && (HAS_NEXT_IN_TILE)) {                                                                     \
       mbar_wait(&full[(it + 1) % NST], ((it + 1) / NST) & 1);                                                              \
-      tc_issue<NC>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) & 1) * L::BUF_COLS, &mma_bar[(it + 1) & 1]);            \
+      tc_issue<NC, PK>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) % NBUF) * C::BUF_COLS, &mma_bar[(it + 1) % NBUF]);  \
     }                                                                                                                      \
   }                                                                                                                        \
   mbar_wait(&full[it % NST], (it / NST) & 1);                                                                              \
-  mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);                                                                              \
+  mbar_wait(&mma_bar[it % NBUF], (it / NBUF) & 1);                                                                         \
   tc::fence_after_sync();
 #define TC_PRODUCT_AHEAD(HAS_NEXT_IN_TILE)                                                                                 \
-  if (NST == 2 && tid == 0 && (HAS_NEXT_IN_TILE)) {                                                                        \
+  if (NBUF == 2 && NST == 2 && tid == 0 && (HAS_NEXT_IN_TILE)) {                                                           \
     mbar_wait(&full[(it + 1) % NST], ((it + 1) / NST) & 1);                                                                \
-    tc_issue<NC>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) & 1) * L::BUF_COLS, &mma_bar[(it + 1) & 1]);              \
+    tc_issue<NC, PK>(sa, wbuf[(it + 1) % NST], rows, tmem + ((it + 1) % NBUF) * C::BUF_COLS, &mma_bar[(it + 1) % NBUF]);    \
   }
 
-template <int POL, bool RELAX, int NC>
-__global__ void __launch_bounds__(128, (NC <= 8 ? 4 : 3)) fused_fwd_tc_kernel(const KArgs<float> a) {
+template <int POL, bool RELAX, int NC, int PK>
+__global__ void __launch_bounds__(128, (NC <= 8 ? 4 : (PK == 1 ? 3 : 2))) fused_fwd_tc_kernel(const KArgs<float> a) {
   using L = TcLayout<NC>;
+  using C = TcCfg<NC, PK>;
   typedef float T;
-  constexpr int BLKT = 128, NST = TcSmem<NC>::NST;
+  typedef typename Pack<float, PK>::type V;
+  constexpr int BLKT = 128, NST = C::NST, NBUF = C::NBUF;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float(*wbuf)[L::CHUNK_MAX] = reinterpret_cast<float(*)[L::CHUNK_MAX]>(smem_raw + TcSmem<NC>::wbuf);
-  float* const sa = reinterpret_cast<float*>(smem_raw + TcSmem<NC>::sa);
-  float* const scr = reinterpret_cast<float*>(smem_raw + TcSmem<NC>::scr);
-  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + TcSmem<NC>::bars);
+  float(*wbuf)[L::CHUNK_MAX] = reinterpret_cast<float(*)[L::CHUNK_MAX]>(smem_raw + C::wbuf);
+  float* const sa = reinterpret_cast<float*>(smem_raw + C::sa);
+  float* const scr = reinterpret_cast<float*>(smem_raw + C::scr);
+  uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + C::bars);
   uint64_t* const mma_bar = full + NST;
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(full + NST + 2);
   const int tid = threadIdx.x, warp = tid >> 5, n = blockIdx.y;
   const int TCP = a.TCP, K = a.K, nT = a.nT, nChunks = a.nChunks, nM = a.nM, rows = 2 * TCP;
   const uint32_t chunk_bytes = (uint32_t)(a.chunk_elems * sizeof(float));
   const float* wave_n = a.wave + (size_t)n * nChunks * a.chunk_elems;
-  const int tiles = (nM + BLKT - 1) / BLKT;
+  const int tiles = (nM + BLKT * PK - 1) / (BLKT * PK);   // CTA tiles of PK x 128 consecutive spins
   const int my_tiles = ((int)blockIdx.x < tiles) ? (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total = (uint32_t)my_tiles * (uint32_t)nChunks;
   if (tid == 0) {
@@ -893,7 +905,7 @@ __global__ void __launch_bounds__(128, (NC <= 8 ? 4 : 3)) fused_fwd_tc_kernel(co
     mbar_init(&mma_bar[1], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tc::tmem_alloc<L::TMEM_COLS>(tmem_slot);
+  if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -907,27 +919,39 @@ __global__ void __launch_bounds__(128, (NC <= 8 ? 4 : 3)) fused_fwd_tc_kernel(co
   }
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    SpinConst<T, 1> k;
-    T mx, my, mz;
-    int idx[1];
-    const int i = tile * BLKT + tid;
-    const bool ok = i < nM;
-    idx[0] = ok ? i : nM - 1;
-    {   // (the previous tile's products have completed: every chunk waits on its mma_bar, so A may be rewritten)
-      T lx, ly, lz;
-      load_vec3_tile<T, T, 1, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idx, scr, lx, ly, lz);
-      tc_load_spin<NC, RELAX>(a, n, idx[0], lx, ly, lz, k, sa, tid);
+    SpinConst<V, 1> k;
+    V mx, my, mz;
+    int idx[PK];
+    bool ok[PK];
+#pragma unroll
+    for (int q = 0; q < PK; ++q) {
+      const int i = (tile * PK + q) * BLKT + tid;
+      ok[q] = i < nM;
+      idx[q] = ok[q] ? i : nM - 1;
     }
-    load_vec3_tile<T, T, 1, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idx, scr, mx, my, mz);
+    {   // (the previous tile's products have completed: every chunk waits on its mma_bar, so A may be rewritten)
+      V lx, ly, lz;
+      load_vec3_tile<T, V, PK, BLKT>(a.loc + (int64_t)n * a.loc_sn, a.loc_sm, tile, nM, idx, scr, lx, ly, lz);
+      if constexpr (PK == 1) {
+        tc_load_spin<NC, RELAX>(a, n, idx[0], lx, ly, lz, k, sa, tid);
+      } else {
+        SpinConst<float, 1> k0, k1;
+        tc_load_spin<NC, RELAX>(a, n, idx[0], getq<0>(lx), getq<0>(ly), getq<0>(lz), k0, sa, tid);
+        tc_load_spin<NC, RELAX>(a, n, idx[1], getq<1>(lx), getq<1>(ly), getq<1>(lz), k1, sa + L::A_FLOATS, tid);
+        k = pack2<1>(k0, k1);
+      }
+    }
+    load_vec3_tile<T, V, PK, BLKT>(a.Mi + (int64_t)n * a.Mi_sn, a.Mi_sm, tile, nM, idx, scr, mx, my, mz);
     tc::fence_before_sync();
     __syncthreads();
-    const T glx = k.glx, gly = k.gly, glz = k.glz, gbz0 = k.gbz0, e1 = k.e1, e2 = k.e2;
+    const V glx = k.glx, gly = k.gly, glz = k.glz, gbz0 = k.gbz0, e1 = k.e1, e2 = k.e2;
     for (int c = 0; c < nChunks; ++c, ++it) {
       TC_CHUNK_BEGIN(FWD_CHUNK_OF, c == 0, c + 1 < nChunks)
       const float* gw = wbuf[it % NST] + (size_t)2 * L::KC * rows * 4;   // gr rows [3][TCP]
       const int ns = min(K, nT - c * K);
-      const uint32_t tcol = tlane + (it & 1) * L::BUF_COLS;
-      auto steps8 = [&](const float (&b)[16], int j0) {
+      const uint32_t tcol = tlane + (it % NBUF) * C::BUF_COLS;
+      // 8 steps from 16 TMEM columns per tile: (Bx, By) of steps j0 .. j0 + 7
+      auto steps8 = [&](const float (&b)[PK][16], int j0) {
         float g[3][8];
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
@@ -937,45 +961,66 @@ __global__ void __launch_bounds__(128, (NC <= 8 ? 4 : 3)) fused_fwd_tc_kernel(co
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (j0 + u < ns) {
-            const T bz = fma_(glx, g[0][u], fma_(gly, g[1][u], fma_(glz, g[2][u], gbz0)));
-            step_fwd<T, POL, RELAX>(b[2 * u], b[2 * u + 1], bz, e1, e2, mx, my, mz);
+            const V bz = fma_(glx, V(g[0][u]), fma_(gly, V(g[1][u]), fma_(glz, V(g[2][u]), gbz0)));
+            const V bx = mkv(b[0][2 * u], b[PK - 1][2 * u], (V*)nullptr), by = mkv(b[0][2 * u + 1], b[PK - 1][2 * u + 1], (V*)nullptr);
+            step_fwd<V, POL, RELAX>(bx, by, bz, e1, e2, mx, my, mz);
           }
         }
       };
-      float b0[16], b1[16];
-      tc::tmem_ld16_issue(tcol, b0);
+      auto issue = [&](float (&b)[PK][16], int g) {
+#pragma unroll
+        for (int q = 0; q < PK; ++q) tc::tmem_ld16_issue(tcol + q * L::TILE_COLS + 16 * g, b[q]);
+      };
+      auto wait = [&](float (&b)[PK][16]) {
+        tc::tmem_ld_wait(b[0]);
+        if constexpr (PK == 2) tc::tmem_ld_wait(b[1]);
+      };
+      float b0[PK][16], b1[PK][16];
+      issue(b0, 0);
 #pragma unroll 1
       for (int g = 0; g < TC_TCMAX / 8; g += 2) {   // the read of the next 8 steps is in flight while these 8 are computed
         if (8 * g < ns) {
-          tc::tmem_ld_wait(b0);
-          if (8 * (g + 1) < ns) tc::tmem_ld16_issue(tcol + 16 * (g + 1), b1);
+          wait(b0);
+          if (8 * (g + 1) < ns) issue(b1, g + 1);
           steps8(b0, 8 * g);
           if (ns <= 8) { TC_PRODUCT_AHEAD(c + 1 < nChunks) }
         }
         if (8 * (g + 1) < ns) {
-          tc::tmem_ld_wait(b1);
-          if (g + 2 < TC_TCMAX / 8 && 8 * (g + 2) < ns) tc::tmem_ld16_issue(tcol + 16 * (g + 2), b0);
+          wait(b1);
+          if (g + 2 < TC_TCMAX / 8 && 8 * (g + 2) < ns) issue(b0, g + 2);
           steps8(b1, 8 * (g + 1));
           if (g == 0) { TC_PRODUCT_AHEAD(c + 1 < nChunks) }
         }
       }
-      if (c + 1 < nChunks && ok) {   // checkpoint: state after (c+1)*K steps (streaming stores, see fused_fwd_kernel)
+      if (c + 1 < nChunks) {   // checkpoint: state after (c+1)*K steps (streaming stores, see fused_fwd_kernel)
         T* cp = a.ckpt + ((size_t)n * (nChunks - 1) + c) * 3 * (size_t)nM;
-        __stcs(cp + idx[0], mx);
-        __stcs(cp + (size_t)nM + idx[0], my);
-        __stcs(cp + 2 * (size_t)nM + idx[0], mz);
+        if (ok[0]) {
+          __stcs(cp + idx[0], getq<0>(mx));
+          __stcs(cp + (size_t)nM + idx[0], getq<0>(my));
+          __stcs(cp + 2 * (size_t)nM + idx[0], getq<0>(mz));
+        }
+        if (PK == 2 && ok[PK - 1]) {
+          __stcs(cp + idx[PK - 1], getq<1>(mx));
+          __stcs(cp + (size_t)nM + idx[PK - 1], getq<1>(my));
+          __stcs(cp + 2 * (size_t)nM + idx[PK - 1], getq<1>(mz));
+        }
       }
       tc::fence_before_sync();
       __syncthreads();   // everyone is done with this chunk's stage and TMEM buffer
       tc::fence_after_sync();
     }
-    if (ok) {
+    if (ok[0]) {
       T* op = a.Mo + ((size_t)n * nM + idx[0]) * 3;
-      op[0] = mx; op[1] = my; op[2] = mz;
+      op[0] = getq<0>(mx); op[1] = getq<0>(my); op[2] = getq<0>(mz);
+    }
+    if (PK == 2 && ok[PK - 1]) {
+      T* op = a.Mo + ((size_t)n * nM + idx[PK - 1]) * 3;
+      op[0] = getq<1>(mx); op[1] = getq<1>(my); op[2] = getq<1>(mz);
     }
   }
 #undef FWD_CHUNK_OF
-  if (warp == 0) tc::tmem_free<L::TMEM_COLS>(tmem);
+  __syncthreads();
+  if (warp == 0) tc::tmem_free<C::TMEM_COLS>(tmem);
 }
 
 #undef TC_CHUNK_BEGIN
@@ -1318,27 +1363,37 @@ int tc_occupancy(Kern kern, size_t dyn_smem, int tmem_cols) {
 }
 
 // tensor-core multi-coil kernels (fp32): at most 4 CTAs per SM, each owns 128 of the 512 TMEM columns
-template <int POL, bool RELAX, int NC>
-int launch_fwd_tc(KArgs<float> k, const Plan& p, cudaStream_t st) {
-  constexpr size_t smem = TcSmem<NC>::fwd_bytes;
-  auto kern = fused_fwd_tc_kernel<POL, RELAX, NC>;
+template <int POL, bool RELAX, int NC, int PK>
+int launch_fwd_tc_pk(KArgs<float> k, const Plan& p, cudaStream_t st) {
+  using C = TcCfg<NC, PK>;
+  constexpr size_t smem = C::bytes;
+  auto kern = fused_fwd_tc_kernel<POL, RELAX, NC, PK>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k.TCP = p.tc_TCP;
   k.chunk_elems = p.tc_chunk_elems;
-  const int occ = tc_occupancy(kern, smem, TcLayout<NC>::TMEM_COLS);
-  // the one-spin-per-thread step loop is latency-bound: fill every resident slot (pick_ctas trades slots for even passes)
-  k.P = (int)((int64_t)sm_count_cached() * occ / k.N);
+  const int occ = tc_occupancy(kern, smem, C::TMEM_COLS);
+  const int tiles = (k.nM + 128 * PK - 1) / (128 * PK);
+  k.P = (int)((int64_t)sm_count_cached() * occ / k.N);   // every resident slot (pick_ctas trades slots for even passes)
   if (k.P < 1) k.P = 1;
-  if (k.P > p.Pmax) k.P = p.Pmax;
+  if (k.P > tiles) k.P = tiles;
   dim3 grid(k.P, k.N);
   if (getenv("MRPHY_B200_DEBUG"))
-    fprintf(stderr, "[mrphy_b200] fused_fwd_tc<NC=%d> grid=(%d,%d) tiles=%d occ=%d smem=%zu K=%d\n", NC, k.P, k.N, p.tiles, occ, smem, p.K);
+    fprintf(stderr, "[mrphy_b200] fused_fwd_tc<NC=%d,PK=%d> grid=(%d,%d) tiles=%d occ=%d smem=%zu K=%d\n", NC, PK, k.P, k.N, tiles, occ, smem, p.K);
   timing_begin(st);
   kern<<<grid, 128, smem, st>>>(k);
   timing_end(st);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;
+}
+template <int POL, bool RELAX, int NC>
+int launch_fwd_tc(const KArgs<float>& k, const Plan& p, cudaStream_t st) {
+  // two spin tiles per CTA (packed f2 step): measured 3 % (4, 8 coils) to 17 % (16 coils) faster than one tile with two TMEM
+  // buffers; a build with -DMRPHY_TC_SCALAR also carries the one-tile kernels (MRPHY_B200_TC_PACK=1) for measurements
+#ifdef MRPHY_TC_SCALAR
+  if (env_int("MRPHY_B200_TC_PACK", 2) == 1) return launch_fwd_tc_pk<POL, RELAX, NC, 1>(k, p, st);
+#endif
+  return launch_fwd_tc_pk<POL, RELAX, NC, 2>(k, p, st);
 }
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
 int launch_any(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaStream_t st) {

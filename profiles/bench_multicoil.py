@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Throughput of the multi-coil (pTx) code paths: nCoils in {1,2,4,8,16} with a b1Map, 64^3 spins x 1000 steps."""
+"""Throughput of the multi-coil (pTx) code paths: nCoils in {1,2,4,8,16} with a b1Map, 64^3 spins x 1000 steps
+(python profiles/bench_multicoil.py [n] [nT]: n^3 spins x nT steps)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'mrphy.py_b200'))
@@ -8,7 +9,7 @@ from mrphy import _ops, _cabi
 dev = torch.device('cuda:0'); dt = torch.float32
 g = torch.Generator(device='cuda').manual_seed(0)
 U = lambda *s: torch.rand(s, generator=g, device=dev, dtype=dt) * 2 - 1
-nM, nT = 64 ** 3, 1000
+nM, nT = (int(sys.argv[1]) if len(sys.argv) > 1 else 64) ** 3, (int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
 L = _cabi.lib(); L.mrphy_kernel_timing(1)
 out = {}
 for nC in (1, 2, 4, 8, 16):
