@@ -63,7 +63,8 @@ def test_sizing_entry_points(cabi):
     assert L.mrphy_fused_ckpt_elems(a) == 0 and b'K must be' in L.mrphy_last_error()
 
 
-@pytest.mark.parametrize('nC,K,nT', [(1, 64, 1000), (2, 16, 50), (3, 7, 33), (8, 64, 64), (16, 48, 100)])
+@pytest.mark.parametrize('nC,K,nT', [(1, 64, 1000), (2, 16, 50), (3, 7, 33), (8, 64, 64), (16, 48, 100),
+                                      (8, 32, 100), (4, 16, 50), (16, 24, 70), (5, 1, 9)])   # K <= 32, >= 3 coils: tensor-core operand tiles
 def test_fake_shapes_match_sizing_calls(cabi, nC, K, nT):
     """The torch.library fake (shape-only) implementation must allocate what the C sizing entry points ask for."""
     import torch
