@@ -47,7 +47,9 @@ enum mrphy_flags {
   MRPHY_NEED_GBEFF = 1 << 3,   /* explicit-field backward: also write dL/dBeff                  */
   MRPHY_TRIG_FAST_BWD = 1 << 4, /* with MRPHY_TRIG_PRECISE: the BACKWARD kernel uses MUFU trigonometry (M unchanged) */
   MRPHY_SKIP_GRF = 1 << 5,     /* fused backward: dL/drf is not wanted (grf may be NULL); its rows of the spin   */
-  MRPHY_SKIP_GGR = 1 << 6      /* reduction are not computed.  Likewise dL/dgr (ggr may be NULL).               */
+  MRPHY_SKIP_GGR = 1 << 6,     /* reduction are not computed.  Likewise dL/dgr (ggr may be NULL).               */
+  MRPHY_ZERO_GRAD_TAIL = 1 << 7 /* fused backward: grf, ggr are consecutive parts of ONE buffer [grf | ggr | 4 spare elements]
+                                  (what a sharded run all-reduces in place); the epilogue zeroes the 4 spare elements    */
 };
 
 /* A strided per-spin scalar: element (n, i) lives at ptr[n*sn + i*sm]; f64 selects the type. */

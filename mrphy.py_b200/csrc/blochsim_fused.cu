@@ -1495,12 +1495,17 @@ int run_bwd(const mrphy_fused_args* a, int wave_is_packed, const mrphy_reparam_a
   dim3 grid((a->nT + 31) / 32, p.W, a->N), block(32, 32);
   const int coil_dim = (a->flags & MRPHY_RF_COIL_DIM) ? 1 : 0;
   const int w_lo = (p.rows & 1) ? 0 : 2 * p.NC, w_hi = (p.rows & 2) ? p.W : 2 * p.NC;
+  T* tail = nullptr;   // MRPHY_ZERO_GRAD_TAIL: the 4 spare elements behind the last gradient of the caller's flat buffer
+  if (a->flags & MRPHY_ZERO_GRAD_TAIL)
+    tail = (p.rows & 2) ? (T*)a->ggr + (size_t)a->N * 3 * a->nT
+                        : (p.rows & 1) ? (T*)a->grf + (size_t)a->N * 2 * a->nT * (coil_dim ? a->nC : 1) : nullptr;
   if (d)
     grad_finalize_design_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT, coil_dim,
-                                                           p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi, *d, done);
+                                                           p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi, *d, done,
+                                                           tail);
   else
     grad_finalize_kernel<T><<<grid, block, 0, st>>>((const T*)a->partials, g_last_P, p.W, p.NC, a->nC, a->nT, coil_dim,
-                                                    p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi);
+                                                    p.sum_coils, (T)-1, (T*)a->grf, (T*)a->ggr, w_lo, w_hi, tail);
   ++g_launches;
   CK(cudaGetLastError());
   return MRPHY_OK;

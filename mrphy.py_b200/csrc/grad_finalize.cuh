@@ -23,7 +23,16 @@ __device__ __forceinline__ void grad_finalize_tile(const T* __restrict__ partial
   T sum = (T)0;
   if (t < nT) {
     const T* p = partials + ((size_t)n * P * W + w) * (size_t)nT + t;
-    for (int q = ty; q < P; q += NY) sum += p[(size_t)q * W * nT];
+    const size_t stride = (size_t)W * nT;
+    int q = ty;
+    // four independent loads in flight per thread (the grid is small: latency, not bandwidth, is what this kernel waits for);
+    // the order of the additions is fixed by (P, ty) alone
+    for (; q + 3 * NY < P; q += 4 * NY) {
+      const T v0 = p[(size_t)q * stride], v1 = p[(size_t)(q + NY) * stride], v2 = p[(size_t)(q + 2 * NY) * stride],
+              v3 = p[(size_t)(q + 3 * NY) * stride];
+      sum += v0; sum += v1; sum += v2; sum += v3;
+    }
+    for (; q < P; q += NY) sum += p[(size_t)q * stride];
   }
   sm[ty][tx] = sum;
   __syncthreads();
@@ -51,8 +60,9 @@ template <typename T>
 __global__ void __launch_bounds__(1024) grad_finalize_kernel(const T* __restrict__ partials, int P, int W, int NC, int nC,
                                                              int nT, int coil_dim, int bcast_coils, T sign,
                                                              T* __restrict__ grf, T* __restrict__ ggr, int w_lo = 0,
-                                                             int w_hi = 1 << 30) {
+                                                             int w_hi = 1 << 30, T* __restrict__ tail = nullptr) {
   __shared__ T sm[32][33];
+  if (tail && blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 4) tail[threadIdx.x] = (T)0;
   if ((int)blockIdx.y < w_lo || (int)blockIdx.y >= w_hi) return;
   grad_finalize_tile<T>(partials, P, W, NC, nC, nT, coil_dim, bcast_coils, sign, grf, ggr, sm);
 }
@@ -63,10 +73,12 @@ template <typename T>
 __global__ void __launch_bounds__(1024) grad_finalize_design_kernel(const T* __restrict__ partials, int P, int W, int NC,
                                                                     int nC, int nT, int coil_dim, int bcast_coils, T sign,
                                                                     T* grf, T* ggr, int w_lo, int w_hi,
-                                                                    const mrphy_reparam_args d, int* __restrict__ done) {
+                                                                    const mrphy_reparam_args d, int* __restrict__ done,
+                                                                    T* tail) {
   __shared__ T sm[32][33];
   __shared__ double warp_tot[32];
   __shared__ int s_last;
+  if (tail && blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 4) tail[threadIdx.x] = (T)0;
   if ((int)blockIdx.y >= w_lo && (int)blockIdx.y < w_hi)
     grad_finalize_tile<T>(partials, P, W, NC, nC, nT, coil_dim, bcast_coils, sign, grf, ggr, sm);
   const int tid = threadIdx.y * 32 + threadIdx.x, n = blockIdx.z;

@@ -179,7 +179,10 @@ def _fused_bwd_call(gMo, Mo, ckpt, wave, rf, gr, loc, df, b1, T1, T2, gamma, dt,
     # them over ranks with a single in-place all-reduce of the buffer (mrphy.parallel), the spare tail carrying the loss
     n_rf, n_gr = (rf.numel() if want_rf else 0), (a.N * 3 * a.nT if want_gr else 0)
     flat = torch.empty(n_rf + n_gr + GRAD_TAIL, **kw)
-    flat[n_rf + n_gr:].zero_()
+    if want_rf or want_gr:
+        a.flags |= _cabi.FLAG_ZERO_GRAD_TAIL       # the gradient epilogue zeroes the spare tail: no fill launch of its own
+    else:
+        flat.zero_()
     grf = flat[:n_rf].view(rf.shape) if want_rf else flat[:0]
     ggr = flat[n_rf:n_rf + n_gr].view(a.N, 3, a.nT) if want_gr else flat[:0]
     with torch.cuda.device(Mo.device):        # the workspace is sized from THIS device's SM count
