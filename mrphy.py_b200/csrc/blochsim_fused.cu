@@ -87,6 +87,12 @@ __device__ __forceinline__ void load_step(const T* wb, int TCP, int j, T (&sv)[W
 #ifndef MRPHY_RED_BUDGET
 #define MRPHY_RED_BUDGET 10240
 #endif
+#ifndef MRPHY_WRED_TR_BYTES
+#define MRPHY_WRED_TR_BYTES 64   // multi-coil backward: steps per reduction tile x sizeof(T)
+#endif
+#ifndef MRPHY_MC_MINB
+#define MRPHY_MC_MINB 1         // multi-coil backward: minimum resident CTAs per SM asked of the compiler (register cap)
+#endif
 #ifndef MRPHY_BWD_MINB
 #define MRPHY_BWD_MINB 8     // spin-packed backward: 128 registers, 8 CTAs (16 warps) per SM -- measured best of 6..10
 #endif
@@ -110,7 +116,7 @@ template <typename T, int NC, int BLKT> struct BwdSmem {
   static constexpr int W = 2 * NC + 3;
   static constexpr int NW = BLKT / 32;
   static constexpr bool WRED = NC > 1;
-  static constexpr int TR = WRED ? 64 / (int)sizeof(T) : pick_tr(W, (int)sizeof(T));   // WRED: 16 (fp32), 8 (fp64)
+  static constexpr int TR = WRED ? MRPHY_WRED_TR_BYTES / (int)sizeof(T) : pick_tr(W, (int)sizeof(T));   // WRED: 16 (fp32), 8 (fp64)
   static constexpr int WP = (W + 3) & ~3;                                          // weights per spin, padded to 128-bit loads
   static constexpr int E16 = (int)sizeof(T) / 4;                                   // one F entry in 16-byte units
   static constexpr int P16 = TR * E16 + 1;                                         // per-spin pitch of the F tile (odd: conflict-free)
@@ -479,7 +485,7 @@ __device__ __forceinline__ void warp_tile_reduce_weighted(const unsigned char* f
 // ROWS: which gradients the caller wants -- bit 0 dL/drf (rows [0, 2 NC)), bit 1 dL/dgr (rows [2 NC, W)); the other rows
 // of the spin reduction are neither formed nor reduced (an RF-only design skips 3 of its 5 rows).
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT, int ROWS = 3>
-__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : (sizeof(T) == 8 && NC == 1 ? 4 : 1))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : (sizeof(T) == 8 && NC == 1 ? 4 : (sizeof(T) == 4 && NC > 1 ? MRPHY_MC_MINB : 1)))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
   typedef typename Pack<T, PK>::type V;
   using L = BwdSmem<T, NC, BLKT>;
   constexpr int W = L::W, TR = L::TR, NW = L::NW;
