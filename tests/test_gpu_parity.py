@@ -229,6 +229,21 @@ def test_tensor_core_transmit_field_matches_fma_path_and_oracle(dev, nC, monkeyp
     assert torch.equal(Mo64, Mo64_fma)
 
 
+@pytest.mark.parametrize('shape', [(1, 1, 1, 4), (2, 5, 3, 8), (1, 127, 9, 16), (70, 3, 40, 4)])
+def test_tensor_core_forward_tiny_and_many_entries(dev, shape):
+    """Edge sizes of the tensor-core forward: a single spin and a single step (one TMEM lane, 2 of 16 operand rows live), fewer
+    spins than one tile, more batch entries than resident CTA slots per entry (N = 70)."""
+    from oracle import bloch_oracle as orc
+    N, nM, nT, nC = shape
+    p = _random_problem(500 + nM, N, nM, nT, nC, has_b1=True, relax=True, dtype=f32)
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'], T2=p['T2'],
+                                 gamma=p['gam'], dt=p['dt'])
+    g = {('in_' + k): v.numpy() for k, v in p.items()}
+    Mo, gM0, grf, ggr = run_fused(g, dev, f32, p['w'].numpy())
+    assert mx(Mo, ref['Mo']) < ATOL32
+    assert rel(grf, ref['grf']) < RTOL_G32 and rel(ggr, ref['ggr']) < RTOL_G32 and rel(gM0, ref['gM0']) < RTOL_G32
+
+
 def test_tensor_core_forward_is_graph_capturable_and_batched(dev):
     """The tensor-core forward inside a captured design step (its launcher queries function attributes, sets the dynamic
     shared-memory limit and allocates TMEM in-kernel: none of it may break stream capture), with N = 3 batch entries of
