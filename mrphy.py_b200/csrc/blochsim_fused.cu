@@ -87,6 +87,10 @@ __device__ __forceinline__ void load_step(const T* wb, int TCP, int j, T (&sv)[W
 #ifndef MRPHY_RED_BUDGET
 #define MRPHY_RED_BUDGET 10240
 #endif
+#ifndef MRPHY_NC2_MINB
+#define MRPHY_NC2_MINB 14        // packed 2-coil forward: 64-thread CTAs per SM asked of the compiler: 72 registers and a 56-byte
+                                 // spill frame beat 80 / 86 registers without one (measured 0.521 vs 0.588 / 0.598 ms at C2)
+#endif
 #ifndef MRPHY_WRED_TR_BYTES
 #define MRPHY_WRED_TR_BYTES 64   // multi-coil backward: steps per reduction tile x sizeof(T)
 #endif
@@ -284,7 +288,7 @@ __global__ void pack_waveform_kernel(const T* __restrict__ rf, int64_t rf_sn, in
 // ------------------------------------------------------------------------------------------
 // forward.  PK spins per thread (PK == 2: packed f2 arithmetic), BLKT threads per CTA.
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT>
-__global__ void __launch_bounds__(BLKT, (PK == 2 ? 14 : 1)) fused_fwd_kernel(const KArgs<T> a) {
+__global__ void __launch_bounds__(BLKT, (PK == 2 ? (NC == 1 ? 14 : MRPHY_NC2_MINB) : 1)) fused_fwd_kernel(const KArgs<T> a) {
   typedef typename Pack<T, PK>::type V;
   constexpr int W = 2 * NC + 3;
   constexpr int WS = WaveLayout<T, W>::WS;
@@ -1421,6 +1425,8 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
   return fail(MRPHY_ERR_ARG, "built with MRPHY_ONLY_PK2%s");
 #else
   if constexpr (sizeof(T) == 4) {
+    // forward with 2 coils: two spins per thread (FFMA2) like the single-coil kernel; same tiles of 128 spins, same staging
+    if (p.NC == 2 && !bwd && env_int("MRPHY_B200_NC2_PACK", 2) == 2) return launch_fwd_s<T, POL, RELAX, 2, 2, 64>(k, p, st);
     if (p.tc && !bwd) {   // forward with >= 4 coils: transmit field on the tensor cores
       if (p.NC == 4) return launch_fwd_tc<POL, RELAX, 4>(k, p, st);
       if (p.NC == 8) return launch_fwd_tc<POL, RELAX, 8>(k, p, st);
