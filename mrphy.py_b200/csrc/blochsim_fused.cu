@@ -106,7 +106,8 @@ __device__ __forceinline__ void load_step(const T* wb, int TCP, int j, T (&sv)[W
 #endif
 constexpr int pick_tr(int W, int elem) {
   int tr = 16;
-  const int budget = W >= 19 ? 2 * MRPHY_RED_BUDGET : (W == 11 ? MRPHY_RED_BUDGET + 1024 : MRPHY_RED_BUDGET);
+  // W == 7: two coils, two spins per thread -- 16 steps (14 KB per warp, 3 CTAs per SM) measured 8 % faster than 8 (4 CTAs)
+  const int budget = W >= 19 ? 2 * MRPHY_RED_BUDGET : (W == 11 ? MRPHY_RED_BUDGET + 1024 : (W == 7 ? MRPHY_RED_BUDGET + 4096 : MRPHY_RED_BUDGET));
   while (tr > 1 && W * tr * 32 * elem > budget) tr >>= 1;
   return tr;
 }
@@ -116,10 +117,10 @@ constexpr int pick_tr(int W, int elem) {
 // Multi-coil (WRED): it holds only F = -dL/db (3 values + pad per spin and step, one 128-bit store per step instead of
 // 2 NC + 3 scalar ones) and the per-spin weights (g*b1 of every coil, g*loc) sit beside it; they are applied in the reduce
 // phase, where a lane owns ONE time step and sums over its share of the warp's spins (warp_tile_reduce_weighted).
-template <typename T, int NC, int BLKT> struct BwdSmem {
+template <typename T, int NC, int BLKT, int PK = 1> struct BwdSmem {
   static constexpr int W = 2 * NC + 3;
   static constexpr int NW = BLKT / 32;
-  static constexpr bool WRED = NC > 1;
+  static constexpr bool WRED = NC > 1 && PK == 1;   // (two coils, two spins per thread: the single-coil scheme with 7 rows)
   static constexpr int TR = WRED ? MRPHY_WRED_TR_BYTES / (int)sizeof(T) : pick_tr(W, (int)sizeof(T));   // WRED: 16 (fp32), 8 (fp64)
   static constexpr int WP = (W + 3) & ~3;                                          // weights per spin, padded to 128-bit loads
   static constexpr int E16 = (int)sizeof(T) / 4;                                   // one F entry in 16-byte units
@@ -491,7 +492,7 @@ __device__ __forceinline__ void warp_tile_reduce_weighted(const unsigned char* f
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT, int ROWS = 3>
 __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : (sizeof(T) == 8 && NC == 1 ? 4 : (sizeof(T) == 4 && NC > 1 ? MRPHY_MC_MINB : 1)))) fused_bwd_kernel(const KArgs<T> a, const int need_gmi) {
   typedef typename Pack<T, PK>::type V;
-  using L = BwdSmem<T, NC, BLKT>;
+  using L = BwdSmem<T, NC, BLKT, PK>;
   constexpr int W = L::W, TR = L::TR, NW = L::NW;
   constexpr bool WANT_RF = (ROWS & 1) != 0, WANT_GR = (ROWS & 2) != 0;
   constexpr int W0 = WANT_RF ? 0 : 2 * NC, W1 = WANT_GR ? W : 2 * NC;
@@ -1318,7 +1319,7 @@ int launch_fwd_s(KArgs<T> k, const Plan& p, cudaStream_t st) {
 }
 template <typename T, int POL, bool RELAX, int NC, int PK, int BLKT, int ROWS = 3>
 int launch_bwd_s(KArgs<T> k, const Plan& p, int need_gmi, cudaStream_t st) {
-  constexpr size_t smem = BwdSmem<T, NC, BLKT>::bytes;
+  constexpr size_t smem = BwdSmem<T, NC, BLKT, PK>::bytes;
   auto kern = fused_bwd_kernel<T, POL, RELAX, NC, PK, BLKT, ROWS>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // static + dynamic may exceed 48 KB
   int occ = 0;
@@ -1426,7 +1427,14 @@ int dispatch_nc(bool bwd, const KArgs<T>& k, const Plan& p, int need_gmi, cudaSt
 #else
   if constexpr (sizeof(T) == 4) {
     // forward with 2 coils: two spins per thread (FFMA2) like the single-coil kernel; same tiles of 128 spins, same staging
-    if (p.NC == 2 && !bwd && env_int("MRPHY_B200_NC2_PACK", 2) == 2) return launch_fwd_s<T, POL, RELAX, 2, 2, 64>(k, p, st);
+    if (p.NC == 2 && env_int("MRPHY_B200_NC2_PACK", 2) == 2) {
+      if (!bwd) return launch_fwd_s<T, POL, RELAX, 2, 2, 64>(k, p, st);
+      if (env_int("MRPHY_B200_NC2_PACK_BWD", 2) == 2) {
+        if (p.rows == 1) return launch_bwd_s<T, POL, RELAX, 2, 2, MRPHY_BWD_BLKT, 1>(k, p, need_gmi, st);
+        if (p.rows == 2) return launch_bwd_s<T, POL, RELAX, 2, 2, MRPHY_BWD_BLKT, 2>(k, p, need_gmi, st);
+        return launch_bwd_s<T, POL, RELAX, 2, 2, MRPHY_BWD_BLKT>(k, p, need_gmi, st);
+      }
+    }
     if (p.tc && !bwd) {   // forward with >= 4 coils: transmit field on the tensor cores
       if (p.NC == 4) return launch_fwd_tc<POL, RELAX, 4>(k, p, st);
       if (p.NC == 8) return launch_fwd_tc<POL, RELAX, 8>(k, p, st);
