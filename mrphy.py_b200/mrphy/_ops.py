@@ -757,6 +757,9 @@ torch.library.register_autograd('mrphy_b200::clamp_waveform', _clamp_backward, s
 # waveforms they return with the design variables they came from (`tag_design`); when such a waveform reaches
 # `fused_applypulse`, the simulation is recorded in autograd as a function of the DESIGN VARIABLES, and its backward evaluates
 # their gradients in the tail of the simulation's own gradient epilogue -- the backward launch of the chain disappears.
+# Consequence: such a waveform is no longer a node of Mo's graph.  `x.retain_grad()` / `x.register_hook()` before the call are
+# honoured (two-stage path); `torch.autograd.grad(loss, [rf])` on a re-parametrised rf raises ("not used in the graph") --
+# MRPHY_B200_FUSE_DESIGN=0 restores the reference's graph.
 class _DesignRecord:
     __slots__ = ('tensors', 'kind', 'versions', 'out_version')
 
@@ -781,8 +784,9 @@ def tag_design(rf: Optional[Tensor], gr: Optional[Tensor], rho, theta, rfmax, ts
 
 def _design_of(x: Tensor, used: Tensor) -> Optional[_DesignRecord]:
     rec = getattr(x, '_mrphy_design', None)
-    if rec is None or used is not x or not x.requires_grad or x.retains_grad or not rec.valid_for(x):
-        return None
+    if rec is None or used is not x or not x.requires_grad or x.retains_grad or getattr(x, '_backward_hooks', None) \
+            or not rec.valid_for(x):
+        return None          # (a caller who wants dL/dx itself -- retain_grad, a hook -- gets the two-stage path)
     return rec
 
 

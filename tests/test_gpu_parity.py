@@ -875,7 +875,7 @@ def _design_problem(dev, dtype, nC, seed=3, N=2, nM=301, nT=333):
     return {k: v.to(dtype).to(f64) for k, v in d.items()}, p
 
 
-def _design_step(dev, dtype, d, p, mode, fuse, extra_penalty=False, retain=False):
+def _design_step(dev, dtype, d, p, mode, fuse, extra_penalty=False, retain=False, hook=None):
     """loss = Σ w·Mo(applypulse(chain(tρ, θ, ts))) -> (Mo, dL/dtρ, dL/dθ, dL/dts, backward launches)."""
     from mrphy import utils, _ops, _cabi
     os.environ['MRPHY_B200_FUSE_DESIGN'] = '1' if fuse else '0'
@@ -893,6 +893,8 @@ def _design_step(dev, dtype, d, p, mode, fuse, extra_penalty=False, retain=False
             gr = utils.ts2g(ts, t['smax'], t['dt'])
         if retain:
             rf.retain_grad()
+        if hook is not None:
+            rf.register_hook(hook)
         q = {k: (None if v is None else T(v.numpy(), dev, dtype)) for k, v in p.items()}
         Mo = _ops.fused_applypulse(q['M0'], rf, gr, q['loc'], Δf_=q['df'], b1Map_=q['b1'], T1_=q['T1'], T2_=q['T2'],
                                    γ_=T(p['gam'].numpy(), dev, f64), dt=T(p['dt'].numpy(), dev, f64))
@@ -958,8 +960,8 @@ def test_design_adjoint_fused_into_gradient_epilogue(dev, dtype, mode, nC):
 
 def test_design_tail_second_consumer_retain_grad_and_graph_replay(dev):
     """(1) rf also feeds a penalty term: the simulation's share arrives through the fused tail, the penalty's through the
-    chain's own backward, and autograd adds them at the leaves.  (2) `rf.retain_grad()`: the caller wants dL/drf itself, so
-    the two-stage path runs and rf.grad is filled.  (3) a captured step replays with the finished-CTA counters reset by the
+    chain's own backward, and autograd adds them at the leaves.  (2) `rf.retain_grad()` or a hook on rf: the caller wants dL/drf
+    itself, so the two-stage path runs and rf.grad is filled / the hook fires.  (3) a captured step replays with the finished-CTA counters reset by the
     kernels themselves: three replays, bit-identical gradients."""
     from mrphy import utils, _ops, graphs
     d, p = _design_problem(dev, f32, 1, seed=9, N=1, nM=700, nT=130)
@@ -970,6 +972,9 @@ def test_design_tail_second_consumer_retain_grad_and_graph_replay(dev):
     _, g_r, n_r, rf_grad = _design_step(dev, f32, d, p, 'joint', fuse=True, retain=True)
     _, g_0, n_0, _ = _design_step(dev, f32, d, p, 'joint', fuse=False)
     assert rf_grad is not None and n_r == n_0 and all(torch.equal(a, b) for a, b in zip(g_r, g_0))
+    seen = []
+    _, g_h, n_h, _ = _design_step(dev, f32, d, p, 'joint', fuse=True, hook=lambda g: seen.append(g.clone()))
+    assert len(seen) == 1 and torch.equal(seen[0], rf_grad) and n_h == n_0      # a hook on rf still sees dL/drf
     t = {k: T(v.numpy(), dev, f32) for k, v in d.items()}
     rho, theta, ts = (t[k].clone().requires_grad_(True) for k in ('rho', 'theta', 'ts'))
     q = {k: (None if v is None else T(v.numpy(), dev, f32)) for k, v in p.items()}
