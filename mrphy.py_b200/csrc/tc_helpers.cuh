@@ -24,19 +24,8 @@ __device__ __forceinline__ uint64_t kmajor_desc(const void* smem_tile, int rows)
   d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)      bits [46,48)
   return d;                                                 // base offset 0, layout type 0 = no swizzle
 }
-// the same tile read as an MN-major operand (MN = the 4-element chunks, K = the rows): 8 rows x 16 B core matrices again,
-// next MN group = next chunk (SBO = rows * 16 B), next 8 K = next 8 rows (LBO = 128 B)
-__device__ __forceinline__ uint64_t mnmajor_desc(const void* smem_tile, int rows) {
-  const uint32_t addr = smem_u32(smem_tile);
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fff);
-  d |= (uint64_t)((128u >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((((uint32_t)rows * 16u) >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-// instruction descriptor: D fp32, A and B tf32; a_mn / b_mn: operand is MN-major
+// instruction descriptor: D fp32, A and B tf32; a_mn / b_mn: operand is MN-major (TF32: only in the 128B_BASE32B swizzled
+// layout -- an unswizzled MN-major descriptor is accepted and yields zeros, profiles/ubench/tc_field.cu)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);

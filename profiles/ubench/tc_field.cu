@@ -118,6 +118,86 @@ int run(int nprod) {
   return 0;
 }
 
+// The spin reduction of the adjoint as a product (not shipped): D2[e][n] = sum_s Wt[s][e] * F[n][s], K = 128 spins.
+// B2 = F^T K-major (tile[chunk s/4][row n][4]).  A2 = the weights, either re-laid out spin-minor (K-major, amn = 0: works) or as the
+// MN-MAJOR view of the tile the field product reads (tile[chunk e/4][spin][4], amn = 1): an unswizzled MN-major TF32 descriptor
+// is accepted but produces zeros -- the reduce product would need its own copy of the weights.
+template <int N>
+__global__ void __launch_bounds__(128) tc_reduce_kernel(const float* __restrict__ Wt /*[128 spins][128]*/, const float* __restrict__ F /*[N][128 spins]*/,
+                                                        float* __restrict__ D /*[128][N]*/, uint32_t lbo, uint32_t sbo, uint32_t kstep, int amn) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  float (*sa)[128][4] = reinterpret_cast<float (*)[128][4]>(dyn);                            // [32 chunks of e][128 spins][4]
+  float (*sb)[N][4] = reinterpret_cast<float (*)[N][4]>(dyn + sizeof(float) * 32 * 128 * 4);  // [32 chunks of s][N rows][4]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  constexpr int COLS = N <= 32 ? 32 : N <= 64 ? 64 : 128;
+  if (warp == 0) tc::tmem_alloc<COLS>(&tmem_slot);
+  for (int e = 0; e < 128; ++e) {       // thread = spin
+    if (amn) sa[e / 4][tid][e % 4] = tc::tf32_rn(Wt[tid * 128 + e]);
+    else sa[tid / 4][e][tid % 4] = tc::tf32_rn(Wt[tid * 128 + e]);   // K-major control: tile[chunk s/4][row e][4 spins]
+  }
+  for (int i = tid; i < N * 128; i += 128) { const int n = i / 128, sp = i % 128; sb[sp / 4][n][sp % 4] = tc::tf32_rn(F[i]); }
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32(128, N, /*a_mn=*/amn != 0, /*b_mn=*/false);
+    for (int ks = 0; ks < 16; ++ks)     // 8 spins per instruction: 8 rows of A2's tile, 2 chunks of B2's
+    {
+      uint64_t d = (uint64_t)(((smem_u32(&sa[0][0][0]) + ks * kstep) >> 4) & 0x3fff) | (uint64_t)((lbo >> 4) & 0x3fff) << 16 |
+                   (uint64_t)((sbo >> 4) & 0x3fff) << 32 | (uint64_t)1 << 46;
+      if (!amn) d = tc::kmajor_desc(&sa[2 * ks][0][0], 128);
+      tc::mma_tf32(tmem, d, tc::kmajor_desc(&sb[2 * ks][0][0], N), idesc, ks > 0);
+    }
+    tc::commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  float acc[16];
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, acc);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)tid * N + c0 + i] = acc[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free<COLS>(tmem);
+}
+
+template <int N>
+int run_reduce(uint32_t lbo, uint32_t sbo, uint32_t kstep, int amn = 1) {
+  std::vector<float> W(128 * 128), F(N * 128), D(128 * N);
+  srand(2);
+  for (auto& x : W) x = (float)rand() / RAND_MAX * 2 - 1;
+  for (auto& x : F) x = (float)rand() / RAND_MAX * 2 - 1;
+  float *dW, *dF, *dD;
+  cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dF, F.size() * 4); cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dF, F.data(), F.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = sizeof(float) * 32 * (128 + N) * 4;
+  cudaFuncSetAttribute(tc_reduce_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_reduce_kernel<N><<<1, 128, smem>>>(dW, dF, dD, lbo, sbo, kstep, amn);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("reduce N=%d: CUDA error %s\n", N, cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0, maxref = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      for (int sp = 0; sp < 128; ++sp) ref += (double)W[sp * 128 + m] * (double)F[n * 128 + sp];
+      maxerr = fmax(maxerr, fabs(ref - (double)D[m * N + n]));
+      maxref = fmax(maxref, fabs(ref));
+    }
+  printf("reduce product D2 = Wt^T F, N=%d, K=128 spins, LBO=%u SBO=%u kstep=%u amn=%d, single TF32 part: max|D - fp64| = %.3e (max|D| = %.2f)"
+         " -> descriptor %s   D[0][0..2] = %.3f %.3f %.3f\n", N, lbo, sbo, kstep, amn, maxerr, maxref, maxerr < 2e-2 ? "OK (error = TF32 rounding of the operands)" : "NO RESULT", D[0], D[1], D[2]);
+  cudaFree(dW); cudaFree(dF); cudaFree(dD);
+  return maxerr < 2e-2 ? 0 : 1;
+}
+
 int main() {
   int rc = 0;
   rc |= run<8, 128>(6);
@@ -127,5 +207,8 @@ int main() {
   rc |= run<32, 128>(6);
   rc |= run<16, 64>(6);
   rc |= run<32, 64>(6);
+  rc |= run_reduce<64>(0, 0, 0, 0);          // control: weights re-laid out spin-minor (K-major A)
+  run_reduce<64>(128, 2048, 128, 1);         // the field product's tile read MN-major, unswizzled: all zeros on B200 (TF32 MN-major
+  run_reduce<64>(2048, 128, 128, 1);         // operands exist only in the 128B_BASE32B swizzled layout); either LBO/SBO assignment
   return rc;
 }
