@@ -1168,11 +1168,13 @@ def test_geometry_gradients_route_through_explicit_field(dev):
 
 
 @pytest.mark.parametrize('trig', ['fast', 'mixed', 'precise', 'strict'])
-def test_fp32_policies_agree_with_oracle(dev, trig):
-    """The fp32 arithmetic policies on a ragged problem (nT = 203: short enough for fp32 to meet the north_star's flat 1e-5)."""
+@pytest.mark.parametrize('nC', [1, 2, 8])
+def test_fp32_policies_agree_with_oracle(dev, trig, nC):
+    """The fp32 arithmetic policies on a ragged problem (nT = 203: short enough for fp32 to meet the north_star's flat 1e-5),
+    single coil (packed kernels), 2 coils (packed kernels, FMA field) and 8 coils (tensor-core forward, weighted reduce)."""
     from mrphy import _ops
     from oracle import bloch_oracle as orc
-    p = _random_problem(55, 2, 333, 203, 1, has_b1=True, relax=True, dtype=f32)
+    p = _random_problem(55 + nC, 2, 333, 203, nC, has_b1=True, relax=True, dtype=f32)
     ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'],
                                  T2=p['T2'], gamma=p['gam'], dt=p['dt'])
     g = {('in_' + k): v.numpy() for k, v in p.items() if v is not None}
