@@ -35,7 +35,14 @@
 
 namespace mrphy {
 
-constexpr int TCMAX = 64;   // max steps per staged waveform chunk (== max checkpoint interval)
+// Max steps per staged waveform chunk (== max checkpoint interval).  fp32 single coil: 128 -- half the chunk transitions
+// (barrier, mbarrier wait, checkpoint traffic) of 64: +0.6 % at C5, +0.8 % at C2, gradients move by 1e-6 relative (the
+// time-reversed states are resynchronised half as often); the other kernels keep 64 (their staged rows are wider).
+#ifndef MRPHY_TCMAX1
+#define MRPHY_TCMAX1 128
+#endif
+constexpr int TCMAX = 64;
+template <typename T, int NC> struct ChunkMax { static constexpr int v = (sizeof(T) == 4 && NC == 1) ? MRPHY_TCMAX1 : TCMAX; };
 
 #ifdef MRPHY_CTA_TRACE
 // measurement build only (profiles/cta_trace.py): per CTA of the backward kernel (SM id, start, end) in ns
@@ -128,7 +135,8 @@ template <typename T, int NC, int BLKT, int PK = 1> struct BwdSmem {
   static constexpr size_t red_bytes = WRED ? (size_t)NW * 32 * (P16 * 16 + WP * sizeof(T)) : (size_t)NW * W * TR * 32 * sizeof(T);
   static constexpr size_t wbuf = 0;                                                // T[2][W*TCMAX]
   static constexpr int WS = WaveLayout<T, W>::WS;
-  static constexpr size_t red = (2 * WS * TCMAX * sizeof(T) + 127) / 128 * 128;    // T[NW][W][TR][32]  |  F tiles + weights
+  static constexpr int TCM = ChunkMax<T, NC>::v;
+  static constexpr size_t red = (2 * WS * TCM * sizeof(T) + 127) / 128 * 128;      // T[NW][W][TR][32]  |  F tiles + weights
   static constexpr size_t cta = (red + red_bytes + 15) / 16 * 16;                  // T[2][NW][W][TR] (double-buffered)
   static constexpr size_t bar = (cta + (size_t)2 * NW * W * TR * sizeof(T) + 15) / 16 * 16;   // uint64_t[2]
   static constexpr size_t bytes = bar + 16;
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? (NC == 1 ? 14 : MRPHY_NC2_MIN
   typedef typename Pack<T, PK>::type V;
   constexpr int W = 2 * NC + 3;
   constexpr int WS = WaveLayout<T, W>::WS;
-  __shared__ __align__(128) T wbuf[2][WS * TCMAX];
+  __shared__ __align__(128) T wbuf[2][WS * ChunkMax<T, NC>::v];
   __shared__ __align__(16) T scr[3 * BLKT * PK];
   __shared__ __align__(8) uint64_t full[2];
   const int tid = threadIdx.x, n = blockIdx.y;
@@ -498,7 +506,7 @@ __global__ void __launch_bounds__(BLKT, (PK == 2 ? MRPHY_BWD_MINB * 64 / BLKT : 
   constexpr int W0 = WANT_RF ? 0 : 2 * NC, W1 = WANT_GR ? W : 2 * NC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int WS = L::WS;
-  T(*wbuf)[WS * TCMAX] = reinterpret_cast<T(*)[WS * TCMAX]>(smem_raw + L::wbuf);
+  T(*wbuf)[WS * L::TCM] = reinterpret_cast<T(*)[WS * L::TCM]>(smem_raw + L::wbuf);
   T(*red)[W][TR][32] = reinterpret_cast<T(*)[W][TR][32]>(smem_raw + L::red);   // per-warp transposition tile (single coil)
   constexpr bool WRED = L::WRED;
   unsigned char* const ft = smem_raw + L::red + (size_t)(threadIdx.x >> 5) * 32 * L::P16 * 16;            // WRED: this warp's F tile
@@ -1151,11 +1159,12 @@ int make_plan(const mrphy_fused_args* a, Plan* p, bool need_device) {
   if (!a) return fail(MRPHY_ERR_ARG, "null args%s");
   if (a->dtype != MRPHY_F32 && a->dtype != MRPHY_F64) return fail(MRPHY_ERR_ARG, "dtype must be MRPHY_F32 or MRPHY_F64%s");
   if (a->N < 1 || a->nM < 1 || a->nT < 1 || a->nC < 1 || a->N > 65535) return fail(MRPHY_ERR_ARG, "need 1 <= N <= 65535 and nM, nT, nC >= 1%s");
-  if (a->K < 1 || a->K > TCMAX) return fail(MRPHY_ERR_ARG, "checkpoint interval K must be in [1, 64]%s");
   p->sum_coils = a->b1 == nullptr;
   const int nc = p->sum_coils ? 1 : a->nC;
   if (nc > 16) return fail(MRPHY_ERR_ARG, "more than 16 transmit coils with a b1Map are not supported%s");
   p->NC = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : nc <= 8 ? 8 : 16;
+  if (a->K < 1 || a->K > ((a->dtype == MRPHY_F32 && p->NC == 1) ? MRPHY_TCMAX1 : TCMAX))
+    return fail(MRPHY_ERR_ARG, "checkpoint interval K must be in [1, 64] (fp32 with one transmit channel: [1, 128])%s");
   p->W = 2 * p->NC + 3;
   p->stepmajor = (size_t)p->W * (a->dtype == MRPHY_F64 ? 8 : 4) > 44;
   p->WS = p->stepmajor ? ((p->W + 3) & ~3) : p->W;

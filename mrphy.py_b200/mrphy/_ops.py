@@ -16,6 +16,7 @@ from mrphy import _cabi
 
 _F = (torch.float32, torch.float64)
 K_MAX = 64                  # checkpoint interval cap == staged chunk length (csrc: TCMAX)
+K_MAX1 = 128                # ... of the fp32 single-coil kernels (csrc: MRPHY_TCMAX1)
 TC_K_MAX = 32               # ... of the tensor-core multi-coil kernels (fp32, >= 3 coils with a b1Map; csrc: TC_TCMAX)
 _AMPLIFY_BUDGET = 0.4       # resync before exp(K*dt/T2) exceeds e^0.4 ~ 1.5 (time-reversed states)
 
@@ -890,8 +891,8 @@ def _cached_tmin(T1: Tensor, T2: Tensor) -> float:
     return v
 
 
-def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -> int:
-    """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at K_MAX.
+def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor], kmax: int = K_MAX) -> int:
+    """K such that exp(K*dt/min(T1,T2)) <= e^0.4, capped at `kmax` (K_MAX; K_MAX1 for the fp32 single-coil kernels).
 
     Needs max(dt) and min(T1, T2) on the host.  Both are cached per tensor OBJECT and in-place version (weak references
     guard against id reuse) and SEPARATELY: the spin object keeps its T1/T2 across a design loop, while every iteration
@@ -899,12 +900,12 @@ def pick_ckpt_interval(dt: Tensor, T1: Optional[Tensor], T2: Optional[Tensor]) -
     loop stays free of device->host reads.  MRPHY_B200_CKPT overrides."""
     env = os.environ.get('MRPHY_B200_CKPT')
     if env:
-        return max(1, min(K_MAX, int(env)))
+        return max(1, min(kmax, int(env)))
     if T1 is None:
-        return K_MAX
+        return kmax
     tmin = _cached_tmin(T1, T2)
     r = _cached_max(dt) / tmin if tmin > 0 else float('nan')
-    K = K_MAX if not (r > 0) else int(max(1, min(K_MAX, _AMPLIFY_BUDGET / r)))
+    K = kmax if not (r > 0) else int(max(1, min(kmax, _AMPLIFY_BUDGET / r)))
     if K >= 16:
         K -= K % 16
     return K
@@ -992,7 +993,8 @@ def fused_applypulse(M_: Tensor, rf: Tensor, gr: Tensor, loc_: Tensor, *, Δf_: 
         # a single-coil b1Map with multi-coil rf broadcasts over coils, as upstream (beffective.py:153-165)
         b1 = _inner_contig(b1.expand(N, nM, 2, nC) if tuple(b1.shape) != (N, nM, 2, nC) else b1, 2)
     df, T1, T2, gam, dtt = (move(x) for x in (Δf_, T1_, T2_, γ_, dt))
-    K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2)
+    one_channel = b1 is None or b1.shape[3] == 1
+    K = int(ckpt) if ckpt is not None else pick_ckpt_interval(dtt, T1, T2, K_MAX1 if (dtype == torch.float32 and one_channel) else K_MAX)
     if ckpt is None and dtype == torch.float32 and b1 is not None and b1.shape[3] >= 3:
         K = min(K, TC_K_MAX)                     # the tensor-core kernels stage 32 steps per chunk
     fl = default_flags() if flags is None else flags

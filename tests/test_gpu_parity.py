@@ -268,6 +268,29 @@ def test_tensor_core_forward_is_graph_capturable_and_batched(dev):
         assert torch.equal(rf.grad, want[0]) and torch.equal(gr.grad, want[1])
 
 
+@pytest.mark.parametrize('K', [100, 128])
+def test_single_coil_fp32_chunks_up_to_128_steps(dev, K):
+    """The fp32 single-coil kernels stage up to 128 steps per chunk (checkpoint interval K <= 128; the default picks 128 when the
+    relaxation allows it); every other kernel family stops at 64 and says so."""
+    from oracle import bloch_oracle as orc
+    from mrphy import _ops
+    p = _random_problem(700 + K, 2, 300, 333, 1, has_b1=True, relax=True, dtype=f32)
+    ref = orc.applypulse_fwd_bwd(p['M0'], p['rf'], p['gr'], p['loc'], p['w'], df=p['df'], b1=p['b1'], T1=p['T1'], T2=p['T2'],
+                                 gamma=p['gam'], dt=p['dt'])
+    p32 = {k: v.to(f32) for k, v in p.items()}
+    ref32 = orc.applypulse_fwd_bwd(p32['M0'], p32['rf'], p32['gr'], p32['loc'], p32['w'], df=p32['df'], b1=p32['b1'],
+                                   T1=p32['T1'], T2=p32['T2'], gamma=p32['gam'], dt=p32['dt'], dtype=f32)
+    g = {('in_' + k): v.numpy() for k, v in p.items()}
+    Mo, gM0, grf, ggr = run_fused(g, dev, f32, p['w'].numpy(), ckpt=K)
+    assert mx(Mo, ref['Mo']) < _fp32_bound(ref32['Mo'], ref['Mo'])
+    assert rel(grf, ref['grf']) < RTOL_G32 and rel(ggr, ref['ggr']) < RTOL_G32 and rel(gM0, ref['gM0']) < RTOL_G32
+    Mo64, _, grf64, _ = run_fused(g, dev, f32, p['w'].numpy(), ckpt=64)
+    assert torch.equal(Mo, Mo64) and rel(grf, grf64) < 1e-5          # the forward does not depend on K, the adjoint barely
+    assert _ops.pick_ckpt_interval(T(p['dt'].numpy(), dev, f64), None, None, _ops.K_MAX1) == 128
+    with pytest.raises(RuntimeError, match='checkpoint interval'):
+        run_fused(g, dev, f64, p['w'].numpy(), ckpt=K)               # fp64: 64 at most
+
+
 def test_multi_tile_ctas_accumulate(dev, monkeypatch):
     """Force a 3-CTA grid so every CTA walks several spin tiles (partial-sum read-modify-write path)."""
     from oracle import bloch_oracle as orc
