@@ -522,6 +522,8 @@ def measure(workload, scaling, args, dev, rank, world, flush, full):
     res['units'] = P.units_local * world if scaling == 'weak' else float(P.N) * (P.n ** 3) * P.nT
     res['units_local'] = P.units_local
     res['esz'] = 4 if dtype == torch.float32 else 8
+    # checkpoint interval the kernels ran with: T1 / T2 of the synthetic spins allow the cap of the kernel family
+    res['K'] = _ops.K_MAX1 if dtype == torch.float32 and _ops.trig_policy() != 'strict' else _ops.K_MAX
     del P
     torch.cuda.empty_cache()
     return res
@@ -565,7 +567,7 @@ def run_ours(args):
         ms_f, ms_b = r['k_fwd'], r['k_bwd']
         per_launch = r['units_local']
         ach_tf = per_launch * FLOP_BWD / (ms_b * 1e-3) / 1e12
-        ck_bytes = per_launch / 64 * 3 * r['esz'] + r['N'] * r['nM'] * (3 + 3 + 3 + 2 + 1 + 3) * r['esz']   # bwd: ckpt reads + operands
+        ck_bytes = per_launch / r['K'] * 3 * r['esz'] + r['N'] * r['nM'] * (3 + 3 + 3 + 2 + 1 + 3) * r['esz']   # bwd: ckpt reads + operands
         traffic, traffic_src = None, None
         try:   # dram__bytes_read+write per launch of the same kernel from the committed ncu capture of the same workload
             with open(os.path.join(ROOT, 'profiles', 'r2_ncu_summary.json')) as f:
@@ -594,7 +596,7 @@ def run_ours(args):
             'clocks': clocks,
             'roofline': {'bound': 'fp32_issue', 'kernel': 'fused_bwd_kernel', 'achieved': ach_tf, 'peak': peak_tf,
                          'unit': 'TFLOP/s', 'frac': ach_tf / peak_tf, 'traffic': traffic, 'traffic_unit': 'bytes/launch',
-                         'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': ck_bytes,
+                         'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': ck_bytes, 'checkpoint_interval': r['K'],
                          'peak_source': f'{sms} SMs (device query) x 128 FP32 lanes x 2 x sm_max_mhz ({src} {sm_mhz:.0f} MHz); the path '
                                         'is FP32-issue-bound (SURVEY 8d), not HBM- or tensor-bound',
                          'ms_per_launch': ms_b, 'algorithmic_flop_per_spin_step': FLOP_BWD,
