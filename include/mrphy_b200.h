@@ -69,7 +69,8 @@ typedef struct mrphy_fused_args {
   int32_t flags;  /* mrphy_flags */
   int32_t N, nM, nT;
   int32_t nC;     /* coils of rf; with b1 == NULL the coils are summed (beffective.py:147-151) */
-  int32_t K;      /* checkpoint interval in steps (>= 1)                                       */
+  int32_t K;      /* checkpoint interval in steps: 1..64; fp32 with one transmit channel (nC == 1 or
+                     b1 == NULL): 1..128.  fp32, >= 3 coils, K <= 32: the forward runs its tensor-core kernel */
   int32_t _pad;
 
   const void* Mi; int64_t Mi_sn, Mi_sm;   /* (N,nM,3), inner stride 1                          */
