@@ -16,7 +16,7 @@ from torch import Tensor
 
 from mrphy import mobjs
 
-__all__ = ['shard_range', 'shard_spins', 'allreduce_waveform_grads', 'flat_wave_grads']
+__all__ = ['shard_range', 'shard_spins', 'shard_batch', 'allreduce_waveform_grads', 'flat_wave_grads']
 
 
 def shard_range(nM: int, rank: int, world: int) -> Tuple[int, int]:
@@ -44,6 +44,37 @@ def shard_spins(obj, rank: int, world: int, *, loc_: Optional[Tensor] = None, Δ
     local = mobjs.SpinArray((sp.shape[0], hi - lo), T1_=cut(sp.T1_), T2_=cut(sp.T2_), γ_=cut(sp.γ_),
                             M_=cut(sp.M_).contiguous(), device=device, dtype=sp.dtype)
     return local, {'loc_': cut(loc_).contiguous(), 'Δf_': cut(Δf_), 'b1Map_': cut(b1Map_)}
+
+
+def shard_batch(obj, pulse, rank: int, world: int, *, loc_: Optional[Tensor] = None, Δf_: Optional[Tensor] = None,
+                b1Map_: Optional[Tensor] = None, device: Optional[torch.device] = None):
+    """The batch axis ``N`` as the shard axis (the second natural one: N different pulses on N copies of the spins, e.g. 64
+    candidate pulses): rank ``rank`` gets the entries ``[lo, hi)`` of the spins AND of the pulse.  Every entry's ``rf.grad`` /
+    ``gr.grad`` is complete on the rank that owns it, so this split needs NO collective at all.
+
+    Returns ``(spinarray, kw, pulse_local, (lo, hi))``; quantities with a broadcast batch dimension (size 1) are shared.
+    The local pulse holds views ``pulse.rf[lo:hi]``, ``pulse.gr[lo:hi]``: gradients reach the caller's leaves through them.
+    """
+    sp = obj.spinarray if isinstance(obj, mobjs.SpinCube) else obj
+    N = sp.shape[0]
+    assert pulse.rf.shape[0] == N, 'pulse and spins disagree on the batch size'
+    lo, hi = shard_range(N, rank, world)
+    device = sp.device if device is None else device
+    if isinstance(obj, mobjs.SpinCube):
+        loc_ = obj.loc_ if loc_ is None else loc_
+        Δf_ = obj.Δf_ if Δf_ is None else Δf_
+    assert loc_ is not None, 'a SpinArray has no geometry: pass loc_'
+
+    def cut(x):
+        if x is None or not isinstance(x, Tensor):
+            return x
+        return (x[lo:hi] if (x.ndim >= 1 and x.shape[0] == N and N > 1) else x).to(device)
+
+    local = mobjs.SpinArray((hi - lo, sp.nM), T1_=cut(sp.T1_), T2_=cut(sp.T2_), γ_=cut(sp.γ_), M_=cut(sp.M_).contiguous(),
+                            device=device, dtype=sp.dtype)
+    p_local = mobjs.Pulse(rf=cut(pulse.rf), gr=cut(pulse.gr), dt=cut(pulse.dt), gmax=cut(pulse.gmax), smax=cut(pulse.smax),
+                          rfmax=cut(pulse.rfmax), desc=pulse.desc, device=device, dtype=pulse.dtype)
+    return local, {'loc_': cut(loc_).contiguous(), 'Δf_': cut(Δf_), 'b1Map_': cut(b1Map_)}, p_local, (lo, hi)
 
 
 def flat_wave_grads(rf: Tensor, gr: Tensor) -> Optional[Tensor]:

@@ -291,6 +291,34 @@ def test_single_coil_fp32_chunks_up_to_128_steps(dev, K):
         run_fused(g, dev, f64, p['w'].numpy(), ckpt=K)               # fp64: 64 at most
 
 
+def test_batch_sharding_needs_no_collective(dev):
+    """mrphy.parallel.shard_batch: the batch axis as the shard axis.  Both "ranks" of a world of 2, run one after the
+    other on this GPU, together reproduce the unsharded magnetisation and -- through the views of the caller's leaves -- its
+    rf / gr gradients bit for bit, with no all-reduce."""
+    from mrphy import mobjs, parallel
+    kw = {'dtype': f32, 'device': dev}
+    gen = torch.Generator().manual_seed(12)
+    N, n, nT = 4, 6, 50
+    cube = mobjs.SpinCube((N, n, n, n), tensor([[24., 24., 24.]]), **kw)
+    cube.Δf = (torch.rand(N, n, n, n, generator=gen) * 200 - 100).to(dev)
+    b1 = (torch.rand(N, n ** 3, 2, generator=gen) * 0.2 + tensor([0.9, -0.1])).to(dev)
+    rf0, gr0 = (torch.rand(N, 2, nT, generator=gen) * 0.2 - 0.1).to(dev), (torch.rand(N, 3, nT, generator=gen) * 4 - 2).to(dev)
+    w = (torch.rand(N, n ** 3, 3, generator=gen) * 2 - 1).to(dev)
+    pulse = mobjs.Pulse(rf=rf0.clone().requires_grad_(True), gr=gr0.clone().requires_grad_(True), **kw)
+    M = cube.applypulse(pulse, b1Map_=b1)
+    (M * w).sum().backward()
+    want = (M.detach().clone(), pulse.rf.grad.clone(), pulse.gr.grad.clone())
+    pulse2 = mobjs.Pulse(rf=rf0.clone().requires_grad_(True), gr=gr0.clone().requires_grad_(True), **kw)
+    outs = []
+    for rank in range(2):
+        sp, kws, pl, (lo, hi) = parallel.shard_batch(cube, pulse2, rank, 2, b1Map_=b1)
+        Ml = sp.applypulse(pl, **kws)
+        (Ml * w[lo:hi]).sum().backward()
+        outs.append(Ml.detach())
+    assert torch.equal(torch.cat(outs), want[0])
+    assert torch.equal(pulse2.rf.grad, want[1]) and torch.equal(pulse2.gr.grad, want[2])
+
+
 def test_multi_tile_ctas_accumulate(dev, monkeypatch):
     """Force a 3-CTA grid so every CTA walks several spin tiles (partial-sum read-modify-write path)."""
     from oracle import bloch_oracle as orc

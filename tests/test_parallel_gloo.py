@@ -43,6 +43,14 @@ def _worker(rank, world, port, ret):
         tot = sum(r + 1 for r in range(world))
         ok &= bool((rf.grad == tot).all()) and torch.equal(gr.grad, torch.arange(42.).reshape(2, 3, 7).double() * tot)
         ok &= float(loss) == 10.0 * tot
+        # the batch axis as the shard axis: entries [lo, hi) of spins and pulse, shared (size-1) quantities untouched
+        pulse = mobjs.Pulse(rf=torch.rand((2, 2, 7), generator=g, dtype=torch.float64), gr=torch.rand((2, 3, 7), generator=g,
+                            dtype=torch.float64), dt=torch.tensor([4e-6, 8e-6], dtype=torch.float64), dtype=torch.float64)
+        spb, kwb, pb, (blo, bhi) = parallel.shard_batch(cube, pulse, rank, world, b1Map_=b1)
+        ok &= (blo, bhi) == parallel.shard_range(2, rank, world) and spb.shape == (bhi - blo, 60)
+        ok &= torch.equal(pb.rf, pulse.rf[blo:bhi]) and torch.equal(pb.gr, pulse.gr[blo:bhi]) and torch.equal(pb.dt, pulse.dt[blo:bhi])
+        ok &= torch.equal(kwb['loc_'], cube.loc_[blo:bhi]) and torch.equal(kwb['Δf_'], cube.Δf_[blo:bhi])
+        ok &= torch.equal(kwb['b1Map_'], b1[blo:bhi]) and torch.equal(spb.T1_, cube.T1_[blo:bhi]) and torch.equal(spb.M_, cube.M_[blo:bhi])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
