@@ -81,6 +81,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   tmem_ld_wait(v);
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T: A read from TMEM -- row i of A = lane i, its K values in consecutive 32-bit columns
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// 8 consecutive columns of this thread's TMEM lane <- registers (warp-collective); tmem_st_wait before anything reads them
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // x = hi + mid + lo exactly, every part representable in TF32 (11-bit significand): products of parts are exact in the
 // tensor core, so the six products hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi reproduce x*y to 2^-33.
 __device__ __forceinline__ float tf32_rn(float x) {

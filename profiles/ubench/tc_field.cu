@@ -118,6 +118,92 @@ int run(int nprod) {
   return 0;
 }
 
+// The field product with A in TMEM (thread t stores its own row with tcgen05.st: no shared memory for A), two parts, 3 products.
+template <int K, int N>
+__global__ void __launch_bounds__(128) tc_field_ts_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+  constexpr int KC = K / 4;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  float (*sb)[KC][N][4] = reinterpret_cast<float (*)[KC][N][4]>(dyn);     // [2 parts][KC][N][4]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int COLS = (N + 2 * K) <= 128 ? 128 : 256;                    // D: N columns, then A hi (K), A mid (K)
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc<COLS>(&tmem_slot);
+  for (int i = tid; i < N * K; i += 128) {
+    const int n = i / K, e = i % K;
+    const float h = tc::tf32_rn(B[i]), m = tc::tf32_rn(B[i] - h);
+    sb[0][e / 4][n][e % 4] = h; sb[1][e / 4][n][e % 4] = m;
+  }
+  fence_proxy_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot, tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int e0 = 0; e0 < K; e0 += 8) {          // this thread's row of A, both parts, 8 columns at a time
+    float h[8], m[8];
+    for (int e = 0; e < 8; ++e) { const float x = A[tid * K + e0 + e]; h[e] = tc::tf32_rn(x); m[e] = tc::tf32_rn(x - h[e]); }
+    tc::tmem_st8(tlane + N + e0, h);
+    tc::tmem_st8(tlane + N + K + e0, m);
+  }
+  tc::tmem_st_wait();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (tid == 0) {
+    constexpr uint32_t idesc = tc::idesc_tf32(128, N);
+    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+    bool acc = false;
+    for (int q = 0; q < 3; ++q)
+      for (int ks = 0; ks < K / 8; ++ks) {
+        tc::mma_tf32_ts(tmem, tmem + N + pa[q] * K + 8 * ks, tc::kmajor_desc(&sb[pb[q]][2 * ks][0][0], N), idesc, acc);
+        acc = true;
+      }
+    tc::commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  float acc16[16];
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    tc::tmem_ld16(tlane + c0, acc16);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)tid * N + c0 + i] = acc16[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free<COLS>(tmem);
+}
+
+template <int K, int N>
+int run_ts() {
+  std::vector<float> A(128 * K), B(N * K), D(128 * N);
+  srand(1);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2 - 1;
+  for (auto& x : B) x = ((float)rand() / RAND_MAX * 2 - 1) * 0.1f;
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  const size_t smem = sizeof(float) * 2 * (K / 4) * N * 4;
+  cudaFuncSetAttribute(tc_field_ts_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_field_ts_kernel<K, N><<<1, 128, smem>>>(dA, dB, dD);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("A in TMEM K=%d N=%d: CUDA error %s\n", K, N, cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0, err32 = 0;
+  for (int s = 0; s < 128; ++s)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0; float f = 0.f;
+      for (int k = 0; k < K; ++k) { ref += (double)A[s * K + k] * (double)B[n * K + k]; f = fmaf(A[s * K + k], B[n * K + k], f); }
+      maxerr = fmax(maxerr, fabs(ref - (double)D[s * N + n]));
+      err32 = fmax(err32, fabs(ref - (double)f));
+    }
+  printf("field product with A in TMEM (tcgen05.st rows, 2 parts, 3 products), K=%d N=%d: max|D - fp64| = %.3e (fp32 FMA chain: %.3e) -> %s\n",
+         K, N, maxerr, err32, maxerr < 4 * err32 + 1e-7 ? "OK" : "WRONG");
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return maxerr < 4 * err32 + 1e-7 ? 0 : 1;
+}
+
 // The spin reduction of the adjoint as a product (not shipped): D2[e][n] = sum_s Wt[s][e] * F[n][s], K = 128 spins.
 // B2 = F^T K-major (tile[chunk s/4][row n][4]).  A2 = the weights, either re-laid out spin-minor (K-major, amn = 0: works) or as the
 // MN-MAJOR view of the tile the field product reads (tile[chunk e/4][spin][4], amn = 1): an unswizzled MN-major TF32 descriptor
@@ -207,6 +293,9 @@ int main() {
   rc |= run<32, 128>(6);
   rc |= run<16, 64>(6);
   rc |= run<32, 64>(6);
+  rc |= run_ts<16, 64>();
+  rc |= run_ts<32, 64>();
+  rc |= run_ts<8, 16>();
   rc |= run_reduce<64>(0, 0, 0, 0);          // control: weights re-laid out spin-minor (K-major A)
   run_reduce<64>(128, 2048, 128, 1);         // the field product's tile read MN-major, unswizzled: all zeros on B200 (TF32 MN-major
   run_reduce<64>(2048, 128, 128, 1);         // operands exist only in the 128B_BASE32B swizzled layout); either LBO/SBO assignment
